@@ -1,0 +1,350 @@
+/*
+ * ptrs_b200.h — C ABI of the B200-native rendering hot path for pathtracer-rs.
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer today: its path
+ * integrator is called in-process as
+ *     PathIntegrator::new(log, sampler_builder, max_depth, progress)   src/pathtracer/integrator.rs:230
+ *     PathIntegrator::preprocess(&RenderScene)                         src/pathtracer/integrator.rs:250
+ *     PathIntegrator::render(&self, &Camera, &RenderScene)             src/pathtracer/integrator.rs:536
+ *     RenderScene::{intersect, intersect_p, world_bound}               src/pathtracer/mod.rs:92-102
+ *     Film::{clear, get_sample_bounds, to_rgba_image, ...}             src/common/film.rs:164-271
+ * and its own (stub) GPU hook sits at OptixAccelerator::new(&RenderScene)/intersect()
+ * (src/pathtracer/gpu/optix.rs:160,292).  The entry points below are what a Rust `extern "C"` block
+ * built from build.rs (build.rs:14-36 is where the reference shells out to nvcc) would bind; the
+ * binding stub is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, POD structs, explicit sizes; no exceptions or aborts cross the boundary
+ *   - every call returns int32_t: PTRS_OK (0) or a negative PtrsStatus; ptrs_last_error() gives a
+ *     thread-local message for the last failing call
+ *   - host pointers unless the name says `_device`; `stream` is a cudaStream_t passed as void*
+ *     (NULL = the legacy default stream)
+ *   - a scene handle owns device copies of everything in the PtrsSceneDesc (the caller may free its
+ *     buffers as soon as ptrs_scene_create returns); a handle is not re-entrant
+ *   - there is no CPU fallback: with no usable CUDA device every call fails with PTRS_ERR_CUDA
+ */
+#ifndef PTRS_B200_H
+#define PTRS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTRS_ABI_VERSION 1
+
+typedef enum PtrsStatus {
+  PTRS_OK = 0,
+  PTRS_ERR_INVALID_ARGUMENT = -1,
+  PTRS_ERR_CUDA = -2,
+  PTRS_ERR_UNSUPPORTED = -3,
+  PTRS_ERR_OUT_OF_MEMORY = -4
+} PtrsStatus;
+
+/* ------------------------------------------------------------------------------------------------
+ * Accelerator records
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Ray {o, d, t_max}: src/common/ray.rs:2-6 (28 bytes). */
+typedef struct PtrsRay {
+  float o[3];
+  float d[3];
+  float t_max;
+} PtrsRay;
+
+/* What the integrator keeps of a closest hit: the primitive (index into the BVH-ordered primitive
+ * array, -1 = miss), the parametric distance and the barycentrics of Triangle::intersect
+ * (src/pathtracer/shape.rs:156-161).  Everything else in SurfaceMediumInteraction is a pure
+ * function of these and the ray. */
+typedef struct PtrsHit {
+  int32_t prim;
+  float t;
+  float b0, b1, b2;
+} PtrsHit;
+
+/* LinearBVHNode, #[repr(C, align(32))]: src/pathtracer/accelerator.rs:83-95.
+ * offset = primitives_offset for a leaf (n_prims > 0) / second_child_offset for an interior node;
+ * the first child of an interior node is the next node in the array. */
+typedef struct PtrsBvhNode {
+  float bounds_min[3];
+  float bounds_max[3];
+  uint32_t offset;
+  uint16_t n_prims;
+  uint8_t axis;
+  uint8_t pad;
+} PtrsBvhNode;
+
+/* ------------------------------------------------------------------------------------------------
+ * Scene description (what RenderScene holds after the importers ran, flattened)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* TriangleMesh attribute presence: src/pathtracer/shape.rs:581-589 (`normal`, `s`, `uv` may be
+ * empty Vecs; `alpha_mask` is an Option). */
+enum {
+  PTRS_MESH_HAS_NORMAL = 1,
+  PTRS_MESH_HAS_TANGENT = 2,
+  PTRS_MESH_HAS_UV = 4
+};
+
+typedef struct PtrsMesh {
+  uint32_t flags;
+  int32_t alpha_tex; /* float texture id or -1 (shape.rs:228-244, 471-521) */
+} PtrsMesh;
+
+/* Texture<T>: src/pathtracer/texture.rs.  `channels` is 1 for f32 and 3 for Spectrum / Vector3. */
+typedef enum PtrsTextureType {
+  PTRS_TEX_CONSTANT = 0, /* texture.rs:15-29   value = v1 */
+  PTRS_TEX_CHECKER = 1,  /* texture.rs:56-89   v1, v2, UVMap */
+  PTRS_TEX_IMAGE = 2     /* texture.rs:91-192  MIPMap + UVMap */
+} PtrsTextureType;
+
+typedef enum PtrsWrapMode { /* src/common/mod.rs:64-69 */
+  PTRS_WRAP_REPEAT = 0,
+  PTRS_WRAP_BLACK = 1,
+  PTRS_WRAP_CLAMP = 2
+} PtrsWrapMode;
+
+typedef struct PtrsTexture {
+  int32_t type;
+  int32_t channels;
+  float v1[3];
+  float v2[3];
+  float su, sv, du, dv; /* UVMap: texture.rs:31-54 */
+  int32_t mip;          /* index into mipmaps, -1 if none */
+  int32_t pad;
+} PtrsTexture;
+
+/* MIPMap pyramid as built by MIPMap::new (texture.rs:279-405), already resampled to powers of two
+ * and box-filtered by the host.  Level l is `height[l]` rows of `width[l]` texels of `channels`
+ * floats, row-major, starting at texels[level_offset[l]] (offset counted in floats). */
+#define PTRS_MAX_MIP_LEVELS 16
+typedef struct PtrsMipMap {
+  int32_t channels;
+  int32_t wrap;
+  int32_t n_levels;
+  int32_t width[PTRS_MAX_MIP_LEVELS];
+  int32_t height[PTRS_MAX_MIP_LEVELS];
+  uint64_t level_offset[PTRS_MAX_MIP_LEVELS];
+} PtrsMipMap;
+
+/* Material enum: src/pathtracer/material/mod.rs:28-37.  tex[] meaning by type:
+ *   MATTE      kd                                            (mod.rs:155-167)
+ *   MIRROR     -                                             (mod.rs:180-195)
+ *   GLASS      kr, kt, index                                 (mod.rs:216-255)
+ *   METAL      eta, k, r, u_roughness, v_roughness           (metal.rs:49-93)
+ *   SUBSTRATE  kd, ks, nu, nv                                (substrate.rs:42-68)
+ *   DISNEY     color, metallic, eta, roughness               (disney.rs:172-263)
+ * normal_map >= 0 wraps the material in Material::Normal (mod.rs:39-79, 130-135). */
+typedef enum PtrsMaterialType {
+  PTRS_MAT_MATTE = 0,
+  PTRS_MAT_MIRROR = 1,
+  PTRS_MAT_GLASS = 2,
+  PTRS_MAT_METAL = 3,
+  PTRS_MAT_SUBSTRATE = 4,
+  PTRS_MAT_DISNEY = 5,
+  PTRS_MAT_COUNT = 6
+} PtrsMaterialType;
+
+typedef struct PtrsMaterial {
+  int32_t type;
+  int32_t normal_map;      /* Vector3 texture id or -1 */
+  int32_t tex[5];
+  int32_t remap_roughness; /* metal.rs:75-78, substrate.rs:56-59 */
+} PtrsMaterial;
+
+/* Lights: src/pathtracer/light.rs. */
+typedef enum PtrsLightType {
+  PTRS_LIGHT_POINT = 0,       /* light.rs:86-150   pos = p_light, color = I */
+  PTRS_LIGHT_DIRECTIONAL = 1, /* light.rs:152-229  pos = w_light (normalised), color = L */
+  PTRS_LIGHT_AREA = 2,        /* light.rs:231-319  one per emissive triangle; prim, ke_tex, area */
+  PTRS_LIGHT_INFINITE = 3     /* light.rs:321-503  env */
+} PtrsLightType;
+
+typedef struct PtrsLight {
+  int32_t type;
+  int32_t prim;   /* AREA: index into the BVH-ordered primitive array */
+  int32_t ke_tex; /* AREA: Spectrum texture id (emission map) */
+  int32_t env;    /* INFINITE: index into envs */
+  float pos[3];
+  float color[3];
+  float area;            /* AREA: Triangle::area(), shape.rs:533-539 */
+  float world_radius;    /* DIRECTIONAL / INFINITE: Light::preprocess, bounds.rs:126-134 */
+  float world_center[3];
+  float pad;
+} PtrsLight;
+
+/* InfiniteAreaLight state: light.rs:321-399.  The Distribution2D (sampling.rs:185-230) is passed
+ * exactly as the reference builds it: nv conditional rows of nu entries. */
+typedef struct PtrsEnvLight {
+  float light_to_world[16]; /* row-major 4x4, Projective3 */
+  float world_to_light[16];
+  int32_t mip;              /* Spectrum MIPMap id (WrapMode::Repeat) */
+  int32_t nu, nv;
+  int32_t pad;
+  const float* cond_func;     /* nv * nu        */
+  const float* cond_cdf;      /* nv * (nu + 1)  */
+  const float* cond_func_int; /* nv             */
+  const float* marg_func;     /* nv  (== cond_func_int) */
+  const float* marg_cdf;      /* nv + 1         */
+  float marg_func_int;
+  float pad2;
+} PtrsEnvLight;
+
+typedef struct PtrsSceneDesc {
+  uint32_t abi_version; /* PTRS_ABI_VERSION */
+
+  /* accelerator: BVH::nodes / BVH::primitives (accelerator.rs:97-100) in the reference's order */
+  uint32_t n_nodes;
+  const PtrsBvhNode* nodes;
+  uint32_t n_prims;
+  const uint32_t* prim_vertex; /* 3 * n_prims global vertex indices (Triangle::indices + mesh base) */
+  const int32_t* prim_mesh;    /* n_prims */
+  const int32_t* prim_material;
+  const int32_t* prim_area_light; /* light id or -1 (GeometricPrimitive::area_light) */
+
+  /* vertex pools; normal / tangent / uv may be NULL when no mesh uses them */
+  uint32_t n_verts;
+  const float* pos;     /* 3 * n_verts, world space (shape.rs:602-604) */
+  const float* normal;  /* 3 * n_verts */
+  const float* tangent; /* 3 * n_verts (TriangleMesh::s) */
+  const float* uv;      /* 2 * n_verts */
+
+  uint32_t n_meshes;
+  const PtrsMesh* meshes;
+  uint32_t n_materials;
+  const PtrsMaterial* materials;
+  uint32_t n_textures;
+  const PtrsTexture* textures;
+  uint32_t n_mipmaps;
+  const PtrsMipMap* mipmaps;
+  uint64_t n_texels; /* floats */
+  const float* texels;
+
+  /* RenderScene::lights / infinite_lights (src/pathtracer/mod.rs:84-89) */
+  uint32_t n_lights;
+  const PtrsLight* lights;
+  uint32_t n_infinite_lights;
+  const int32_t* infinite_lights; /* light ids */
+  uint32_t n_envs;
+  const PtrsEnvLight* envs;
+} PtrsSceneDesc;
+
+/* ------------------------------------------------------------------------------------------------
+ * Camera, sampler and integrator settings
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Camera: src/common/mod.rs:19-62.  The host builds it (Camera::new); the fields are the ones
+ * generate_ray_differential reads (src/pathtracer/mod.rs:59-81). */
+typedef struct PtrsCamera {
+  float rot[4];   /* cam_to_world rotation, unit quaternion (i, j, k, w) */
+  float trans[3]; /* cam_to_world translation */
+  float pad0;
+  float raster_to_screen[16]; /* row-major Affine3 */
+  float persp[4];             /* Perspective3 m00, m11, m22, m23 */
+  float dx_camera[3];
+  float dy_camera[3];
+  int32_t width, height; /* film resolution */
+} PtrsCamera;
+
+#define PTRS_FILTER_TABLE_WIDTH 16 /* src/common/film.rs:121 */
+
+/* PathIntegrator fields (integrator.rs:219-246), SobolSamplerBuilder (sampler/sobol.rs:35-62) and
+ * the film filter (film.rs:132-163, filter.rs:61-89).  Defaults = ptrs_render_params_default(). */
+typedef struct PtrsRenderParams {
+  int32_t spp;       /* samples per pixel as given; rounded up to a power of two like sobol.rs:37 */
+  int32_t max_depth; /* main.rs default 15 */
+  float rr_threshold; /* 1.0 */
+  int32_t rr_start_depth; /* 3 */
+  int32_t rr_enable;      /* 1 */
+  /* sharding (not in the reference): render Sobol sample numbers s with
+   * sample_begin <= s < sample_end and (s % sample_stride) == sample_phase */
+  int32_t sample_begin, sample_end; /* end <= 0 means "all spp" */
+  int32_t sample_stride, sample_phase; /* 1, 0 */
+  float filter_radius[2];                                                 /* 2, 2 */
+  float filter_table[PTRS_FILTER_TABLE_WIDTH * PTRS_FILTER_TABLE_WIDTH]; /* film.rs:135-144 */
+  int32_t paths_per_batch; /* 0 = library default; wavefront batch size */
+  int32_t flags;           /* reserved, 0 */
+} PtrsRenderParams;
+
+/* Counters of the last render on a scene handle. */
+typedef struct PtrsStats {
+  uint64_t camera_paths;
+  uint64_t extension_rays; /* closest-hit rays of the main path (integrator.rs:416) */
+  uint64_t shadow_rays;    /* any-hit rays (light.rs:39-41) */
+  uint64_t mis_rays;       /* closest-hit rays of estimate_direct's BSDF sample (integrator.rs:119) */
+  uint64_t nodes_tested;   /* only filled by the *_counted entry points / PTRS stats passes */
+  uint64_t tris_tested;
+  float ms_generate, ms_extend, ms_shade, ms_shadow, ms_accumulate, ms_total;
+  uint32_t launches; /* kernels launched by the last call */
+  uint32_t batches;
+} PtrsStats;
+
+typedef struct PtrsScene PtrsScene; /* opaque */
+typedef struct PtrsFilm PtrsFilm;   /* opaque: W x H x (r, g, b, weight) f32 on the device */
+
+/* ------------------------------------------------------------------------------------------------
+ * Entry points
+ * ---------------------------------------------------------------------------------------------- */
+
+/* library / device */
+int32_t ptrs_abi_version(void);
+const char* ptrs_last_error(void);
+int32_t ptrs_device_count(int32_t* count);
+int32_t ptrs_set_device(int32_t device); /* device used by handles created afterwards on this thread */
+
+/* RenderScene construction / teardown (replaces holding Box<BVH> + lights in RenderScene) */
+int32_t ptrs_scene_create(const PtrsSceneDesc* desc, PtrsScene** out);
+int32_t ptrs_scene_destroy(PtrsScene* scene);
+int32_t ptrs_scene_world_bound(const PtrsScene* scene, float out_min_max[6]); /* mod.rs:100-102 */
+uint64_t ptrs_scene_device_bytes(const PtrsScene* scene);
+
+/* RenderScene::intersect / intersect_p over a batch (mod.rs:92-98; accelerator.rs:359-475).
+ * Host-buffer forms copy in and out; *_device forms take device pointers and only enqueue. */
+int32_t ptrs_intersect(PtrsScene* scene, const PtrsRay* rays, size_t n, PtrsHit* hits);
+int32_t ptrs_intersect_p(PtrsScene* scene, const PtrsRay* rays, size_t n, uint8_t* occluded);
+int32_t ptrs_intersect_device(PtrsScene* scene, const PtrsRay* d_rays, size_t n, PtrsHit* d_hits,
+                              void* stream);
+int32_t ptrs_intersect_p_device(PtrsScene* scene, const PtrsRay* d_rays, size_t n,
+                                uint8_t* d_occluded, void* stream);
+/* same traversal with node / triangle test counters (roofline bookkeeping) */
+int32_t ptrs_intersect_counted_device(PtrsScene* scene, const PtrsRay* d_rays, size_t n,
+                                      PtrsHit* d_hits, int32_t any_hit, uint8_t* d_occluded,
+                                      uint64_t* nodes_tested, uint64_t* tris_tested, void* stream);
+
+/* Film (film.rs) */
+int32_t ptrs_film_create(int32_t width, int32_t height, PtrsFilm** out);
+int32_t ptrs_film_wrap_device(int32_t width, int32_t height, float* d_rgbw, PtrsFilm** out);
+int32_t ptrs_film_destroy(PtrsFilm* film);
+int32_t ptrs_film_clear(PtrsFilm* film, void* stream);                    /* film.rs:164-172 */
+int32_t ptrs_film_download(PtrsFilm* film, float* rgbw /* W*H*4 */);       /* raw sums */
+int32_t ptrs_film_resolve(PtrsFilm* film, float* rgb /* W*H*3 */);         /* film.rs:253-271 */
+int32_t ptrs_film_resolve_srgb8(PtrsFilm* film, uint8_t* rgba /* W*H*4 */); /* film.rs:230-251 */
+float* ptrs_film_device_ptr(PtrsFilm* film);
+int32_t ptrs_film_sample_bounds(int32_t width, int32_t height, const float filter_radius[2],
+                                int32_t out_min_max[4]); /* film.rs:174-185 */
+
+/* PathIntegrator */
+int32_t ptrs_render_params_default(PtrsRenderParams* params); /* integrator.rs:237-245 + Gaussian */
+int32_t ptrs_render(PtrsScene* scene, const PtrsCamera* camera, const PtrsRenderParams* params,
+                    PtrsFilm* film, void* stream); /* integrator.rs:536; accumulates into film */
+int32_t ptrs_stats(const PtrsScene* scene, PtrsStats* out);
+int32_t ptrs_set_stats_mode(PtrsScene* scene, int32_t count_visits); /* counted traversal in render */
+
+/* Parity probes: single stages of the path, for bit-level checks against the oracle. */
+/* SobolSampler::{start_pixel, get_index_for_sample, sample_dimension} (sampler/sobol.rs:81-193):
+ * out[i * n_dims + k] = sample_dimension(index(pixels[i], sample_nums[i]), dims[k]) */
+int32_t ptrs_sobol_samples(const PtrsCamera* camera, const PtrsRenderParams* params,
+                           const int32_t* pixels_xy, const int32_t* sample_nums, size_t n,
+                           const int32_t* dims, size_t n_dims, float* out, uint64_t* out_index);
+/* camera sample + Camera::generate_ray_differential + scale_differentials (mod.rs:59-81,
+ * ray.rs:30-35): rays[i], p_film[2i..], rx/ry directions [6i..] */
+int32_t ptrs_generate_rays(const PtrsCamera* camera, const PtrsRenderParams* params,
+                           const int32_t* pixels_xy, const int32_t* sample_nums, size_t n,
+                           PtrsRay* rays, float* p_film, float* rxry_dir);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTRS_B200_H */

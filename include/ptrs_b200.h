@@ -329,6 +329,10 @@ int32_t ptrs_film_sample_bounds(int32_t width, int32_t height, const float filte
 int32_t ptrs_render_params_default(PtrsRenderParams* params); /* integrator.rs:237-245 + Gaussian */
 int32_t ptrs_render(PtrsScene* scene, const PtrsCamera* camera, const PtrsRenderParams* params,
                     PtrsFilm* film, void* stream); /* integrator.rs:536; accumulates into film */
+/* li() of integrator.rs:579 for chosen (pixel, sample number) pairs: out_rgb[3 i ..] = radiance of that
+ * camera path.  Same kernels as ptrs_render with the film splat left out; parity probe. */
+int32_t ptrs_path_radiance(PtrsScene* scene, const PtrsCamera* camera, const PtrsRenderParams* params,
+                           const int32_t* pixels_xy, const int32_t* sample_nums, size_t n, float* out_rgb);
 int32_t ptrs_stats(const PtrsScene* scene, PtrsStats* out);
 int32_t ptrs_set_stats_mode(PtrsScene* scene, int32_t count_visits); /* counted traversal in render */
 

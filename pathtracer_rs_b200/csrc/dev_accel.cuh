@@ -1,0 +1,239 @@
+// BVH traversal and watertight ray/triangle intersection on the device.
+//   Bounds3::intersect_p_precomp   src/common/bounds.rs:190-232
+//   Triangle::intersect(_p)        src/pathtracer/shape.rs:74-185, 362-524
+//   BVH::intersect / intersect_p   src/pathtracer/accelerator.rs:359-475
+// The visit order (near child first by dir_is_neg[axis], 64-entry stack, triangles of a leaf in
+// array order, current t_max used for every later box test) is the reference's, so ties at equal t
+// resolve to the same primitive and node / triangle test counts equal the CPU path's.
+#pragma once
+#include "dev_texture.cuh"
+
+namespace ptrs {
+
+struct RayPre {  // per-ray constants of the triangle test (shape.rs:94-110)
+  int kx, ky, kz;
+  float sx, sy, sz;
+};
+PT_DEV float pick(V3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+
+PT_DEV RayPre ray_precompute(V3 d) {
+  RayPre p;
+  p.kz = max_dimension(vabs(d));
+  p.kx = p.kz + 1;
+  if (p.kx == 3) p.kx = 0;
+  p.ky = p.kx + 1;
+  if (p.ky == 3) p.ky = 0;
+  float dx = pick(d, p.kx), dy = pick(d, p.ky), dz = pick(d, p.kz);
+  p.sx = -dx / dz;
+  p.sy = -dy / dz;
+  p.sz = 1.0f / dz;
+  return p;
+}
+
+// shape.rs:85-185.  Returns true and (t, b0, b1, b2) if the triangle is hit within (0, t_max].
+PT_DEV bool tri_core(V3 p0, V3 p1, V3 p2, V3 o, const RayPre& rp, float t_max, float* t_out, float* b0o, float* b1o, float* b2o) {
+  V3 q0 = p0 - o, q1 = p1 - o, q2 = p2 - o;
+  float p0x = pick(q0, rp.kx), p0y = pick(q0, rp.ky), p0z = pick(q0, rp.kz);
+  float p1x = pick(q1, rp.kx), p1y = pick(q1, rp.ky), p1z = pick(q1, rp.kz);
+  float p2x = pick(q2, rp.kx), p2y = pick(q2, rp.ky), p2z = pick(q2, rp.kz);
+  p0x += rp.sx * p0z;
+  p0y += rp.sy * p0z;
+  p1x += rp.sx * p1z;
+  p1y += rp.sy * p1z;
+  p2x += rp.sx * p2z;
+  p2y += rp.sy * p2z;
+  float e0 = p1x * p2y - p1y * p2x;
+  float e1 = p2x * p0y - p2y * p0x;
+  float e2 = p0x * p1y - p0y * p1x;
+  if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {
+    double p2txp1ty = (double)p2x * (double)p1y, p2typ1tx = (double)p2y * (double)p1x;
+    e0 = (float)(p2typ1tx - p2txp1ty);
+    double p0txp2ty = (double)p0x * (double)p2y, p0typ2tx = (double)p0y * (double)p2x;
+    e1 = (float)(p0typ2tx - p0txp2ty);
+    double p1txp0ty = (double)p1x * (double)p0y, p1typ0tx = (double)p1y * (double)p0x;
+    e2 = (float)(p1typ0tx - p1txp0ty);
+  }
+  if ((e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f)) return false;
+  float det = e0 + e1 + e2;
+  if (det == 0.0f) return false;
+  p0z *= rp.sz;
+  p1z *= rp.sz;
+  p2z *= rp.sz;
+  float t_scaled = e0 * p0z + e1 * p1z + e2 * p2z;
+  if (det < 0.0f && (t_scaled >= 0.0f || t_scaled < t_max * det)) return false;
+  else if (det > 0.0f && (t_scaled <= 0.0f || t_scaled > t_max * det)) return false;
+  float inv_det = 1.0f / det;
+  float b0 = e0 * inv_det, b1 = e1 * inv_det, b2 = e2 * inv_det;
+  float t = t_scaled * inv_det;
+  float max_z_t = fmaxf(fmaxf(fabsf(p0z), fabsf(p1z)), fabsf(p2z));
+  float delta_z = gamma_n(3) * max_z_t;
+  float max_x_t = fmaxf(fmaxf(fabsf(p0x), fabsf(p1x)), fabsf(p2x));
+  float max_y_t = fmaxf(fmaxf(fabsf(p0y), fabsf(p1y)), fabsf(p2y));
+  float delta_x = gamma_n(5) * (max_x_t + max_z_t);
+  float delta_y = gamma_n(5) * (max_y_t + max_z_t);
+  float delta_e = 2.0f * (gamma_n(2) * max_x_t * max_y_t + delta_y * max_x_t + delta_x * max_y_t);
+  float max_e = fmaxf(fmaxf(fabsf(e0), fabsf(e1)), fabsf(e2));
+  float delta_t = 3.0f * (gamma_n(3) * max_e * max_z_t + delta_e * max_z_t + delta_z * max_e) * fabsf(inv_det);
+  if (t <= delta_t) return false;
+  *t_out = t;
+  *b0o = b0;
+  *b1o = b1;
+  *b2o = b2;
+  return true;
+}
+
+// default UVs (shape.rs:34-48) or mesh UVs
+PT_DEV void tri_uvs(const DevScene& sc, uint4 idx, uint32_t mesh_flags, V2 uv[3]) {
+  if (mesh_flags & PTRS_MESH_HAS_UV) {
+    const float2* u = (const float2*)sc.uv;
+    float2 a = __ldg(u + idx.x), b = __ldg(u + idx.y), c = __ldg(u + idx.z);
+    uv[0] = V2{a.x, a.y};
+    uv[1] = V2{b.x, b.y};
+    uv[2] = V2{c.x, c.y};
+  } else {
+    uv[0] = V2{0.f, 0.f};
+    uv[1] = V2{1.f, 0.f};
+    uv[2] = V2{1.f, 1.f};
+  }
+}
+
+// dpdu / dpdv, shape.rs:187-215; false = degenerate triangle ("the intersection is bogus")
+PT_DEV bool tri_partials(V3 p0, V3 p1, V3 p2, const V2 uv[3], V3* dpdu, V3* dpdv) {
+  *dpdu = mk3(0, 0, 0);
+  *dpdv = mk3(0, 0, 0);
+  float duv02x = uv[0].x - uv[2].x, duv02y = uv[0].y - uv[2].y;
+  float duv12x = uv[1].x - uv[2].x, duv12y = uv[1].y - uv[2].y;
+  V3 dp02 = p0 - p2, dp12 = p1 - p2;
+  float determinant = duv02x * duv12y - duv02y * duv12x;
+  bool degenerate_uv = fabsf(determinant) < 1e-8f;
+  if (!degenerate_uv) {
+    float invdet = 1.0f / determinant;
+    *dpdu = (duv12y * dp02 - duv02y * dp12) * invdet;
+    *dpdv = (-duv12x * dp02 + duv02x * dp12) * invdet;
+  }
+  if (degenerate_uv || norm_squared(cross(*dpdu, *dpdv)) == 0.0f) {
+    V3 ng = cross(p2 - p0, p1 - p0);
+    if (norm_squared(ng) == 0.0f) return false;
+    coordinate_system(normalize(ng), dpdu, dpdv);
+  }
+  return true;
+}
+
+// The part of Triangle::intersect after the t test that can still reject the hit: degenerate
+// partials (shape.rs:205-212) — only reachable for zero-area triangles — and the alpha mask
+// (shape.rs:228-244).  Slow path, taken only for primitives whose mesh has an alpha texture or
+// for closest-hit candidates (any-hit only evaluates partials under an alpha mask, shape.rs:471).
+PT_DEVN bool tri_post_reject(const DevScene& sc, int prim, V3 p0, V3 p1, V3 p2, uint32_t meta2, float b0, float b1, float b2, bool closest) {
+  const bool has_alpha = (meta2 & PT_TRI_ALPHA_BIT) != 0;
+  if (!closest && !has_alpha) return false;
+  // zero-area test is exact and cheap; the full partials are only needed with an alpha mask
+  if (!has_alpha) {
+    V3 ng = cross(p2 - p0, p1 - p0);
+    if (norm_squared(ng) != 0.0f) return false;
+  }
+  uint4 idx = __ldg(sc.tri_index + prim);
+  V2 uv[3];
+  tri_uvs(sc, idx, meta2 & 0xffu, uv);
+  V3 dpdu, dpdv;
+  if (!tri_partials(p0, p1, p2, uv, &dpdu, &dpdv)) return true;
+  if (has_alpha) {
+    TexCoord tc{b0 * uv[0].x + b1 * uv[1].x + b2 * uv[2].x, b0 * uv[0].y + b1 * uv[1].y + b2 * uv[2].y, 0.f, 0.f, 0.f, 0.f};
+    if (tex_f32(sc, (int)(meta2 >> 9), tc) == 0.0f) return true;
+  }
+  return false;
+}
+
+struct NodeLoad {
+  float4 a, b;  // a = (min.x, min.y, min.z, max.x)  b = (max.y, max.z, offset bits, n_prims | axis << 16)
+};
+PT_DEV NodeLoad load_node(const float4* __restrict__ nodes, uint32_t i) {
+  NodeLoad n;
+  n.a = __ldg(nodes + 2 * (size_t)i);
+  n.b = __ldg(nodes + 2 * (size_t)i + 1);
+  return n;
+}
+
+// bounds.rs:190-232
+PT_DEV bool box_test(const NodeLoad& n, V3 o, V3 inv_dir, bool nx, bool ny, bool nz, float t_ray_max) {
+  const float g = 1.0f + 2.0f * gamma_n(3);
+  float t_min = ((nx ? n.a.w : n.a.x) - o.x) * inv_dir.x;
+  float t_max = ((nx ? n.a.x : n.a.w) - o.x) * inv_dir.x;
+  float ty_min = ((ny ? n.b.x : n.a.y) - o.y) * inv_dir.y;
+  float ty_max = ((ny ? n.a.y : n.b.x) - o.y) * inv_dir.y;
+  t_max *= g;
+  ty_max *= g;
+  if (t_min > ty_max || ty_min > t_max) return false;
+  if (ty_min > t_min) t_min = ty_min;
+  if (ty_max < t_max) t_max = ty_max;
+  float tz_min = ((nz ? n.b.y : n.a.z) - o.z) * inv_dir.z;
+  float tz_max = ((nz ? n.a.z : n.b.y) - o.z) * inv_dir.z;
+  tz_max *= g;
+  if (t_min > tz_max || tz_min > t_max) return false;
+  if (tz_min > t_min) t_min = tz_min;
+  if (tz_max < t_max) t_max = tz_max;
+  return (t_min < t_ray_max) && (t_max > 0.0f);
+}
+
+#define PT_STACK_SIZE 64
+
+// accelerator.rs:359-475.  ANY_HIT: returns at the first accepted triangle (hit->prim = that prim).
+template <bool ANY_HIT, bool COUNT>
+PT_DEV bool traverse(const DevScene& sc, V3 o, V3 d, float t_max, DevHit* hit, uint32_t* n_nodes, uint32_t* n_tris) {
+  hit->prim = -1;
+  hit->t = t_max;
+  hit->b0 = hit->b1 = hit->b2 = 0.f;
+  if (sc.n_nodes == 0) return false;
+  const V3 inv_dir = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+  const bool nx = inv_dir.x < 0.0f, ny = inv_dir.y < 0.0f, nz = inv_dir.z < 0.0f;
+  const RayPre rp = ray_precompute(d);
+  uint32_t stack[PT_STACK_SIZE];
+  int sp_ = 0;
+  uint32_t curr = 0;
+  bool found = false;
+  for (;;) {
+    const NodeLoad n = load_node(sc.nodes, curr);
+    if (COUNT) ++*n_nodes;
+    bool descend = false;
+    if (box_test(n, o, inv_dir, nx, ny, nz, t_max)) {
+      const uint32_t offset = __float_as_uint(n.b.z);
+      const uint32_t meta = __float_as_uint(n.b.w);
+      const uint32_t n_prims = meta & 0xffffu;
+      if (n_prims > 0) {
+        for (uint32_t i = 0; i < n_prims; ++i) {
+          const uint32_t prim = offset + i;
+          const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim);
+          const float4 v1 = __ldg(sc.tri_verts + 3 * (size_t)prim + 1);
+          const float4 v2 = __ldg(sc.tri_verts + 3 * (size_t)prim + 2);
+          if (COUNT) ++*n_tris;
+          float t, b0, b1, b2;
+          if (tri_core(mk3(v0), mk3(v1), mk3(v2), o, rp, t_max, &t, &b0, &b1, &b2)) {
+            if (tri_post_reject(sc, (int)prim, mk3(v0), mk3(v1), mk3(v2), __float_as_uint(v2.w), b0, b1, b2, !ANY_HIT)) continue;
+            found = true;
+            hit->prim = (int)prim;
+            hit->t = t;
+            hit->b0 = b0;
+            hit->b1 = b1;
+            hit->b2 = b2;
+            if (ANY_HIT) return true;
+            t_max = t;
+          }
+        }
+      } else {
+        const uint32_t axis = (meta >> 16) & 0xffu;
+        const bool neg = axis == 0 ? nx : (axis == 1 ? ny : nz);
+        if (sp_ < PT_STACK_SIZE) stack[sp_] = neg ? curr + 1 : offset;
+        ++sp_;
+        curr = neg ? offset : curr + 1;
+        descend = true;
+      }
+    }
+    if (!descend) {
+      if (sp_ == 0) break;
+      --sp_;
+      curr = stack[sp_ < PT_STACK_SIZE ? sp_ : PT_STACK_SIZE - 1];
+    }
+  }
+  return found;
+}
+
+}  // namespace ptrs

@@ -1,0 +1,59 @@
+// Device-resident scene: the PtrsSceneDesc re-laid-out for 128-bit loads.
+//   nodes      32 B records identical to the reference's LinearBVHNode, read as two float4 via the
+//              non-coherent path (ld.global.nc.v4)
+//   tri_verts  48 B per primitive = 3 x float4: xyz = vertex k, w = {material id, area-light id,
+//              mesh flags | alpha texture} as raw bits.  The 36 algorithmic bytes + 12 B of shading
+//              metadata that would otherwise be a second dependent load.
+//   tri_index  16 B per primitive: three global vertex indices + mesh id, only read by shading.
+#pragma once
+#include "../../include/ptrs_b200.h"
+#include "dev_math.cuh"
+
+namespace ptrs {
+
+struct DevEnv {
+  float light_to_world[16];
+  float world_to_light[16];
+  int mip, nu, nv, pad;
+  const float* cond_func;
+  const float* cond_cdf;
+  const float* cond_func_int;
+  const float* marg_func;
+  const float* marg_cdf;
+  float marg_func_int;
+  float pad2;
+};
+
+struct DevScene {
+  const float4* nodes;      // 2 per node
+  const float4* tri_verts;  // 3 per prim
+  const uint4* tri_index;   // 1 per prim
+  const float* normal;
+  const float* tangent;
+  const float* uv;
+  const PtrsMesh* meshes;
+  const PtrsMaterial* materials;
+  const PtrsTexture* textures;
+  const PtrsMipMap* mipmaps;
+  const float* texels;
+  const PtrsLight* lights;
+  const int* infinite_lights;
+  const DevEnv* envs;
+  const uint32_t* sobol;  // SOBOL_MATRICES_32, 1024 x 52
+  uint32_t n_nodes, n_prims, n_lights, n_infinite_lights;
+};
+
+// tri_verts[3 * prim + 2].w packs: bits 0..7 mesh flags, bit 8 has-alpha, bits 9.. alpha texture id
+#define PT_TRI_ALPHA_BIT 0x100u
+
+struct DevRay {
+  V3 o, d;
+  float t_max;
+};
+
+struct DevHit {
+  int prim;
+  float t, b0, b1, b2;
+};
+
+}  // namespace ptrs

@@ -1,0 +1,90 @@
+// Global Sobol sampler on the device: src/pathtracer/sampler/sobol.rs:81-193,
+// src/pathtracer/lowdiscrepancy.rs:9-57.  Integer XOR networks; bit-exact with the CPU path.
+#pragma once
+#include "dev_math.cuh"
+
+namespace ptrs {
+
+// VD_C_SOBOL_MATRICES[m-1] / VD_C_SOBOL_MATRICES_INV[m-1] for the render's log2 resolution m
+// (at most 52 u64 each), uploaded per render into constant memory.
+struct SobolConfig {
+  uint64_t vdc[52];
+  uint64_t vdc_inv[52];
+  int32_t bounds_min[2];
+  int32_t resolution;
+  uint32_t log2_resolution;
+  uint32_t n_vdc, n_vdc_inv;
+  int32_t spp;  // rounded up to a power of two
+  int32_t pad;
+};
+
+#define PT_SOBOL_COLS 52
+#define PT_ARRAY_START_DIM 5
+
+// lowdiscrepancy.rs:9-39
+PT_DEV uint64_t sobol_interval_to_index(const SobolConfig& c, uint64_t frame, int32_t px, int32_t py) {
+  const uint32_t m = c.log2_resolution;
+  if (m == 0) return 0;
+  uint64_t index = frame << (m << 1);
+  uint64_t delta = 0;
+  for (int k = 0; frame != 0; frame >>= 1, ++k)
+    if (frame & 1) delta ^= c.vdc[k];
+  uint64_t b = ((uint64_t)(((uint32_t)px) << m) | (uint64_t)(int64_t)py) ^ delta;
+  for (int k = 0; b != 0; b >>= 1, ++k)
+    if (b & 1) index ^= c.vdc_inv[k];
+  return index;
+}
+
+// lowdiscrepancy.rs:42-57
+PT_DEV float sobol_sample(const uint32_t* __restrict__ matrices, uint64_t index, uint32_t dimension, uint32_t scramble) {
+  uint32_t v = scramble;
+  const uint32_t* col = matrices + dimension * PT_SOBOL_COLS;
+  uint32_t lo = (uint32_t)index, hi = (uint32_t)(index >> 32);
+  while (lo) {
+    int k = __ffs(lo) - 1;
+    v ^= __ldg(col + k);
+    lo &= lo - 1;
+  }
+  while (hi) {
+    int k = __ffs(hi) - 1;
+    v ^= __ldg(col + 32 + k);
+    hi &= hi - 1;
+  }
+  return fminf(PT_ONE_MINUS_EPSILON, (float)v * 0x1.p-32f);
+}
+
+// Per-path sampler state: the reference's SobolSampler minus everything that is constant per render.
+struct PathSampler {
+  uint64_t index;     // interval_sample_index
+  uint32_t scramble;  // current_scramble_index as u32
+  uint32_t dimension;
+  int32_t px, py;
+};
+
+PT_DEV uint32_t pixel_scramble(int32_t x, int32_t y) {  // sobol.rs:83-86 (+ `scramble as u32`)
+  return (uint32_t)cantor_pairing((uint64_t)(int64_t)(x + PT_HALF_MAX_I32), (uint64_t)(int64_t)(y + PT_HALF_MAX_I32));
+}
+
+PT_DEV float sample_dimension(const SobolConfig& c, const uint32_t* __restrict__ matrices, const PathSampler& s, uint32_t dim) {
+  float v = sobol_sample(matrices, s.index, dim, s.scramble);  // sobol.rs:177-193
+  if (dim == 0 || dim == 1) {
+    int32_t pmin = dim == 0 ? c.bounds_min[0] : c.bounds_min[1];
+    int32_t pix = dim == 0 ? s.px : s.py;
+    v = v * (float)c.resolution + (float)pmin;
+    v = rclamp(v - (float)pix, 0.f, PT_ONE_MINUS_EPSILON);
+  }
+  return v;
+}
+PT_DEV float get_1d(const SobolConfig& c, const uint32_t* __restrict__ m, PathSampler& s) {  // sobol.rs:129-137 (array range empty)
+  float v = sample_dimension(c, m, s, s.dimension);
+  s.dimension += 1;
+  return v;
+}
+PT_DEV V2 get_2d(const SobolConfig& c, const uint32_t* __restrict__ m, PathSampler& s) {  // sobol.rs:139-151
+  if (s.dimension + 1 >= PT_ARRAY_START_DIM && s.dimension < PT_ARRAY_START_DIM) s.dimension = PT_ARRAY_START_DIM;
+  V2 v{sample_dimension(c, m, s, s.dimension), sample_dimension(c, m, s, s.dimension + 1)};
+  s.dimension += 2;
+  return v;
+}
+
+}  // namespace ptrs

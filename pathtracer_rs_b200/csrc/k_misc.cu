@@ -1,0 +1,212 @@
+// generate / shade_miss / accumulate / resolve / parity-probe kernels
+#include "launch.hpp"
+#include "wavefront.cuh"
+
+namespace ptrs {
+
+// ---- generate --------------------------------------------------------------------------------------
+// Work item w of a batch -> (sample j, pixel).  Pixels are enumerated in 8x4 blocks so that a warp
+// covers a compact screen tile (coherent primary rays); samples are the slow index.
+PT_DEV void work_to_pixel(const RenderConst& rc, uint64_t w, int* px, int* py, int* sample) {
+  const uint32_t bw = ((uint32_t)rc.sb_ext[0] + 7u) >> 3, bh = ((uint32_t)rc.sb_ext[1] + 3u) >> 2;
+  const uint64_t per_sample = (uint64_t)bw * bh * 32u;
+  const uint32_t j = (uint32_t)(w / per_sample);
+  const uint32_t r = (uint32_t)(w % per_sample);
+  const uint32_t blk = r >> 5, in = r & 31u;
+  const uint32_t bx = blk % bw, by = blk / bw;
+  *px = rc.sb_min[0] + (int)(bx * 8u + (in & 7u));
+  *py = rc.sb_min[1] + (int)(by * 4u + (in >> 3));
+  *sample = rc.s_begin + (int)j * rc.s_stride;
+}
+
+__global__ void __launch_bounds__(256) generate_kernel(const __grid_constant__ RenderConst rc, const uint32_t* __restrict__ sobol,
+                                                        PathArrays P, uint64_t work_base, uint32_t n_work, const int* __restrict__ list_xy,
+                                                        const int* __restrict__ list_s, int* __restrict__ q_ext, RoundCounters* ctr) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n_work + 31u) & ~31u); i += stride) {
+    bool valid = i < n_work;
+    int px = 0, py = 0, s = 0;
+    if (valid) {
+      if (list_xy) {
+        px = list_xy[2 * i];
+        py = list_xy[2 * i + 1];
+        s = list_s[i];
+      } else {
+        work_to_pixel(rc, work_base + i, &px, &py, &s);
+        valid = px < rc.sb_min[0] + rc.sb_ext[0] && py < rc.sb_min[1] + rc.sb_ext[1];
+      }
+    }
+    if (valid) {
+      PathSampler ps;
+      ps.px = px;
+      ps.py = py;
+      ps.scramble = pixel_scramble(px, py);
+      ps.index = sobol_interval_to_index(rc.sobol, (uint64_t)s, px - rc.sobol.bounds_min[0], py - rc.sobol.bounds_min[1]);
+      ps.dimension = 0;
+      V2 u = get_2d(rc.sobol, sobol, ps);
+      const float fx = (float)px + u.x, fy = (float)py + u.y;  // get_camera_sample, sobol.rs:116-120
+      V3 o, d;
+      camera_ray(rc.cam, fx, fy, rc.diff_scale, &o, &d, nullptr, nullptr);
+      P.ray_o[i] = make_float4(o.x, o.y, o.z, 0.f);
+      P.ray_d[i] = make_float4(d.x, d.y, d.z, 0.f);
+      P.beta[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+      P.L[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      P.sobol_index[i] = ps.index;
+      P.pixel[i] = make_int2(px, py);
+      P.bounces[i] = 0;
+      P.flags[i] = ps.dimension | PT_F_HAS_DIFF;
+      P.p_film[i] = make_float2(fx, fy);
+    } else if (i < n_work) {
+      P.L[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      P.p_film[i] = make_float2(-1e30f, -1e30f);  // padding lane of an 8x4 block outside the sample bounds
+    }
+    warp_push(valid, i, q_ext, &ctr->n_ext);
+  }
+}
+
+// ---- shade -----------------------------------------------------------------------------------------
+// "miss" class: Σ infinite lights Le for camera / specular paths, then the path ends (integrator.rs:418-431)
+__global__ void __launch_bounds__(128) shade_miss_kernel(DevScene sc, PathArrays P, const int* __restrict__ q, RoundCounters* ctr) {
+  const uint32_t n = ctr->n_class[PT_CLASS_MISS];
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    const uint32_t base = warp_fetch32(&ctr->t_class[PT_CLASS_MISS]);
+    if (base >= n) break;
+    const uint32_t i = base + lane;
+    if (i >= n) continue;
+    const int p = q[i];
+    const uint32_t flags = P.flags[p];
+    if (P.bounces[p] == 0 || (flags & PT_F_SPECULAR)) {
+      const float4 b4 = P.beta[p];
+      float4 l4 = P.L[p];
+      const V3 d = mk3(P.ray_d[p]);
+      Spec l = sp(l4.x, l4.y, l4.z), beta = sp(b4.x, b4.y, b4.z);
+      for (uint32_t k = 0; k < sc.n_infinite_lights; ++k) l = l + beta * env_le(sc, sc.lights[sc.infinite_lights[k]], d);
+      P.L[p] = make_float4(l.r, l.g, l.b, 0.f);
+    }
+  }
+}
+
+// ---- accumulate ------------------------------------------------------------------------------------
+// FilmTile::add_sample + merge_film_tile (film.rs:60-106, 213-228) straight into the film with
+// 128-bit float atomics (red.global.add.v4.f32, sm_90+).
+__global__ void __launch_bounds__(256) accumulate_kernel(const __grid_constant__ RenderConst rc, PathArrays P, uint32_t n, float4* film) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const int W = rc.cam.width, H = rc.cam.height;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float2 pf = P.p_film[i];
+    if (pf.x < -1e29f) continue;
+    const float4 l = P.L[i];
+    const float dx = pf.x - 0.5f, dy = pf.y - 0.5f;
+    int p0x = (int)ceilf(dx - rc.filter_radius[0]), p0y = (int)ceilf(dy - rc.filter_radius[1]);
+    int p1x = (int)(floorf(dx + rc.filter_radius[0]) + 1.0f), p1y = (int)(floorf(dy + rc.filter_radius[1]) + 1.0f);
+    p0x = max(p0x, 0);
+    p0y = max(p0y, 0);
+    p1x = min(p1x, W);
+    p1y = min(p1y, H);
+    for (int y = p0y; y < p1y; ++y) {
+      const float fy = fabsf(((float)y - dy) * rc.inv_filter_radius[1] * 16.0f);
+      const int iy = min((int)floorf(fy), 15);
+      for (int x = p0x; x < p1x; ++x) {
+        const float fx = fabsf(((float)x - dx) * rc.inv_filter_radius[0] * 16.0f);
+        const int ix = min((int)floorf(fx), 15);
+        const float w = rc.filter_table[iy * 16 + ix];
+        atomicAdd(&film[(size_t)y * W + x], make_float4(l.x * w, l.y * w, l.z * w, w));
+      }
+    }
+  }
+}
+
+// ---- parity probes -----------------------------------------------------------------------------------
+__global__ void sobol_probe_kernel(const __grid_constant__ RenderConst rc, const uint32_t* __restrict__ sobol, const int* xy, const int* s,
+                                   uint32_t n, const int* dims, uint32_t n_dims, float* out, uint64_t* out_index) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  PathSampler ps;
+  ps.px = xy[2 * i];
+  ps.py = xy[2 * i + 1];
+  ps.scramble = pixel_scramble(ps.px, ps.py);
+  ps.index = sobol_interval_to_index(rc.sobol, (uint64_t)s[i], ps.px - rc.sobol.bounds_min[0], ps.py - rc.sobol.bounds_min[1]);
+  ps.dimension = 0;
+  if (out_index) out_index[i] = ps.index;
+  for (uint32_t k = 0; k < n_dims; ++k) out[(size_t)i * n_dims + k] = sample_dimension(rc.sobol, sobol, ps, (uint32_t)dims[k]);
+}
+
+__global__ void ray_probe_kernel(const __grid_constant__ RenderConst rc, const uint32_t* __restrict__ sobol, const int* xy, const int* s,
+                                 uint32_t n, PtrsRay* rays, float* p_film, float* rxry) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  PathSampler ps;
+  ps.px = xy[2 * i];
+  ps.py = xy[2 * i + 1];
+  ps.scramble = pixel_scramble(ps.px, ps.py);
+  ps.index = sobol_interval_to_index(rc.sobol, (uint64_t)s[i], ps.px - rc.sobol.bounds_min[0], ps.py - rc.sobol.bounds_min[1]);
+  ps.dimension = 0;
+  V2 u = get_2d(rc.sobol, sobol, ps);
+  const float fx = (float)ps.px + u.x, fy = (float)ps.py + u.y;
+  V3 o, d, rx, ry;
+  camera_ray(rc.cam, fx, fy, rc.diff_scale, &o, &d, &rx, &ry);
+  rays[i].o[0] = o.x; rays[i].o[1] = o.y; rays[i].o[2] = o.z;
+  rays[i].d[0] = d.x; rays[i].d[1] = d.y; rays[i].d[2] = d.z;
+  rays[i].t_max = CUDART_INF_F;
+  if (p_film) { p_film[2 * i] = fx; p_film[2 * i + 1] = fy; }
+  if (rxry) {
+    rxry[6 * i] = rx.x; rxry[6 * i + 1] = rx.y; rxry[6 * i + 2] = rx.z;
+    rxry[6 * i + 3] = ry.x; rxry[6 * i + 4] = ry.y; rxry[6 * i + 5] = ry.z;
+  }
+}
+
+// Film::to_channel_updates (film.rs:253-271) and to_rgba_image (film.rs:230-251, spectrum.rs:95-102)
+__global__ void resolve_kernel(const float4* film, uint32_t n, float* rgb, uint8_t* rgba8) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = film[i];
+  const float inv_wt = 1.f / p.w;
+  const float c[3] = {p.x * inv_wt, p.y * inv_wt, p.z * inv_wt};
+  if (rgb) {
+    rgb[3 * i] = c[0];
+    rgb[3 * i + 1] = c[1];
+    rgb[3 * i + 2] = c[2];
+  }
+  if (rgba8) {
+    for (int k = 0; k < 3; ++k) {
+      float v = c[k];
+      float gc = v <= 0.0031308f ? 12.92f * v : 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;  // math.rs:133-139
+      float q = rclamp(gc * 255.0f + 0.5f, 0.0f, 255.0f);
+      rgba8[4 * i + k] = (uint8_t)q;  // NaN -> 0 like Rust's saturating cast
+    }
+    rgba8[4 * i + 3] = 255;
+  }
+}
+
+
+// ---- launchers -----------------------------------------------------------------------------------------
+void launch_generate(cudaStream_t st, int sm, const RenderConst& rc, const uint32_t* sobol, const PathArrays& P, uint64_t work_base,
+                     uint32_t n_work, const int* list_xy, const int* list_s, int* q_ext, RoundCounters* ctr) {
+  static int grid = 0;
+  if (!grid) grid = persistent_grid(generate_kernel, 256, sm);
+  generate_kernel<<<grid, 256, 0, st>>>(rc, sobol, P, work_base, n_work, list_xy, list_s, q_ext, ctr);
+}
+void launch_shade_miss(cudaStream_t st, int sm, const DevScene& sc, const PathArrays& P, const int* q, RoundCounters* ctr) {
+  static int grid = 0;
+  if (!grid) grid = persistent_grid(shade_miss_kernel, 128, sm);
+  shade_miss_kernel<<<grid, 128, 0, st>>>(sc, P, q, ctr);
+}
+void launch_accumulate(cudaStream_t st, int sm, const RenderConst& rc, const PathArrays& P, uint32_t n, float4* film) {
+  static int grid = 0;
+  if (!grid) grid = persistent_grid(accumulate_kernel, 256, sm);
+  accumulate_kernel<<<grid, 256, 0, st>>>(rc, P, n, film);
+}
+void launch_resolve(cudaStream_t st, const float4* film, uint32_t n, float* rgb, uint8_t* rgba8) {
+  resolve_kernel<<<(n + 255) / 256, 256, 0, st>>>(film, n, rgb, rgba8);
+}
+void launch_sobol_probe(cudaStream_t st, const RenderConst& rc, const uint32_t* sobol, const int* xy, const int* s, uint32_t n,
+                        const int* dims, uint32_t n_dims, float* out, uint64_t* out_index) {
+  sobol_probe_kernel<<<(n + 127) / 128, 128, 0, st>>>(rc, sobol, xy, s, n, dims, n_dims, out, out_index);
+}
+void launch_ray_probe(cudaStream_t st, const RenderConst& rc, const uint32_t* sobol, const int* xy, const int* s, uint32_t n, PtrsRay* rays,
+                      float* p_film, float* rxry) {
+  ray_probe_kernel<<<(n + 127) / 128, 128, 0, st>>>(rc, sobol, xy, s, n, rays, p_film, rxry);
+}
+
+}  // namespace ptrs

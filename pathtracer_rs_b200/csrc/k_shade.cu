@@ -1,0 +1,253 @@
+// shade<MAT> kernel; compiled once per material type with -DPT_SHADE_MAT=<n> so the six
+// instantiations build in parallel and each gets its own register allocation
+#include "launch.hpp"
+#include "wavefront.cuh"
+
+namespace ptrs {
+
+// first half of estimate_direct (integrator.rs:38-80): light sample, BSDF eval, shadow segment; and
+// the BSDF-sampling half up to the point where a ray must be traced (integrator.rs:82-114)
+PT_DEV void nee_prepare(const DevScene& sc, const SurfInter& si, const Bsdf& bsdf, V2 u_scattering, int light_idx, V2 u_light,
+                        float4* n0, float4* n1, float4* n2, float4* n3, float4* n4, float* scat_pdf_out, uint32_t* nee_flags) {
+  const PtrsLight& light = sc.lights[light_idx];
+  const uint32_t bsdf_flags = BSDF_ALL & ~BSDF_SPECULAR;
+  V3 wi = mk3(0, 0, 0);
+  float light_pdf = 0.0f, scattering_pdf = 0.0f;
+  Inter p1;  // VisibilityTester.p1
+  p1.p_error = mk3(0, 0, 0);
+  p1.n = mk3(0, 0, 0);
+  Spec li = sp(0.f);
+  const bool delta = light.type == PTRS_LIGHT_POINT || light.type == PTRS_LIGHT_DIRECTIONAL;
+  if (light.type == PTRS_LIGHT_POINT) {  // light.rs:97-116
+    V3 pl = mk3(light.pos[0], light.pos[1], light.pos[2]);
+    wi = normalize(pl - si.g.p);
+    light_pdf = 1.0f;
+    p1.p = pl;
+    li = sp(light.color[0], light.color[1], light.color[2]) / norm_squared(pl - si.g.p);
+  } else if (light.type == PTRS_LIGHT_DIRECTIONAL) {  // light.rs:176-196
+    V3 wl = mk3(light.pos[0], light.pos[1], light.pos[2]);
+    wi = wl;
+    light_pdf = 1.0f;
+    p1.p = si.g.p + wl * (2.0f * light.world_radius);
+    li = sp(light.color[0], light.color[1], light.color[2]);
+  } else if (light.type == PTRS_LIGHT_AREA) {  // light.rs:262-280
+    TriPoint tp = triangle_sample(sc, light.prim, u_light);
+    wi = normalize(tp.it.p - si.g.p);
+    light_pdf = triangle_pdf_at_point(sc, light.prim, si.g, wi, light.area);
+    p1 = tp.it;
+    if (dot(tp.it.n, -wi) > 0.0f) li = tex_spec(sc, light.ke_tex, TexCoord{tp.uv.x, tp.uv.y, 0.f, 0.f, 0.f, 0.f});
+  } else {  // PTRS_LIGHT_INFINITE, light.rs:402-441
+    const DevEnv& e = sc.envs[light.env];
+    float map_pdf = 0.0f;
+    V2 uv = dist2d_sample(e, u_light, &map_pdf);
+    if (map_pdf == 0.0f) {
+      // the reference panics here (visibility.unwrap() on None, integrator.rs:51); unreachable for a
+      // distribution with positive integral.  Contribute nothing.
+      light_pdf = 0.0f;
+    } else {
+      float theta = uv.y * PT_PI, phi = uv.x * 2.0f * PT_PI;
+      float cos_t = cosf(theta), sin_t = sinf(theta);
+      float sin_p = sinf(phi), cos_p = cosf(phi);
+      wi = xform_vec(e.light_to_world, mk3(sin_t * cos_p, sin_t * sin_p, cos_t));
+      light_pdf = sin_t == 0.0f ? 0.0f : map_pdf / (2.0f * PT_PI * PT_PI * sin_t);
+      p1.p = si.g.p + wi * (2.0f * light.world_radius);
+      li = env_lookup(sc, e, uv.x, uv.y);
+    }
+  }
+  uint32_t nf = (uint32_t)light_idx;
+  Spec A = sp(0.f);
+  V3 sh_o = mk3(0, 0, 0), sh_d = mk3(0, 0, 0);
+  if (light_pdf > 0.0f && !is_black(li)) {
+    Spec f = bsdf_f(bsdf, si.wo, wi, bsdf_flags) * fabsf(dot(wi, si.sh_n));
+    scattering_pdf = bsdf_pdf(bsdf, si.wo, wi, bsdf_flags);
+    if (!is_black(f)) {
+      spawn_ray_to_it(si.g, p1, &sh_o, &sh_d);
+      nf |= PT_NEE_SHADOW;
+      if (delta) A = f * li / light_pdf;
+      else A = f * li * power_heuristic(light_pdf, scattering_pdf) / light_pdf;
+    }
+  }
+  V3 mo = mk3(0, 0, 0), md = mk3(0, 0, 0);
+  Spec f2 = sp(0.f);
+  float weight = 1.0f;
+  if (!delta) {
+    uint32_t sampled_type = BSDF_ALL;
+    V3 wi2 = mk3(0, 0, 0);
+    f2 = bsdf_sample_f(bsdf, si.wo, &wi2, u_scattering, &scattering_pdf, bsdf_flags, &sampled_type);
+    f2 = f2 * fabsf(dot(wi2, si.sh_n));
+    const bool sampled_specular = (sampled_type & BSDF_SPECULAR) == BSDF_SPECULAR;
+    if (!is_black(f2) && scattering_pdf > 0.0f) {
+      bool go = true;
+      if (!sampled_specular) {
+        float lp;
+        if (light.type == PTRS_LIGHT_AREA) {
+          lp = triangle_pdf_at_point(sc, light.prim, si.g, wi2, light.area);
+        } else {  // infinite, light.rs:447-461
+          const DevEnv& e = sc.envs[light.env];
+          V3 w = xform_vec(e.world_to_light, wi2);
+          float theta = spherical_theta(w), phi = spherical_phi(w);
+          float sin_t = sinf(theta);
+          lp = sin_t == 0.0f ? 0.0f : dist2d_pdf(e, phi * PT_INV_2_PI, theta * PT_FRAC_1_PI) / (2.0f * PT_PI * PT_PI * sin_t);
+        }
+        if (lp == 0.0f) go = false;  // `return ld` (integrator.rs:107-109)
+        else weight = power_heuristic(scattering_pdf, lp);
+      }
+      if (go) {
+        spawn_ray(si.g, wi2, &mo);
+        md = wi2;
+        nf |= PT_NEE_MIS;
+      }
+    }
+  }
+  *n0 = make_float4(sh_o.x, sh_o.y, sh_o.z, A.r);
+  *n1 = make_float4(sh_d.x, sh_d.y, sh_d.z, A.g);
+  *n2 = make_float4(mo.x, mo.y, mo.z, A.b);
+  *n3 = make_float4(md.x, md.y, md.z, __uint_as_float(nf));
+  *n4 = make_float4(f2.r, f2.g, f2.b, weight);
+  *scat_pdf_out = scattering_pdf;
+  *nee_flags = nf;
+}
+
+template <int MAT>
+__global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ RenderConst rc, DevScene sc, PathArrays P,
+                                                     const int* __restrict__ q, int* __restrict__ q_ext_next, int* __restrict__ q_nee,
+                                                     RoundCounters* ctr, RoundCounters* ctr_next) {
+  const uint32_t n = ctr->n_class[MAT];
+  const int lane = threadIdx.x & 31;
+  const uint32_t* __restrict__ sobol = sc.sobol;
+  for (;;) {
+    const uint32_t base = warp_fetch32(&ctr->t_class[MAT]);
+    if (base >= n) break;
+    const uint32_t i = base + lane;
+    bool push_ext = false, push_nee = false;
+    int p = 0;
+    if (i < n) {
+      p = q[i];
+      const V3 ray_d = mk3(P.ray_d[p]);
+      const int prim = P.hit_prim[p];
+      const float4 tb = P.hit_tb[p];
+      SurfInter si;
+      reconstruct_hit(sc, prim, tb.y, tb.z, tb.w, ray_d, &si);
+      uint32_t flags = P.flags[p];
+      int bounces = P.bounces[p];
+      const float4 b4 = P.beta[p];
+      Spec beta = sp(b4.x, b4.y, b4.z);
+      float eta_scale = b4.w;
+      const float4 l4 = P.L[p];
+      Spec L = sp(l4.x, l4.y, l4.z);
+      const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim), v1 = __ldg(sc.tri_verts + 3 * (size_t)prim + 1);
+      const int mat_id = __float_as_int(v0.w), light_id = __float_as_int(v1.w);
+      // emitted radiance at the vertex (integrator.rs:418-422)
+      if (bounces == 0 || (flags & PT_F_SPECULAR)) L = L + beta * area_le(sc, light_id, si, -ray_d);
+      bool alive = bounces < rc.max_depth;  // integrator.rs:429
+      if (alive) {
+        if (flags & PT_F_HAS_DIFF) {  // compute_scattering_functions -> compute_differentials
+          const float2 pf = P.p_film[p];
+          RayDiff rd;
+          V3 o, d;
+          camera_ray(rc.cam, pf.x, pf.y, rc.diff_scale, &o, &d, &rd.rx_d, &rd.ry_d);
+          rd.rx_o = o;
+          rd.ry_o = o;
+          compute_differentials(&si, rd);
+        }
+        flags &= ~PT_F_HAS_DIFF;
+        const PtrsMaterial& m = sc.materials[mat_id];
+        Bsdf bsdf;
+        if (!compute_scattering_functions<MAT>(sc, m, &si, &bsdf)) {
+          // null BSDF: continue straight through; `bounces -= 1; continue` nets -1 (integrator.rs:434-439)
+          V3 o;
+          spawn_ray(si.g, ray_d, &o);
+          P.ray_o[p] = make_float4(o.x, o.y, o.z, 0.f);
+          bounces -= 1;
+          push_ext = true;
+        } else {
+          PathSampler ps;
+          const int2 pix = P.pixel[p];
+          ps.px = pix.x;
+          ps.py = pix.y;
+          ps.scramble = pixel_scramble(pix.x, pix.y);
+          ps.index = P.sobol_index[p];
+          ps.dimension = flags & 0xffffu;
+          // direct lighting (integrator.rs:443-447, 192-217)
+          if (bsdf_num_components(bsdf, BSDF_ALL & ~BSDF_SPECULAR) > 0 && sc.n_lights > 0) {
+            V2 u_light = get_2d(rc.sobol, sobol, ps);
+            V2 u_scattering = get_2d(rc.sobol, sobol, ps);
+            float u_idx = get_1d(rc.sobol, sobol, ps);
+            unsigned long long li64 = (unsigned long long)floorf(u_idx * (float)sc.n_lights);
+            int light_idx = (int)(li64 < (unsigned long long)(sc.n_lights - 1) ? li64 : (unsigned long long)(sc.n_lights - 1));
+            float4 n0, n1, n2, n3, n4;
+            float scat_pdf;
+            uint32_t nf;
+            nee_prepare(sc, si, bsdf, u_scattering, light_idx, u_light, &n0, &n1, &n2, &n3, &n4, &scat_pdf, &nf);
+            if (nf & (PT_NEE_SHADOW | PT_NEE_MIS)) {
+              P.nee0[p] = n0;
+              P.nee1[p] = n1;
+              P.nee2[p] = n2;
+              P.nee3[p] = n3;
+              P.nee4[p] = n4;
+              P.nee5[p] = make_float4(beta.r, beta.g, beta.b, scat_pdf);
+              push_nee = true;
+            }
+          }
+          // continuation (integrator.rs:449-499)
+          V3 wi = mk3(0, 0, 0);
+          float pdf = 0.0f;
+          uint32_t sampled = 0;
+          Spec f = bsdf_sample_f(bsdf, si.wo, &wi, get_2d(rc.sobol, sobol, ps), &pdf, BSDF_ALL, &sampled);
+          if (!(is_black(f) || pdf == 0.0f)) {
+            beta = beta * (f * fabsf(dot(wi, si.sh_n)) / pdf);
+            if (sampled & BSDF_SPECULAR) flags |= PT_F_SPECULAR;
+            else flags &= ~PT_F_SPECULAR;
+            if ((sampled & BSDF_SPECULAR) && (sampled & BSDF_TRANSMISSION)) {
+              float eta = bsdf.eta;
+              eta_scale *= dot(si.wo, si.g.n) > 0.0f ? eta * eta : 1.0f / (eta * eta);
+            }
+            V3 o;
+            spawn_ray(si.g, wi, &o);
+            bool survive = true;
+            if (rc.rr_enable) {
+              Spec rr_beta = beta * eta_scale;
+              float mc = max_component(rr_beta);
+              if (mc < rc.rr_threshold && bounces > rc.rr_start_depth) {
+                float qv = fmaxf(0.05f, 1.0f - mc);
+                if (get_1d(rc.sobol, sobol, ps) < qv) survive = false;
+                else beta = beta / (1.0f - qv);
+              }
+            }
+            if (survive) {
+              P.ray_o[p] = make_float4(o.x, o.y, o.z, 0.f);
+              P.ray_d[p] = make_float4(wi.x, wi.y, wi.z, 0.f);
+              bounces += 1;
+              push_ext = true;
+            }
+          }
+          flags = (flags & 0xffff0000u) | (ps.dimension & 0xffffu);
+        }
+      }
+      P.L[p] = make_float4(L.r, L.g, L.b, 0.f);
+      if (push_ext) {
+        P.beta[p] = make_float4(beta.r, beta.g, beta.b, eta_scale);
+        P.bounces[p] = bounces;
+        P.flags[p] = flags;
+      }
+    }
+    warp_push(push_nee, (uint32_t)p, q_nee, &ctr->n_nee);
+    warp_push(push_ext, (uint32_t)p, q_ext_next, &ctr_next->n_ext);
+  }
+}
+
+
+// ---- launcher ------------------------------------------------------------------------------------------
+#ifndef PT_SHADE_MAT
+#error "compile k_shade.cu with -DPT_SHADE_MAT=<PtrsMaterialType>"
+#endif
+#define PT_CAT2(a, b) a##b
+#define PT_CAT(a, b) PT_CAT2(a, b)
+void PT_CAT(launch_shade_, PT_SHADE_MAT)(cudaStream_t st, int sm, const RenderConst& rc, const DevScene& sc, const PathArrays& P, const int* q,
+                                         int* q_next, int* q_nee, RoundCounters* ctr, RoundCounters* ctr_next) {
+  static int grid = 0;
+  if (!grid) grid = persistent_grid(shade_kernel<PT_SHADE_MAT>, 128, sm);
+  shade_kernel<PT_SHADE_MAT><<<grid, 128, 0, st>>>(rc, sc, P, q, q_next, q_nee, ctr, ctr_next);
+}
+
+}  // namespace ptrs

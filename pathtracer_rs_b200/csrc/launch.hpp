@@ -1,0 +1,48 @@
+// Host-callable launchers of the kernels, one group per translation unit.  Every launcher sizes its
+// persistent grid as (resident CTAs per SM) x (SM count) from the occupancy API, cached per process.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ptrs_b200.h"
+
+namespace ptrs {
+struct DevScene;
+struct PathArrays;
+struct RoundCounters;
+struct GlobalCounters;
+struct RenderConst;
+
+// k_misc.cu
+void launch_generate(cudaStream_t st, int sm, const RenderConst& rc, const uint32_t* sobol, const PathArrays& P, uint64_t work_base,
+                     uint32_t n_work, const int* list_xy, const int* list_s, int* q_ext, RoundCounters* ctr);
+void launch_shade_miss(cudaStream_t st, int sm, const DevScene& sc, const PathArrays& P, const int* q, RoundCounters* ctr);
+void launch_accumulate(cudaStream_t st, int sm, const RenderConst& rc, const PathArrays& P, uint32_t n, float4* film);
+void launch_resolve(cudaStream_t st, const float4* film, uint32_t n, float* rgb, uint8_t* rgba8);
+void launch_sobol_probe(cudaStream_t st, const RenderConst& rc, const uint32_t* sobol, const int* xy, const int* s, uint32_t n,
+                        const int* dims, uint32_t n_dims, float* out, uint64_t* out_index);
+void launch_ray_probe(cudaStream_t st, const RenderConst& rc, const uint32_t* sobol, const int* xy, const int* s, uint32_t n, PtrsRay* rays,
+                      float* p_film, float* rxry);
+
+// k_trace.cu
+void launch_extend(cudaStream_t st, int sm, bool count, const DevScene& sc, const PathArrays& P, const int* q_ext, int* q_class, uint32_t cap,
+                   RoundCounters* ctr, GlobalCounters* g);
+void launch_connect(cudaStream_t st, int sm, bool count, const DevScene& sc, const PathArrays& P, const int* q_nee, RoundCounters* ctr,
+                    GlobalCounters* g);
+void launch_intersect(cudaStream_t st, int sm, bool any_hit, bool count, const DevScene& sc, const PtrsRay* rays, uint32_t n, PtrsHit* hits,
+                      uint8_t* occluded, uint32_t* ticket, GlobalCounters* g);
+
+// k_shade.cu, built once per PtrsMaterialType
+#define PT_DECL_SHADE(M)                                                                                                              \
+  void launch_shade_##M(cudaStream_t st, int sm, const RenderConst& rc, const DevScene& sc, const PathArrays& P, const int* q, int* q_next, \
+                        int* q_nee, RoundCounters* ctr, RoundCounters* ctr_next);
+PT_DECL_SHADE(0) PT_DECL_SHADE(1) PT_DECL_SHADE(2) PT_DECL_SHADE(3) PT_DECL_SHADE(4) PT_DECL_SHADE(5)
+#undef PT_DECL_SHADE
+
+template <class K>
+inline int persistent_grid(K kernel, int block, int sm_count) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return sm_count * per_sm;
+}
+}  // namespace ptrs

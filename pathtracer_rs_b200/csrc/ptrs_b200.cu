@@ -1,0 +1,867 @@
+// libptrs_b200.so — C ABI (include/ptrs_b200.h) over the sm_100a wavefront path tracer.
+// Host side: scene upload and re-layout, film, the per-batch launch schedule, statistics.
+// There is deliberately no CPU code path here: without a CUDA device every entry point fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "launch.hpp"
+#include "wavefront.cuh"
+
+using namespace ptrs;
+
+// Sobol tables (pathtracer_rs_b200/data/sobol_tables.bin) linked into the library by sobol_blob.S
+extern "C" const unsigned char ptrs_sobol_blob[];
+extern "C" const unsigned char ptrs_sobol_blob_end[];
+
+namespace {
+
+thread_local std::string g_err;
+int32_t fail(int32_t code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                         \
+  do {                                                                                                         \
+    cudaError_t e__ = (expr);                                                                                  \
+    if (e__ != cudaSuccess) return fail(PTRS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+struct SobolHost {
+  uint32_t n_dims = 0, n_cols = 0;
+  const uint32_t* matrices = nullptr;
+  std::vector<std::vector<uint64_t>> vdc, vdc_inv;
+  bool ok = false;
+};
+const SobolHost& sobol_host() {
+  static SobolHost h;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const unsigned char* p = ptrs_sobol_blob;
+    const unsigned char* end = ptrs_sobol_blob_end;
+    if (end - p < 20 || std::memcmp(p, "SOBL", 4) != 0) return;
+    uint32_t hdr[4];
+    std::memcpy(hdr, p + 4, 16);
+    p += 20;
+    h.n_dims = hdr[0];
+    h.n_cols = hdr[1];
+    h.matrices = reinterpret_cast<const uint32_t*>(p);
+    p += (size_t)hdr[0] * hdr[1] * 4;
+    auto rd = [&](std::vector<std::vector<uint64_t>>& dst, uint32_t n) {
+      for (uint32_t i = 0; i < n; ++i) {
+        uint32_t len;
+        std::memcpy(&len, p, 4);
+        p += 4;
+        std::vector<uint64_t> v(len);
+        std::memcpy(v.data(), p, (size_t)len * 8);
+        p += (size_t)len * 8;
+        dst.push_back(std::move(v));
+      }
+    };
+    rd(h.vdc, hdr[2]);
+    rd(h.vdc_inv, hdr[3]);
+    h.ok = p <= end && h.n_cols == PT_SOBOL_COLS;
+  });
+  return h;
+}
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc(&p, count * sizeof(T));
+  }
+  cudaError_t upload(const T* src, size_t count) {
+    cudaError_t e = alloc(count);
+    if (e != cudaSuccess || count == 0) return e;
+    return cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice);
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+struct Workspace {
+  uint32_t cap = 0, rounds = 0;
+  DevBuf<float4> ray_o, ray_d, hit_tb, beta, L, nee[6];
+  DevBuf<int> hit_prim, bounces;
+  DevBuf<uint64_t> sobol_index;
+  DevBuf<int2> pixel;
+  DevBuf<uint32_t> flags;
+  DevBuf<float2> p_film;
+  DevBuf<int> q_ext[2], q_nee, q_class;
+  DevBuf<RoundCounters> counters;
+  DevBuf<GlobalCounters> gcount;
+  PathArrays arrays() {
+    PathArrays a;
+    a.ray_o = ray_o.p;
+    a.ray_d = ray_d.p;
+    a.hit_prim = hit_prim.p;
+    a.hit_tb = hit_tb.p;
+    a.beta = beta.p;
+    a.L = L.p;
+    a.sobol_index = sobol_index.p;
+    a.pixel = pixel.p;
+    a.bounces = bounces.p;
+    a.flags = flags.p;
+    a.p_film = p_film.p;
+    a.nee0 = nee[0].p;
+    a.nee1 = nee[1].p;
+    a.nee2 = nee[2].p;
+    a.nee3 = nee[3].p;
+    a.nee4 = nee[4].p;
+    a.nee5 = nee[5].p;
+    return a;
+  }
+  uint64_t bytes() const {
+    return (uint64_t)cap * (16 * 11 + 4 * 2 + 8 + 8 + 4 + 8 + 4 * (3 + PT_N_CLASSES)) + (uint64_t)rounds * sizeof(RoundCounters);
+  }
+};
+
+}  // namespace
+
+struct PtrsScene {
+  int device = 0;
+  DevScene dev{};
+  DevBuf<float4> nodes, tri_verts;
+  DevBuf<uint4> tri_index;
+  DevBuf<float> normal, tangent, uv, texels;
+  DevBuf<PtrsMesh> meshes;
+  DevBuf<PtrsMaterial> materials;
+  DevBuf<PtrsTexture> textures;
+  DevBuf<PtrsMipMap> mipmaps;
+  DevBuf<PtrsLight> lights;
+  DevBuf<int> infinite_lights;
+  DevBuf<DevEnv> envs;
+  std::vector<DevBuf<float>> env_arrays;
+  DevBuf<uint32_t> sobol;
+  DevBuf<uint32_t> ticket;
+  DevBuf<GlobalCounters> gcount;
+  float world_bound[6] = {0, 0, 0, 0, 0, 0};
+  uint64_t scene_bytes = 0;
+  Workspace ws;
+  PtrsStats stats{};
+  bool count_visits = false;
+  bool has_mat[PTRS_MAT_COUNT] = {false, false, false, false, false, false};
+  int sm_count = 148;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> stage_events;
+  ~PtrsScene() {
+    for (cudaEvent_t e : ev)
+      if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : stage_events) cudaEventDestroy(e);
+  }
+};
+
+struct PtrsFilm {
+  int width = 0, height = 0;
+  float4* d = nullptr;
+  bool owned = false;
+};
+
+namespace {
+
+int32_t build_render_const(const PtrsCamera* cam, const PtrsRenderParams* rp, RenderConst* rc, std::string* why) {
+  const SobolHost& sh = sobol_host();
+  if (!sh.ok) {
+    *why = "embedded Sobol tables are corrupt";
+    return PTRS_ERR_INVALID_ARGUMENT;
+  }
+  if (cam->width <= 0 || cam->height <= 0 || rp->spp <= 0 || rp->max_depth < 0) {
+    *why = "bad camera resolution / spp / max_depth";
+    return PTRS_ERR_INVALID_ARGUMENT;
+  }
+  if (rp->max_depth > 120) {  // 8 Sobol dimensions per bounce must stay below 1024 (sobol.rs:178-183 panics)
+    *why = "max_depth > 120 would exceed the 1024 Sobol dimensions";
+    return PTRS_ERR_UNSUPPORTED;
+  }
+  std::memset(rc, 0, sizeof(*rc));
+  // Film::get_sample_bounds, film.rs:174-185
+  const int sbx0 = (int)std::floor(0.5f - rp->filter_radius[0]), sby0 = (int)std::floor(0.5f - rp->filter_radius[1]);
+  const int sbx1 = (int)std::ceil((float)cam->width - 0.5f + rp->filter_radius[0]);
+  const int sby1 = (int)std::ceil((float)cam->height - 0.5f + rp->filter_radius[1]);
+  // SobolSamplerBuilder::new, sobol.rs:35-62
+  int64_t spp = rp->spp;
+  {
+    int64_t v = spp - 1;
+    v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16; v |= v >> 32;
+    spp = v + 1;
+  }
+  int32_t ext = std::max(sbx1 - sbx0, sby1 - sby0);
+  {
+    int32_t v = ext - 1;
+    v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16;
+    ext = v + 1;
+  }
+  uint32_t m = 0;
+  while ((1 << (m + 1)) <= ext) ++m;
+  if (m < 1 || m > 25 || (uint64_t)m * 2 + (uint64_t)std::ceil(std::log2((double)spp)) > 52) {
+    *why = "resolution / spp outside the Sobol tables' range";
+    return PTRS_ERR_UNSUPPORTED;
+  }
+  SobolConfig& sc = rc->sobol;
+  sc.bounds_min[0] = sbx0;
+  sc.bounds_min[1] = sby0;
+  sc.resolution = ext;
+  sc.log2_resolution = m;
+  sc.n_vdc = (uint32_t)sh.vdc[m - 1].size();
+  sc.n_vdc_inv = (uint32_t)sh.vdc_inv[m - 1].size();
+  std::memcpy(sc.vdc, sh.vdc[m - 1].data(), sc.n_vdc * 8);
+  std::memcpy(sc.vdc_inv, sh.vdc_inv[m - 1].data(), sc.n_vdc_inv * 8);
+  sc.spp = (int32_t)spp;
+  rc->cam = *cam;
+  std::memcpy(rc->filter_table, rp->filter_table, sizeof(rc->filter_table));
+  rc->filter_radius[0] = rp->filter_radius[0];
+  rc->filter_radius[1] = rp->filter_radius[1];
+  rc->inv_filter_radius[0] = 1.f / rp->filter_radius[0];
+  rc->inv_filter_radius[1] = 1.f / rp->filter_radius[1];
+  rc->diff_scale = 1.0f / std::sqrt((float)spp);
+  rc->max_depth = rp->max_depth;
+  rc->rr_threshold = rp->rr_threshold;
+  rc->rr_start_depth = rp->rr_start_depth;
+  rc->rr_enable = rp->rr_enable;
+  rc->sb_min[0] = sbx0;
+  rc->sb_min[1] = sby0;
+  rc->sb_ext[0] = sbx1 - sbx0;
+  rc->sb_ext[1] = sby1 - sby0;
+  const int stride = rp->sample_stride > 0 ? rp->sample_stride : 1;
+  const int phase = ((rp->sample_phase % stride) + stride) % stride;
+  const int s_lo = std::max(rp->sample_begin, 0);
+  const int s_hi = rp->sample_end > 0 ? std::min<int64_t>(rp->sample_end, spp) : (int)spp;
+  int first = s_lo + ((phase - s_lo % stride) + stride) % stride;
+  rc->s_begin = first;
+  rc->s_stride = stride;
+  rc->s_phase = phase;
+  rc->s_count = first < s_hi ? (s_hi - first + stride - 1) / stride : 0;
+  return PTRS_OK;
+}
+
+int32_t ensure_workspace(PtrsScene* s, uint32_t cap, uint32_t rounds) {
+  Workspace& w = s->ws;
+  if (w.cap >= cap && w.rounds >= rounds) return PTRS_OK;
+  cap = std::max(cap, w.cap);
+  rounds = std::max(rounds, w.rounds);
+#define WS_ALLOC(buf, count) \
+  if ((buf).alloc(count) != cudaSuccess) return fail(PTRS_ERR_OUT_OF_MEMORY, "workspace allocation failed")
+  WS_ALLOC(w.ray_o, cap);
+  WS_ALLOC(w.ray_d, cap);
+  WS_ALLOC(w.hit_tb, cap);
+  WS_ALLOC(w.beta, cap);
+  WS_ALLOC(w.L, cap);
+  for (auto& b : w.nee) WS_ALLOC(b, cap);
+  WS_ALLOC(w.hit_prim, cap);
+  WS_ALLOC(w.bounces, cap);
+  WS_ALLOC(w.sobol_index, cap);
+  WS_ALLOC(w.pixel, cap);
+  WS_ALLOC(w.flags, cap);
+  WS_ALLOC(w.p_film, cap);
+  WS_ALLOC(w.q_ext[0], cap);
+  WS_ALLOC(w.q_ext[1], cap);
+  WS_ALLOC(w.q_nee, cap);
+  WS_ALLOC(w.q_class, (size_t)cap * PT_N_CLASSES);
+  WS_ALLOC(w.counters, rounds + 1);
+  WS_ALLOC(w.gcount, 1);
+#undef WS_ALLOC
+  w.cap = cap;
+  w.rounds = rounds;
+  return PTRS_OK;
+}
+
+struct StageTimer {
+  PtrsScene* s;
+  cudaStream_t st;
+  size_t used = 0;
+  std::vector<std::pair<int, size_t>> spans;  // (stage id, first event index)
+  cudaEvent_t next() {
+    if (used == s->stage_events.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      s->stage_events.push_back(e);
+    }
+    return s->stage_events[used++];
+  }
+  void begin(int stage) {
+    spans.emplace_back(stage, used);
+    cudaEventRecord(next(), st);
+  }
+  void end() { cudaEventRecord(next(), st); }
+  void collect(float ms[5]) {  // call after a stream sync
+    for (auto& sp_ : spans) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, s->stage_events[sp_.second], s->stage_events[sp_.second + 1]);
+      ms[sp_.first] += t;
+    }
+    spans.clear();
+    used = 0;
+  }
+};
+enum { ST_GENERATE, ST_EXTEND, ST_SHADE, ST_CONNECT, ST_ACCUMULATE };
+
+// One wavefront batch: `n_work` path slots already described by (work_base | lists); runs rounds until
+// every path has ended.  Leaves per-path radiance in ws.L.
+int32_t run_batch(PtrsScene* s, const RenderConst& rc, uint64_t work_base, uint32_t n_work, const int* d_list_xy, const int* d_list_s,
+                  cudaStream_t st, StageTimer& tm, uint64_t* ext_rays) {
+  Workspace& w = s->ws;
+  PathArrays P = w.arrays();
+  const uint32_t cap = w.cap;
+  const int sm = s->sm_count;
+  CUDA_TRY(cudaMemsetAsync(w.counters.p, 0, (size_t)(w.rounds + 1) * sizeof(RoundCounters), st));
+  tm.begin(ST_GENERATE);
+  launch_generate(st, sm, rc, s->dev.sobol, P, work_base, n_work, d_list_xy, d_list_s, w.q_ext[0].p, w.counters.p);
+  tm.end();
+  s->stats.launches += 1;
+  uint32_t round = 0;
+  const uint32_t planned = (uint32_t)rc.max_depth + 1;
+  std::vector<RoundCounters> host_ctr;
+  for (;;) {
+    const uint32_t upto = std::min(std::max(planned, round + 4), w.rounds);
+    for (; round < upto; ++round) {
+      RoundCounters* c = w.counters.p + round;
+      int* q_in = w.q_ext[round & 1].p;
+      int* q_out = w.q_ext[(round + 1) & 1].p;
+      tm.begin(ST_EXTEND);
+      launch_extend(st, sm, s->count_visits, s->dev, P, q_in, w.q_class.p, cap, c, w.gcount.p);
+      tm.end();
+      tm.begin(ST_SHADE);
+      if (s->dev.n_infinite_lights > 0) {
+        launch_shade_miss(st, sm, s->dev, P, w.q_class.p + (size_t)PT_CLASS_MISS * cap, c);
+        s->stats.launches += 1;
+      }
+#define SHADE(M)                                                                                                               \
+  if (s_has_mat[M]) {                                                                                                          \
+    launch_shade_##M(st, sm, rc, s->dev, P, w.q_class.p + (size_t)(M)*cap, q_out, w.q_nee.p, c, c + 1);                        \
+    s->stats.launches += 1;                                                                                                    \
+  }
+      const bool* s_has_mat = s->has_mat;
+      SHADE(0) SHADE(1) SHADE(2) SHADE(3) SHADE(4) SHADE(5)
+#undef SHADE
+      tm.end();
+      tm.begin(ST_CONNECT);
+      if (s->dev.n_lights > 0) {
+        launch_connect(st, sm, s->count_visits, s->dev, P, w.q_nee.p, c, w.gcount.p);
+        s->stats.launches += 1;
+      }
+      tm.end();
+      s->stats.launches += 1;
+    }
+    // all planned rounds are enqueued: read the queue lengths back once (also the ray statistics)
+    host_ctr.resize(round + 1);
+    CUDA_TRY(cudaMemcpyAsync(host_ctr.data(), w.counters.p, (size_t)(round + 1) * sizeof(RoundCounters), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (host_ctr[round].n_ext == 0 || round >= w.rounds) break;  // only null-BSDF chains need extra rounds
+  }
+  for (uint32_t r = 0; r < round; ++r) *ext_rays += host_ctr[r].n_ext;
+  if (host_ctr[round].n_ext != 0) return fail(PTRS_ERR_UNSUPPORTED, "paths still alive after the maximum number of wavefront rounds");
+  return PTRS_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int32_t ptrs_abi_version(void) { return PTRS_ABI_VERSION; }
+const char* ptrs_last_error(void) { return g_err.c_str(); }
+
+int32_t ptrs_device_count(int32_t* count) {
+  int n = 0;
+  CUDA_TRY(cudaGetDeviceCount(&n));
+  *count = n;
+  return PTRS_OK;
+}
+int32_t ptrs_set_device(int32_t device) {
+  CUDA_TRY(cudaSetDevice(device));
+  return PTRS_OK;
+}
+
+int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) {
+  if (!d || !out) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  if (d->abi_version != PTRS_ABI_VERSION) return fail(PTRS_ERR_INVALID_ARGUMENT, "PtrsSceneDesc.abi_version mismatch");
+  if (d->n_prims > 0 && (!d->nodes || !d->prim_vertex || !d->prim_mesh || !d->prim_material || !d->prim_area_light || !d->pos || !d->meshes))
+    return fail(PTRS_ERR_INVALID_ARGUMENT, "missing geometry arrays");
+  const SobolHost& sh = sobol_host();
+  if (!sh.ok) return fail(PTRS_ERR_INVALID_ARGUMENT, "embedded Sobol tables are corrupt");
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  std::unique_ptr<PtrsScene> s(new PtrsScene());
+  s->device = dev;
+  CUDA_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev));
+  // validate indices once on the host so that the kernels can trust them
+  for (uint32_t i = 0; i < d->n_prims; ++i) {
+    if (d->prim_mesh[i] < 0 || (uint32_t)d->prim_mesh[i] >= d->n_meshes || d->prim_material[i] < 0 ||
+        (uint32_t)d->prim_material[i] >= d->n_materials || d->prim_area_light[i] >= (int32_t)d->n_lights)
+      return fail(PTRS_ERR_INVALID_ARGUMENT, "primitive references an out-of-range mesh / material / light");
+    for (int k = 0; k < 3; ++k)
+      if (d->prim_vertex[3 * (size_t)i + k] >= d->n_verts) return fail(PTRS_ERR_INVALID_ARGUMENT, "vertex index out of range");
+  }
+  for (uint32_t i = 0; i < d->n_nodes; ++i) {
+    const PtrsBvhNode& n = d->nodes[i];
+    if (n.n_prims > 0 ? (uint64_t)n.offset + n.n_prims > d->n_prims : (n.offset >= d->n_nodes || i + 1 >= d->n_nodes || n.axis > 2))
+      return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH node");
+  }
+  for (uint32_t i = 0; i < d->n_materials; ++i) {
+    const PtrsMaterial& m = d->materials[i];
+    if (m.type < 0 || m.type >= PTRS_MAT_COUNT) return fail(PTRS_ERR_UNSUPPORTED, "unknown material type");
+    s->has_mat[m.type] = true;
+    static const int n_tex[PTRS_MAT_COUNT] = {1, 0, 3, 5, 4, 4};
+    for (int k = 0; k < n_tex[m.type]; ++k)
+      if (m.tex[k] < 0 || (uint32_t)m.tex[k] >= d->n_textures) return fail(PTRS_ERR_INVALID_ARGUMENT, "material texture id out of range");
+    if (m.normal_map >= (int32_t)d->n_textures) return fail(PTRS_ERR_INVALID_ARGUMENT, "normal map id out of range");
+  }
+  for (uint32_t i = 0; i < d->n_textures; ++i)
+    if (d->textures[i].type == PTRS_TEX_IMAGE && (d->textures[i].mip < 0 || (uint32_t)d->textures[i].mip >= d->n_mipmaps))
+      return fail(PTRS_ERR_INVALID_ARGUMENT, "image texture without a MIP pyramid");
+  for (uint32_t i = 0; i < d->n_lights; ++i) {
+    const PtrsLight& l = d->lights[i];
+    if (l.type < 0 || l.type > PTRS_LIGHT_INFINITE) return fail(PTRS_ERR_UNSUPPORTED, "unknown light type");
+    if (l.type == PTRS_LIGHT_AREA && (l.prim < 0 || (uint32_t)l.prim >= d->n_prims || l.ke_tex < 0 || (uint32_t)l.ke_tex >= d->n_textures))
+      return fail(PTRS_ERR_INVALID_ARGUMENT, "area light references an out-of-range primitive / texture");
+    if (l.type == PTRS_LIGHT_INFINITE && (l.env < 0 || (uint32_t)l.env >= d->n_envs)) return fail(PTRS_ERR_INVALID_ARGUMENT, "env id out of range");
+  }
+
+  // re-layout: nodes verbatim (32 B), triangles as 3 x float4 with metadata in .w
+  CUDA_TRY(s->nodes.upload(reinterpret_cast<const float4*>(d->nodes), (size_t)d->n_nodes * 2));
+  {
+    std::vector<float4> tv((size_t)d->n_prims * 3);
+    std::vector<uint4> ti(d->n_prims);
+    for (uint32_t i = 0; i < d->n_prims; ++i) {
+      const PtrsMesh& m = d->meshes[d->prim_mesh[i]];
+      uint32_t meta2 = m.flags & 0xffu;
+      if (m.alpha_tex >= 0) meta2 |= PT_TRI_ALPHA_BIT | ((uint32_t)m.alpha_tex << 9);
+      const int32_t w[3] = {d->prim_material[i], d->prim_area_light[i], (int32_t)meta2};
+      for (int k = 0; k < 3; ++k) {
+        const uint32_t v = d->prim_vertex[3 * (size_t)i + k];
+        float4 f;
+        f.x = d->pos[3 * (size_t)v];
+        f.y = d->pos[3 * (size_t)v + 1];
+        f.z = d->pos[3 * (size_t)v + 2];
+        std::memcpy(&f.w, &w[k], 4);
+        tv[3 * (size_t)i + k] = f;
+      }
+      ti[i] = make_uint4(d->prim_vertex[3 * (size_t)i], d->prim_vertex[3 * (size_t)i + 1], d->prim_vertex[3 * (size_t)i + 2],
+                         (uint32_t)d->prim_mesh[i]);
+    }
+    CUDA_TRY(s->tri_verts.upload(tv.data(), tv.size()));
+    CUDA_TRY(s->tri_index.upload(ti.data(), ti.size()));
+  }
+  if (d->normal) CUDA_TRY(s->normal.upload(d->normal, (size_t)d->n_verts * 3));
+  if (d->tangent) CUDA_TRY(s->tangent.upload(d->tangent, (size_t)d->n_verts * 3));
+  if (d->uv) CUDA_TRY(s->uv.upload(d->uv, (size_t)d->n_verts * 2));
+  for (uint32_t i = 0; i < d->n_meshes; ++i) {
+    const uint32_t f = d->meshes[i].flags;
+    if (((f & PTRS_MESH_HAS_NORMAL) && !d->normal) || ((f & PTRS_MESH_HAS_TANGENT) && !d->tangent) || ((f & PTRS_MESH_HAS_UV) && !d->uv))
+      return fail(PTRS_ERR_INVALID_ARGUMENT, "mesh flags name an attribute pool that is NULL");
+  }
+  CUDA_TRY(s->meshes.upload(d->meshes, d->n_meshes));
+  CUDA_TRY(s->materials.upload(d->materials, d->n_materials));
+  CUDA_TRY(s->textures.upload(d->textures, d->n_textures));
+  CUDA_TRY(s->mipmaps.upload(d->mipmaps, d->n_mipmaps));
+  CUDA_TRY(s->texels.upload(d->texels, d->n_texels));
+  CUDA_TRY(s->lights.upload(d->lights, d->n_lights));
+  CUDA_TRY(s->infinite_lights.upload(d->infinite_lights, d->n_infinite_lights));
+  {
+    std::vector<DevEnv> envs(d->n_envs);
+    s->env_arrays.resize((size_t)d->n_envs * 5);
+    for (uint32_t i = 0; i < d->n_envs; ++i) {
+      const PtrsEnvLight& e = d->envs[i];
+      if (e.nu <= 0 || e.nv <= 0 || !e.cond_func || !e.cond_cdf || !e.cond_func_int || !e.marg_func || !e.marg_cdf || e.mip < 0 ||
+          (uint32_t)e.mip >= d->n_mipmaps)
+        return fail(PTRS_ERR_INVALID_ARGUMENT, "incomplete env light");
+      DevEnv& o = envs[i];
+      std::memcpy(o.light_to_world, e.light_to_world, 64);
+      std::memcpy(o.world_to_light, e.world_to_light, 64);
+      o.mip = e.mip;
+      o.nu = e.nu;
+      o.nv = e.nv;
+      o.marg_func_int = e.marg_func_int;
+      DevBuf<float>* a = &s->env_arrays[(size_t)i * 5];
+      CUDA_TRY(a[0].upload(e.cond_func, (size_t)e.nu * e.nv));
+      CUDA_TRY(a[1].upload(e.cond_cdf, (size_t)(e.nu + 1) * e.nv));
+      CUDA_TRY(a[2].upload(e.cond_func_int, e.nv));
+      CUDA_TRY(a[3].upload(e.marg_func, e.nv));
+      CUDA_TRY(a[4].upload(e.marg_cdf, (size_t)e.nv + 1));
+      o.cond_func = a[0].p;
+      o.cond_cdf = a[1].p;
+      o.cond_func_int = a[2].p;
+      o.marg_func = a[3].p;
+      o.marg_cdf = a[4].p;
+      s->scene_bytes += ((size_t)e.nu * e.nv * 2 + e.nv * 4 + 1) * 4;
+    }
+    CUDA_TRY(s->envs.upload(envs.data(), envs.size()));
+  }
+  CUDA_TRY(s->sobol.upload(sh.matrices, (size_t)sh.n_dims * sh.n_cols));
+  CUDA_TRY(s->ticket.alloc(4));
+  CUDA_TRY(s->gcount.alloc(1));
+  DevScene& v = s->dev;
+  v.nodes = s->nodes.p;
+  v.tri_verts = s->tri_verts.p;
+  v.tri_index = s->tri_index.p;
+  v.normal = s->normal.p;
+  v.tangent = s->tangent.p;
+  v.uv = s->uv.p;
+  v.meshes = s->meshes.p;
+  v.materials = s->materials.p;
+  v.textures = s->textures.p;
+  v.mipmaps = s->mipmaps.p;
+  v.texels = s->texels.p;
+  v.lights = s->lights.p;
+  v.infinite_lights = s->infinite_lights.p;
+  v.envs = s->envs.p;
+  v.sobol = s->sobol.p;
+  v.n_nodes = d->n_nodes;
+  v.n_prims = d->n_prims;
+  v.n_lights = d->n_lights;
+  v.n_infinite_lights = d->n_infinite_lights;
+  if (d->n_nodes > 0) {
+    std::memcpy(s->world_bound, d->nodes[0].bounds_min, 12);
+    std::memcpy(s->world_bound + 3, d->nodes[0].bounds_max, 12);
+  }
+  s->scene_bytes += (uint64_t)d->n_nodes * 32 + (uint64_t)d->n_prims * 64 + (uint64_t)d->n_verts * 4 * ((d->normal ? 3 : 0) + (d->tangent ? 3 : 0) + (d->uv ? 2 : 0)) +
+                    d->n_texels * 4 + (uint64_t)sh.n_dims * sh.n_cols * 4;
+  CUDA_TRY(cudaEventCreate(&s->ev[0]));
+  CUDA_TRY(cudaEventCreate(&s->ev[1]));
+  CUDA_TRY(cudaDeviceSynchronize());
+  *out = s.release();
+  return PTRS_OK;
+}
+
+int32_t ptrs_scene_destroy(PtrsScene* scene) {
+  if (!scene) return PTRS_OK;
+  cudaSetDevice(scene->device);
+  cudaDeviceSynchronize();
+  delete scene;
+  return PTRS_OK;
+}
+
+int32_t ptrs_scene_world_bound(const PtrsScene* scene, float out[6]) {
+  if (!scene || !out) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  std::memcpy(out, scene->world_bound, 24);
+  return PTRS_OK;
+}
+uint64_t ptrs_scene_device_bytes(const PtrsScene* scene) { return scene ? scene->scene_bytes + scene->ws.bytes() : 0; }
+
+// ---- intersect -----------------------------------------------------------------------------------
+static int32_t do_intersect(PtrsScene* s, const PtrsRay* d_rays, size_t n, PtrsHit* d_hits, uint8_t* d_occ, bool any_hit, bool count,
+                                cudaStream_t st) {
+  if (n > 0xfffffff0ull) return fail(PTRS_ERR_INVALID_ARGUMENT, "too many rays in one call");
+  CUDA_TRY(cudaMemsetAsync(s->ticket.p, 0, 16, st));
+  if (count) CUDA_TRY(cudaMemsetAsync(s->gcount.p, 0, sizeof(GlobalCounters), st));
+  launch_intersect(st, s->sm_count, any_hit, count, s->dev, d_rays, (uint32_t)n, d_hits, d_occ, s->ticket.p, s->gcount.p);
+  CUDA_TRY(cudaGetLastError());
+  return PTRS_OK;
+}
+
+int32_t ptrs_intersect_device(PtrsScene* scene, const PtrsRay* d_rays, size_t n, PtrsHit* d_hits, void* stream) {
+  if (!scene || (n && (!d_rays || !d_hits))) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  if (n == 0) return PTRS_OK;
+  return do_intersect(scene, d_rays, n, d_hits, nullptr, false, false, (cudaStream_t)stream);
+}
+int32_t ptrs_intersect_p_device(PtrsScene* scene, const PtrsRay* d_rays, size_t n, uint8_t* d_occ, void* stream) {
+  if (!scene || (n && (!d_rays || !d_occ))) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  if (n == 0) return PTRS_OK;
+  return do_intersect(scene, d_rays, n, nullptr, d_occ, true, false, (cudaStream_t)stream);
+}
+int32_t ptrs_intersect_counted_device(PtrsScene* scene, const PtrsRay* d_rays, size_t n, PtrsHit* d_hits, int32_t any_hit, uint8_t* d_occ,
+                                      uint64_t* nodes_tested, uint64_t* tris_tested, void* stream) {
+  if (!scene || (n && !d_rays) || (n && (any_hit ? !d_occ : !d_hits))) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  GlobalCounters g{};
+  if (n) {
+    int32_t rc = do_intersect(scene, d_rays, n, d_hits, d_occ, any_hit != 0, true, (cudaStream_t)stream);
+    if (rc != PTRS_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(&g, scene->gcount.p, sizeof(g), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  }
+  if (nodes_tested) *nodes_tested = g.nodes_tested;
+  if (tris_tested) *tris_tested = g.tris_tested;
+  return PTRS_OK;
+}
+
+int32_t ptrs_intersect(PtrsScene* scene, const PtrsRay* rays, size_t n, PtrsHit* hits) {
+  if (!scene || (n && (!rays || !hits))) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  if (n == 0) return PTRS_OK;
+  DevBuf<PtrsRay> dr;
+  DevBuf<PtrsHit> dh;
+  CUDA_TRY(dr.upload(rays, n));
+  CUDA_TRY(dh.alloc(n));
+  int32_t rc = do_intersect(scene, dr.p, n, dh.p, nullptr, false, false, 0);
+  if (rc != PTRS_OK) return rc;
+  CUDA_TRY(cudaMemcpy(hits, dh.p, n * sizeof(PtrsHit), cudaMemcpyDeviceToHost));
+  return PTRS_OK;
+}
+int32_t ptrs_intersect_p(PtrsScene* scene, const PtrsRay* rays, size_t n, uint8_t* occluded) {
+  if (!scene || (n && (!rays || !occluded))) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  if (n == 0) return PTRS_OK;
+  DevBuf<PtrsRay> dr;
+  DevBuf<uint8_t> dh;
+  CUDA_TRY(dr.upload(rays, n));
+  CUDA_TRY(dh.alloc(n));
+  int32_t rc = do_intersect(scene, dr.p, n, nullptr, dh.p, true, false, 0);
+  if (rc != PTRS_OK) return rc;
+  CUDA_TRY(cudaMemcpy(occluded, dh.p, n, cudaMemcpyDeviceToHost));
+  return PTRS_OK;
+}
+
+// ---- film ----------------------------------------------------------------------------------------
+int32_t ptrs_film_create(int32_t width, int32_t height, PtrsFilm** out) {
+  if (!out || width <= 0 || height <= 0) return fail(PTRS_ERR_INVALID_ARGUMENT, "bad film size");
+  std::unique_ptr<PtrsFilm> f(new PtrsFilm());
+  f->width = width;
+  f->height = height;
+  f->owned = true;
+  CUDA_TRY(cudaMalloc(&f->d, (size_t)width * height * sizeof(float4)));
+  CUDA_TRY(cudaMemset(f->d, 0, (size_t)width * height * sizeof(float4)));
+  *out = f.release();
+  return PTRS_OK;
+}
+int32_t ptrs_film_wrap_device(int32_t width, int32_t height, float* d_rgbw, PtrsFilm** out) {
+  if (!out || !d_rgbw || width <= 0 || height <= 0 || ((uintptr_t)d_rgbw & 15)) return fail(PTRS_ERR_INVALID_ARGUMENT, "bad film buffer (needs 16-byte alignment)");
+  PtrsFilm* f = new PtrsFilm();
+  f->width = width;
+  f->height = height;
+  f->d = reinterpret_cast<float4*>(d_rgbw);
+  f->owned = false;
+  *out = f;
+  return PTRS_OK;
+}
+int32_t ptrs_film_destroy(PtrsFilm* film) {
+  if (!film) return PTRS_OK;
+  if (film->owned && film->d) cudaFree(film->d);
+  delete film;
+  return PTRS_OK;
+}
+int32_t ptrs_film_clear(PtrsFilm* film, void* stream) {
+  if (!film) return fail(PTRS_ERR_INVALID_ARGUMENT, "null film");
+  CUDA_TRY(cudaMemsetAsync(film->d, 0, (size_t)film->width * film->height * sizeof(float4), (cudaStream_t)stream));
+  return PTRS_OK;
+}
+int32_t ptrs_film_download(PtrsFilm* film, float* rgbw) {
+  if (!film || !rgbw) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  CUDA_TRY(cudaMemcpy(rgbw, film->d, (size_t)film->width * film->height * sizeof(float4), cudaMemcpyDeviceToHost));
+  return PTRS_OK;
+}
+int32_t ptrs_film_resolve(PtrsFilm* film, float* rgb) {
+  if (!film || !rgb) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  const uint32_t n = (uint32_t)film->width * film->height;
+  DevBuf<float> d;
+  CUDA_TRY(d.alloc((size_t)n * 3));
+  launch_resolve(0, film->d, n, d.p, nullptr);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(rgb, d.p, (size_t)n * 12, cudaMemcpyDeviceToHost));
+  return PTRS_OK;
+}
+int32_t ptrs_film_resolve_srgb8(PtrsFilm* film, uint8_t* rgba) {
+  if (!film || !rgba) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  const uint32_t n = (uint32_t)film->width * film->height;
+  DevBuf<uint8_t> d;
+  CUDA_TRY(d.alloc((size_t)n * 4));
+  launch_resolve(0, film->d, n, nullptr, d.p);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(rgba, d.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return PTRS_OK;
+}
+float* ptrs_film_device_ptr(PtrsFilm* film) { return film ? reinterpret_cast<float*>(film->d) : nullptr; }
+
+int32_t ptrs_film_sample_bounds(int32_t width, int32_t height, const float r[2], int32_t out[4]) {
+  if (!r || !out) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  out[0] = (int)std::floor(0.5f - r[0]);
+  out[1] = (int)std::floor(0.5f - r[1]);
+  out[2] = (int)std::ceil((float)width - 0.5f + r[0]);
+  out[3] = (int)std::ceil((float)height - 0.5f + r[1]);
+  return PTRS_OK;
+}
+
+// ---- integrator ----------------------------------------------------------------------------------
+int32_t ptrs_render_params_default(PtrsRenderParams* p) {
+  if (!p) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  std::memset(p, 0, sizeof(*p));
+  p->spp = 1;
+  p->max_depth = 15;
+  p->rr_threshold = 1.0f;  // integrator.rs:240-242
+  p->rr_start_depth = 3;
+  p->rr_enable = 1;
+  p->sample_stride = 1;
+  p->filter_radius[0] = p->filter_radius[1] = 2.0f;  // GuassianFilter::new(2.), common/mod.rs:59, filter.rs:68-75
+  const float alpha = 2.0f, radius = 2.0f;
+  const float expv = std::exp(-alpha * radius * radius);
+  int off = 0;
+  for (int y = 0; y < 16; ++y)
+    for (int x = 0; x < 16; ++x) {  // Film::new, film.rs:135-144
+      float px = ((float)x + 0.5f) * radius / 16.0f, py = ((float)y + 0.5f) * radius / 16.0f;
+      float gx = std::fmax(0.0f, std::exp(-alpha * px * px) - expv), gy = std::fmax(0.0f, std::exp(-alpha * py * py) - expv);
+      p->filter_table[off++] = gx * gy;
+    }
+  return PTRS_OK;
+}
+
+static int32_t render_impl(PtrsScene* s, const PtrsCamera* cam, const PtrsRenderParams* rp, PtrsFilm* film, const int32_t* list_xy,
+                           const int32_t* list_s, size_t n_list, float* out_rgb, cudaStream_t st) {
+  RenderConst rc;
+  std::string why;
+  int32_t r = build_render_const(cam, rp, &rc, &why);
+  if (r != PTRS_OK) return fail(r, why);
+  CUDA_TRY(cudaSetDevice(s->device));
+  const uint32_t bw = ((uint32_t)rc.sb_ext[0] + 7u) >> 3, bh = ((uint32_t)rc.sb_ext[1] + 3u) >> 2;
+  const uint64_t per_sample = (uint64_t)bw * bh * 32u;
+  const uint64_t total = list_xy ? (uint64_t)n_list : per_sample * (uint64_t)rc.s_count;
+  uint32_t cap = rp->paths_per_batch > 0 ? (uint32_t)rp->paths_per_batch : (1u << 22);
+  cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((cap + 31u) & ~31u, 32u), std::max<uint64_t>((total + 31) & ~31ull, 32));
+  const uint32_t rounds = (uint32_t)rc.max_depth + 1 + 32;
+  r = ensure_workspace(s, cap, rounds);
+  if (r != PTRS_OK) return r;
+  rc.cap = s->ws.cap;
+  s->stats = PtrsStats{};
+  CUDA_TRY(cudaMemsetAsync(s->ws.gcount.p, 0, sizeof(GlobalCounters), st));
+  DevBuf<int> d_xy, d_s;
+  DevBuf<float4> d_dummy;
+  if (list_xy) {
+    CUDA_TRY(d_xy.upload(list_xy, n_list * 2));
+    CUDA_TRY(d_s.upload(list_s, n_list));
+  }
+  StageTimer tm{s, st};
+  float ms[5] = {0, 0, 0, 0, 0};
+  uint64_t ext_rays = 0, paths = 0;
+  CUDA_TRY(cudaEventRecord(s->ev[0], st));
+  for (uint64_t base = 0; base < total; base += s->ws.cap) {
+    const uint32_t n_work = (uint32_t)std::min<uint64_t>(s->ws.cap, total - base);
+    r = run_batch(s, rc, base, n_work, list_xy ? d_xy.p + 2 * base : nullptr, list_xy ? d_s.p + base : nullptr, st, tm, &ext_rays);
+    if (r != PTRS_OK) return r;
+    if (film) {
+      tm.begin(ST_ACCUMULATE);
+      launch_accumulate(st, s->sm_count, rc, s->ws.arrays(), n_work, film->d);
+      tm.end();
+      s->stats.launches += 1;
+    }
+    if (out_rgb) {
+      std::vector<float4> l(n_work);
+      CUDA_TRY(cudaMemcpyAsync(l.data(), s->ws.L.p, (size_t)n_work * 16, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      for (uint32_t i = 0; i < n_work; ++i) {
+        out_rgb[3 * (base + i)] = l[i].x;
+        out_rgb[3 * (base + i) + 1] = l[i].y;
+        out_rgb[3 * (base + i) + 2] = l[i].z;
+      }
+    }
+    s->stats.batches += 1;
+  }
+  CUDA_TRY(cudaEventRecord(s->ev[1], st));
+  GlobalCounters g{};
+  CUDA_TRY(cudaMemcpyAsync(&g, s->ws.gcount.p, sizeof(g), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  tm.collect(ms);
+  float total_ms = 0.f;
+  cudaEventElapsedTime(&total_ms, s->ev[0], s->ev[1]);
+  // camera paths = valid (pixel, sample) pairs; 8x4 block padding outside the sample bounds is not counted
+  paths = list_xy ? n_list : (uint64_t)rc.sb_ext[0] * rc.sb_ext[1] * (uint64_t)rc.s_count;
+  s->stats.camera_paths = paths;
+  s->stats.extension_rays = ext_rays;
+  s->stats.shadow_rays = g.shadow_rays;
+  s->stats.mis_rays = g.mis_rays;
+  s->stats.nodes_tested = g.nodes_tested;
+  s->stats.tris_tested = g.tris_tested;
+  s->stats.ms_generate = ms[ST_GENERATE];
+  s->stats.ms_extend = ms[ST_EXTEND];
+  s->stats.ms_shade = ms[ST_SHADE];
+  s->stats.ms_shadow = ms[ST_CONNECT];
+  s->stats.ms_accumulate = ms[ST_ACCUMULATE];
+  s->stats.ms_total = total_ms;
+  return PTRS_OK;
+}
+
+int32_t ptrs_render(PtrsScene* scene, const PtrsCamera* camera, const PtrsRenderParams* params, PtrsFilm* film, void* stream) {
+  if (!scene || !camera || !params || !film) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  if (film->width != camera->width || film->height != camera->height) return fail(PTRS_ERR_INVALID_ARGUMENT, "film / camera resolution mismatch");
+  return render_impl(scene, camera, params, film, nullptr, nullptr, 0, nullptr, (cudaStream_t)stream);
+}
+
+int32_t ptrs_path_radiance(PtrsScene* scene, const PtrsCamera* camera, const PtrsRenderParams* params, const int32_t* pixels_xy,
+                           const int32_t* sample_nums, size_t n, float* out_rgb) {
+  if (!scene || !camera || !params || (n && (!pixels_xy || !sample_nums || !out_rgb))) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  if (n == 0) return PTRS_OK;
+  return render_impl(scene, camera, params, nullptr, pixels_xy, sample_nums, n, out_rgb, 0);
+}
+
+int32_t ptrs_stats(const PtrsScene* scene, PtrsStats* out) {
+  if (!scene || !out) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  *out = scene->stats;
+  return PTRS_OK;
+}
+int32_t ptrs_set_stats_mode(PtrsScene* scene, int32_t count_visits) {
+  if (!scene) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  scene->count_visits = count_visits != 0;
+  return PTRS_OK;
+}
+
+// ---- parity probes ---------------------------------------------------------------------------------
+int32_t ptrs_sobol_samples(const PtrsCamera* camera, const PtrsRenderParams* params, const int32_t* pixels_xy, const int32_t* sample_nums,
+                           size_t n, const int32_t* dims, size_t n_dims, float* out, uint64_t* out_index) {
+  if (!camera || !params || (n && (!pixels_xy || !sample_nums || !dims || !out))) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  if (n == 0 || n_dims == 0) return PTRS_OK;
+  for (size_t k = 0; k < n_dims; ++k)
+    if (dims[k] < 0 || dims[k] >= 1024) return fail(PTRS_ERR_INVALID_ARGUMENT, "dimension out of range");
+  RenderConst rc;
+  std::string why;
+  int32_t r = build_render_const(camera, params, &rc, &why);
+  if (r != PTRS_OK) return fail(r, why);
+  const SobolHost& sh = sobol_host();
+  DevBuf<uint32_t> tab;
+  DevBuf<int> d_xy, d_s, d_dims;
+  DevBuf<float> d_out;
+  DevBuf<uint64_t> d_idx;
+  CUDA_TRY(tab.upload(sh.matrices, (size_t)sh.n_dims * sh.n_cols));
+  CUDA_TRY(d_xy.upload(pixels_xy, n * 2));
+  CUDA_TRY(d_s.upload(sample_nums, n));
+  CUDA_TRY(d_dims.upload(dims, n_dims));
+  CUDA_TRY(d_out.alloc(n * n_dims));
+  CUDA_TRY(d_idx.alloc(n));
+  launch_sobol_probe(0, rc, tab.p, d_xy.p, d_s.p, (uint32_t)n, d_dims.p, (uint32_t)n_dims, d_out.p, d_idx.p);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(out, d_out.p, n * n_dims * 4, cudaMemcpyDeviceToHost));
+  if (out_index) CUDA_TRY(cudaMemcpy(out_index, d_idx.p, n * 8, cudaMemcpyDeviceToHost));
+  return PTRS_OK;
+}
+
+int32_t ptrs_generate_rays(const PtrsCamera* camera, const PtrsRenderParams* params, const int32_t* pixels_xy, const int32_t* sample_nums,
+                           size_t n, PtrsRay* rays, float* p_film, float* rxry_dir) {
+  if (!camera || !params || (n && (!pixels_xy || !sample_nums || !rays))) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  if (n == 0) return PTRS_OK;
+  RenderConst rc;
+  std::string why;
+  int32_t r = build_render_const(camera, params, &rc, &why);
+  if (r != PTRS_OK) return fail(r, why);
+  const SobolHost& sh = sobol_host();
+  DevBuf<uint32_t> tab;
+  DevBuf<int> d_xy, d_s;
+  DevBuf<PtrsRay> d_rays;
+  DevBuf<float> d_pf, d_rx;
+  CUDA_TRY(tab.upload(sh.matrices, (size_t)sh.n_dims * sh.n_cols));
+  CUDA_TRY(d_xy.upload(pixels_xy, n * 2));
+  CUDA_TRY(d_s.upload(sample_nums, n));
+  CUDA_TRY(d_rays.alloc(n));
+  CUDA_TRY(d_pf.alloc(n * 2));
+  CUDA_TRY(d_rx.alloc(n * 6));
+  launch_ray_probe(0, rc, tab.p, d_xy.p, d_s.p, (uint32_t)n, d_rays.p, d_pf.p, d_rx.p);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(rays, d_rays.p, n * sizeof(PtrsRay), cudaMemcpyDeviceToHost));
+  if (p_film) CUDA_TRY(cudaMemcpy(p_film, d_pf.p, n * 8, cudaMemcpyDeviceToHost));
+  if (rxry_dir) CUDA_TRY(cudaMemcpy(rxry_dir, d_rx.p, n * 24, cudaMemcpyDeviceToHost));
+  return PTRS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+// Wavefront path-tracing kernels for sm_100a: generate / extend / shade<material> / connect /
+// accumulate, plus the standalone closest-hit / any-hit kernels behind ptrs_intersect*.
+//
+// Execution model
+//   * every kernel is persistent: grid = k x 148 SMs, each warp pulls 32 work items at a time from
+//     a device-side ticket with ONE atomicAdd per warp (warp-aggregated fetch) until the queue whose
+//     length sits in device memory is drained — no host round trip between bounces
+//   * queues hold path-slot indices; extend classifies hits by material type and appends to one
+//     queue per material class with ballot-aggregated atomics (one atomic per class per warp), so
+//     every shade<MAT> launch runs warps that are uniform in material code (material sorting)
+//   * shade emits at most three rays per path and bounce — the extension ray into the next round's
+//     extend queue, the NEE shadow segment and the MIS ray into the connect queue
+//   * connect traces the shadow (any-hit) and MIS (closest-hit) rays of a path in ONE thread and adds
+//     beta * n_lights * (Ld_light + Ld_bsdf) to the path's radiance: a single writer per path per
+//     launch keeps the float summation order of integrator.rs:443-447 (deterministic images)
+//   * per-round counters (queue lengths, tickets) live in one zero-initialised block per batch
+//
+// Path state is SoA in HBM, 16-byte fields, so every access is one 128-bit load/store.
+#pragma once
+#include "dev_shading.cuh"
+#include "dev_sobol.cuh"
+
+namespace ptrs {
+
+#define PT_N_CLASSES (PTRS_MAT_COUNT + 1)  // material types + "miss"
+#define PT_CLASS_MISS PTRS_MAT_COUNT
+
+struct PathArrays {
+  float4* ray_o;  // xyz
+  float4* ray_d;  // xyz
+  int* hit_prim;
+  float4* hit_tb;  // t, b0, b1, b2
+  float4* beta;    // rgb, eta_scale
+  float4* L;       // rgb
+  uint64_t* sobol_index;
+  int2* pixel;
+  int* bounces;
+  uint32_t* flags;  // bits 0..15 sobol dimension, PT_F_*
+  float2* p_film;
+  // pending direct-lighting record of the current bounce (estimate_direct, integrator.rs:23-139)
+  float4* nee0;  // shadow origin xyz,            A.r   (A = f * Li * w / light_pdf)
+  float4* nee1;  // shadow segment xyz,           A.g
+  float4* nee2;  // MIS ray origin xyz,           A.b
+  float4* nee3;  // MIS ray dir xyz,              bits: light id | PT_NEE_*
+  float4* nee4;  // f (already * |wi.ns|) rgb,     MIS weight
+  float4* nee5;  // beta before the bounce rgb,   scattering pdf
+};
+#define PT_F_SPECULAR (1u << 16)
+#define PT_F_HAS_DIFF (1u << 17)
+#define PT_NEE_SHADOW (1u << 30)
+#define PT_NEE_MIS (1u << 31)
+
+// per-round device counters; one RoundCounters per extend/shade/connect round of a batch
+struct RoundCounters {
+  uint32_t n_ext;                  // length of the extend queue of this round
+  uint32_t n_class[PT_N_CLASSES];  // lengths of the per-material shade queues
+  uint32_t n_nee;                  // length of the connect queue
+  uint32_t t_ext, t_class[PT_N_CLASSES], t_nee;  // work tickets
+  uint32_t pad[32 - 4 - 2 * PT_N_CLASSES];  // 128 B per round
+};
+
+struct GlobalCounters {
+  unsigned long long shadow_rays, mis_rays, nodes_tested, tris_tested, ext_rays;
+};
+
+struct RenderConst {
+  SobolConfig sobol;
+  PtrsCamera cam;
+  float filter_table[256];
+  float filter_radius[2];
+  float inv_filter_radius[2];
+  float diff_scale;  // 1 / sqrt(spp)
+  int32_t max_depth;
+  float rr_threshold;
+  int32_t rr_start_depth;
+  int32_t rr_enable;
+  int32_t sb_min[2], sb_ext[2];  // sample bounds min and extent
+  int32_t s_begin, s_count, s_stride, s_phase;  // sample numbers: s = s_begin + s_phase' + j * s_stride
+  uint32_t cap;
+};
+
+// ---- work fetch --------------------------------------------------------------------------------------
+PT_DEV uint32_t warp_fetch32(uint32_t* ticket) {
+  uint32_t base = 0;
+  if ((threadIdx.x & 31) == 0) base = atomicAdd(ticket, 32u);
+  return __shfl_sync(0xffffffffu, base, 0);
+}
+// append `item` for lanes with pred to queue q (length counter n) — one atomic per warp
+PT_DEV void warp_push(bool pred, uint32_t item, int* q, uint32_t* n) {
+  const uint32_t mask = __ballot_sync(0xffffffffu, pred);
+  if (mask == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(mask) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(n, (uint32_t)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pred) q[base + __popc(mask & ((1u << lane) - 1))] = (int)item;
+}
+PT_DEV void warp_count(bool pred, unsigned long long* ctr) {
+  const uint32_t mask = __ballot_sync(0xffffffffu, pred);
+  if (mask && (threadIdx.x & 31) == (__ffs(mask) - 1)) atomicAdd(ctr, (unsigned long long)__popc(mask));
+}
+PT_DEV void warp_sum_add(uint32_t v, unsigned long long* ctr) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(ctr, (unsigned long long)v);
+}
+
+// ---- camera ----------------------------------------------------------------------------------------
+PT_DEV V3 quat_rotate(const float q[4], V3 v) {  // UnitQuaternion * Vector3 (nalgebra)
+  V3 qv = mk3(q[0], q[1], q[2]);
+  V3 t = cross(qv, v) * 2.0f;
+  V3 c = cross(qv, t);
+  return t * q[3] + c + v;
+}
+// Camera::generate_ray_differential + scale_differentials (pathtracer/mod.rs:59-81, ray.rs:30-35)
+PT_DEV void camera_ray(const PtrsCamera& cam, float fx, float fy, float diff_scale, V3* o, V3* d, V3* rx_d, V3* ry_d) {
+  const float* m = cam.raster_to_screen;
+  float sx = (m[0] * fx + m[1] * fy) + m[2] * 0.0f + m[3];
+  float sy = (m[4] * fx + m[5] * fy) + m[6] * 0.0f + m[7];
+  float sz = (m[8] * fx + m[9] * fy) + m[10] * 0.0f + m[11];
+  float inverse_denom = cam.persp[3] / (sz + cam.persp[2]);
+  V3 pc = mk3(sx * inverse_denom / cam.persp[0], sy * inverse_denom / cam.persp[1], -inverse_denom);
+  *o = mk3(cam.trans[0], cam.trans[1], cam.trans[2]);
+  *d = normalize(quat_rotate(cam.rot, pc));
+  if (rx_d) {
+    V3 rx = normalize(quat_rotate(cam.rot, pc + mk3(cam.dx_camera[0], cam.dx_camera[1], cam.dx_camera[2])));
+    V3 ry = normalize(quat_rotate(cam.rot, pc + mk3(cam.dy_camera[0], cam.dy_camera[1], cam.dy_camera[2])));
+    *rx_d = *d + (rx - *d) * diff_scale;
+    *ry_d = *d + (ry - *d) * diff_scale;
+  }
+}
+
+}  // namespace ptrs

@@ -1,0 +1,272 @@
+"""ctypes binding of libptrs_b200.so (the C ABI in include/ptrs_b200.h) plus a thin mirror of the
+reference's host-facing interface for this path:
+
+    SamplerBuilder(spp, sample_bounds)            src/pathtracer/sampler/sobol.rs:35
+    PathIntegrator(sampler_builder, max_depth)    src/pathtracer/integrator.rs:230
+    PathIntegrator.preprocess(scene)              src/pathtracer/integrator.rs:250
+    PathIntegrator.render(camera, scene)          src/pathtracer/integrator.rs:536
+    RenderScene.{intersect, intersect_p, world_bound}   src/pathtracer/mod.rs:92-102
+    Film.{clear, get_sample_bounds, to_rgba_image, to_channel_updates}   src/common/film.rs:164-271
+
+There is no CPU fallback: if the library is missing or no CUDA device is usable, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._abi import *  # noqa: F401,F403
+from .host import HIT_DTYPE, RAY_DTYPE, FlatScene, default_render_params
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libptrs_b200.so")
+_LIB = None
+
+EXPORTS = [
+    "ptrs_abi_version", "ptrs_last_error", "ptrs_device_count", "ptrs_set_device", "ptrs_scene_create", "ptrs_scene_destroy",
+    "ptrs_scene_world_bound", "ptrs_scene_device_bytes", "ptrs_intersect", "ptrs_intersect_p", "ptrs_intersect_device",
+    "ptrs_intersect_p_device", "ptrs_intersect_counted_device", "ptrs_film_create", "ptrs_film_wrap_device", "ptrs_film_destroy",
+    "ptrs_film_clear", "ptrs_film_download", "ptrs_film_resolve", "ptrs_film_resolve_srgb8", "ptrs_film_device_ptr",
+    "ptrs_film_sample_bounds", "ptrs_render_params_default", "ptrs_render", "ptrs_path_radiance", "ptrs_stats",
+    "ptrs_set_stats_mode", "ptrs_sobol_samples", "ptrs_generate_rays",
+]
+
+
+class PtrsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ptrs error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} missing: the CUDA library was not built (run __graft_entry__.build()); "
+                               "there is no CPU fallback for this path")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, sz = C.c_void_p, C.c_int32, C.c_size_t
+        fp, i32p, u64p, u8p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)
+        camp, rpp, descp = C.POINTER(PtrsCamera), C.POINTER(PtrsRenderParams), C.POINTER(PtrsSceneDesc)
+        rayp, hitp = C.POINTER(PtrsRay), C.POINTER(PtrsHit)
+        L.ptrs_last_error.restype = C.c_char_p
+        L.ptrs_device_count.argtypes = [i32p]
+        L.ptrs_set_device.argtypes = [i32]
+        L.ptrs_scene_create.argtypes = [descp, C.POINTER(vp)]
+        L.ptrs_scene_destroy.argtypes = [vp]
+        L.ptrs_scene_world_bound.argtypes = [vp, fp]
+        L.ptrs_scene_device_bytes.restype = C.c_uint64
+        L.ptrs_scene_device_bytes.argtypes = [vp]
+        L.ptrs_intersect.argtypes = [vp, rayp, sz, hitp]
+        L.ptrs_intersect_p.argtypes = [vp, rayp, sz, u8p]
+        L.ptrs_intersect_device.argtypes = [vp, vp, sz, vp, vp]
+        L.ptrs_intersect_p_device.argtypes = [vp, vp, sz, vp, vp]
+        L.ptrs_intersect_counted_device.argtypes = [vp, vp, sz, vp, i32, vp, u64p, u64p, vp]
+        L.ptrs_film_create.argtypes = [i32, i32, C.POINTER(vp)]
+        L.ptrs_film_wrap_device.argtypes = [i32, i32, vp, C.POINTER(vp)]
+        L.ptrs_film_destroy.argtypes = [vp]
+        L.ptrs_film_clear.argtypes = [vp, vp]
+        L.ptrs_film_download.argtypes = [vp, fp]
+        L.ptrs_film_resolve.argtypes = [vp, fp]
+        L.ptrs_film_resolve_srgb8.argtypes = [vp, u8p]
+        L.ptrs_film_device_ptr.restype = vp
+        L.ptrs_film_device_ptr.argtypes = [vp]
+        L.ptrs_film_sample_bounds.argtypes = [i32, i32, fp, i32p]
+        L.ptrs_render_params_default.argtypes = [rpp]
+        L.ptrs_render.argtypes = [vp, camp, rpp, vp, vp]
+        L.ptrs_path_radiance.argtypes = [vp, camp, rpp, i32p, i32p, sz, fp]
+        L.ptrs_stats.argtypes = [vp, C.POINTER(PtrsStats)]
+        L.ptrs_set_stats_mode.argtypes = [vp, i32]
+        L.ptrs_sobol_samples.argtypes = [camp, rpp, i32p, i32p, sz, i32p, sz, fp, u64p]
+        L.ptrs_generate_rays.argtypes = [camp, rpp, i32p, i32p, sz, rayp, fp, fp]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise PtrsError(rc, lib().ptrs_last_error().decode())
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def device_count():
+    n = C.c_int32(0)
+    _check(lib().ptrs_device_count(C.byref(n)))
+    return n.value
+
+
+def set_device(i):
+    _check(lib().ptrs_set_device(i))
+
+
+class Film:
+    """W x H x (r, g, b, weight) f32 on the device (src/common/film.rs FilmPixel sums)."""
+
+    def __init__(self, width, height, device_ptr=None):
+        self.width, self.height = width, height
+        h = C.c_void_p()
+        if device_ptr is None:
+            _check(lib().ptrs_film_create(width, height, C.byref(h)))
+        else:
+            _check(lib().ptrs_film_wrap_device(width, height, C.c_void_p(device_ptr), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().ptrs_film_destroy(self._h)
+            self._h = None
+
+    def clear(self, stream=None):  # film.rs:164-172
+        _check(lib().ptrs_film_clear(self._h, C.c_void_p(stream or 0)))
+
+    def get_sample_bounds(self, radius=(2.0, 2.0)):  # film.rs:174-185
+        r = (C.c_float * 2)(*radius)
+        out = (C.c_int32 * 4)()
+        _check(lib().ptrs_film_sample_bounds(self.width, self.height, r, out))
+        return tuple(out)
+
+    def download(self):
+        """Raw (H, W, 4) sums: contrib rgb and filter weight."""
+        out = np.empty((self.height, self.width, 4), dtype=np.float32)
+        _check(lib().ptrs_film_download(self._h, _p(out, C.c_float)))
+        return out
+
+    def to_channel_updates(self):  # film.rs:253-271 -> (H, W, 3) f32
+        out = np.empty((self.height, self.width, 3), dtype=np.float32)
+        _check(lib().ptrs_film_resolve(self._h, _p(out, C.c_float)))
+        return out
+
+    def to_rgba_image(self):  # film.rs:230-251 -> (H, W, 4) u8, sRGB
+        out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        _check(lib().ptrs_film_resolve_srgb8(self._h, _p(out, C.c_uint8)))
+        return out
+
+    @property
+    def device_ptr(self):
+        return lib().ptrs_film_device_ptr(self._h)
+
+
+class RenderScene:
+    """Device copy of a flattened scene (src/pathtracer/mod.rs:84-106)."""
+
+    def __init__(self, flat):
+        desc = flat.desc if isinstance(flat, FlatScene) else flat
+        h = C.c_void_p()
+        _check(lib().ptrs_scene_create(desc, C.byref(h)))
+        self._h = h
+        self.n_lights = desc.contents.n_lights
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ptrs_scene_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def world_bound(self):
+        out = (C.c_float * 6)()
+        _check(lib().ptrs_scene_world_bound(self._h, out))
+        return np.array(out[:3], dtype=np.float32), np.array(out[3:], dtype=np.float32)
+
+    @property
+    def device_bytes(self):
+        return lib().ptrs_scene_device_bytes(self._h)
+
+    def intersect(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+        _check(lib().ptrs_intersect(self._h, _p(rays, PtrsRay), rays.shape[0], _p(hits, PtrsHit)))
+        return hits
+
+    def intersect_p(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        occ = np.empty(rays.shape[0], dtype=np.uint8)
+        _check(lib().ptrs_intersect_p(self._h, _p(rays, PtrsRay), rays.shape[0], _p(occ, C.c_uint8)))
+        return occ
+
+    def intersect_device(self, d_rays, n, d_hits, stream=0):
+        _check(lib().ptrs_intersect_device(self._h, C.c_void_p(d_rays), n, C.c_void_p(d_hits), C.c_void_p(stream)))
+
+    def intersect_p_device(self, d_rays, n, d_occ, stream=0):
+        _check(lib().ptrs_intersect_p_device(self._h, C.c_void_p(d_rays), n, C.c_void_p(d_occ), C.c_void_p(stream)))
+
+    def intersect_counted_device(self, d_rays, n, d_out, any_hit=False, stream=0):
+        nodes, tris = C.c_uint64(0), C.c_uint64(0)
+        _check(lib().ptrs_intersect_counted_device(self._h, C.c_void_p(d_rays), n, None if any_hit else C.c_void_p(d_out), 1 if any_hit else 0,
+                                                   C.c_void_p(d_out) if any_hit else None, C.byref(nodes), C.byref(tris), C.c_void_p(stream)))
+        return nodes.value, tris.value
+
+    def set_stats_mode(self, count_visits):
+        _check(lib().ptrs_set_stats_mode(self._h, 1 if count_visits else 0))
+
+    def stats(self):
+        st = PtrsStats()
+        _check(lib().ptrs_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in PtrsStats._fields_}
+
+    def path_radiance(self, cam, params, pixels, samples):
+        px = np.ascontiguousarray(pixels, dtype=np.int32).reshape(-1, 2)
+        sm = np.ascontiguousarray(samples, dtype=np.int32).reshape(-1)
+        out = np.empty((px.shape[0], 3), dtype=np.float32)
+        _check(lib().ptrs_path_radiance(self._h, C.byref(cam), C.byref(params), _p(px, C.c_int32), _p(sm, C.c_int32), px.shape[0],
+                                        _p(out, C.c_float)))
+        return out
+
+
+class SamplerBuilder:
+    """SobolSamplerBuilder::new(log, spp, sample_bounds) — sampler/sobol.rs:35-62.  The seed is ignored
+    exactly like the reference's `with_seed` (sobol.rs:75-77)."""
+
+    def __init__(self, samples_per_pixel, sample_bounds=None):
+        self.samples_per_pixel = int(samples_per_pixel)
+        self.sample_bounds = sample_bounds
+
+    def with_seed(self, _seed):
+        return self
+
+
+class PathIntegrator:
+    """PathIntegrator::new(log, sampler_builder, max_depth, show_progress_bar) — integrator.rs:230."""
+
+    def __init__(self, sampler_builder, max_depth=15, show_progress_bar=False):
+        self.params = default_render_params(sampler_builder.samples_per_pixel, max_depth)
+        self.show_progress_bar = show_progress_bar
+
+    def preprocess(self, scene):  # integrator.rs:250-258
+        self.too_many_lights = scene.n_lights > 16
+
+    def render(self, camera, scene, film, stream=None, sample_range=None, sample_stride=(1, 0)):
+        """integrator.rs:536 — accumulates into `film` (the reference's camera.film).  sample_range /
+        sample_stride select a shard of the Sobol sample numbers (multi-GPU)."""
+        p = PtrsRenderParams.from_buffer_copy(self.params)
+        if sample_range is not None:
+            p.sample_begin, p.sample_end = sample_range
+        p.sample_stride, p.sample_phase = sample_stride
+        _check(lib().ptrs_render(scene._h, C.byref(camera), C.byref(p), film._h, C.c_void_p(stream or 0)))
+        return scene.stats()
+
+
+def sobol_samples(cam, params, pixels, samples, dims):
+    px = np.ascontiguousarray(pixels, dtype=np.int32).reshape(-1, 2)
+    sm = np.ascontiguousarray(samples, dtype=np.int32).reshape(-1)
+    dm = np.ascontiguousarray(dims, dtype=np.int32)
+    out = np.empty((px.shape[0], dm.shape[0]), dtype=np.float32)
+    idx = np.empty(px.shape[0], dtype=np.uint64)
+    _check(lib().ptrs_sobol_samples(C.byref(cam), C.byref(params), _p(px, C.c_int32), _p(sm, C.c_int32), px.shape[0], _p(dm, C.c_int32),
+                                    dm.shape[0], _p(out, C.c_float), _p(idx, C.c_uint64)))
+    return out, idx
+
+
+def generate_rays(cam, params, pixels, samples):
+    px = np.ascontiguousarray(pixels, dtype=np.int32).reshape(-1, 2)
+    sm = np.ascontiguousarray(samples, dtype=np.int32).reshape(-1)
+    n = px.shape[0]
+    rays = np.empty(n, dtype=RAY_DTYPE)
+    pf = np.empty((n, 2), dtype=np.float32)
+    rxry = np.empty((n, 6), dtype=np.float32)
+    _check(lib().ptrs_generate_rays(C.byref(cam), C.byref(params), _p(px, C.c_int32), _p(sm, C.c_int32), n, _p(rays, PtrsRay),
+                                    _p(pf, C.c_float), _p(rxry, C.c_float)))
+    return rays, pf, rxry

@@ -1,0 +1,205 @@
+"""GPU path vs CPU oracle, through the C ABI (include/ptrs_b200.h).
+
+Parity protocol (BASELINE.json north_star / SURVEY.md §8c):
+  * Sobol samples and indices: bit-exact (integer path)
+  * fixed ray sets: hit primitive ids bit-exact; t and barycentrics within 1e-5 relative (they are in
+    fact bit-identical here because the device code is built without FMA contraction)
+  * node / triangle test counts equal the oracle's (same traversal order)
+  * per-path radiance and converged images: relative MSE < 1e-3 (device libm differs from glibc by ulps)
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5  # north_star: t and barycentrics within 1e-5 relative
+
+
+def _rel_mse(a, b, eps=1e-2):
+    return float(np.mean((a - b) ** 2 / (b ** 2 + eps)))
+
+
+def _pixels(cam, params, n, seed=0):
+    rng = np.random.default_rng(seed)
+    px = np.stack([rng.integers(-2, cam.width + 2, n), rng.integers(-2, cam.height + 2, n)], axis=1).astype(np.int32)
+    sm = rng.integers(0, params.spp, n).astype(np.int32)
+    return px, sm
+
+
+@pytest.mark.parametrize("res,spp", [((512, 512), 16), ((1024, 1024), 64), ((1920, 1080), 256), ((3840, 2160), 1024)])
+def test_sobol_bit_exact(gpu, host, oracle, res, spp):
+    cam = host.look_at_camera((0, 0, 5), (0, 0, 0), (0, 1, 0), 40.0, res[0], res[1])
+    params = host.default_render_params(spp=spp)
+    px, sm = _pixels(cam, params, 4096, seed=res[0])
+    # corners of the sample bounds and the last sample too
+    px[:4] = [[-2, -2], [res[0] + 1, res[1] + 1], [-2, res[1] + 1], [res[0] + 1, -2]]
+    sm[:4] = [0, spp - 1, spp - 1, 0]
+    dims = np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 17, 33, 64, 100, 140, 255, 511, 1023], dtype=np.int32)
+    g, gi = gpu.sobol_samples(cam, params, px, sm, dims)
+    o, oi = oracle.sobol_samples(cam, params, px, sm, dims)
+    assert np.array_equal(gi, oi)
+    assert np.array_equal(g.view(np.uint32), o.view(np.uint32))
+
+
+def test_camera_rays(gpu, host, oracle, cornell):
+    _, cam = cornell
+    params = host.default_render_params(spp=16)
+    px, sm = _pixels(cam, params, 4096, seed=3)
+    gr, gpf, grx = gpu.generate_rays(cam, params, px, sm)
+    orr, opf, orx = oracle.generate_rays(cam, params, px, sm)
+    assert np.array_equal(gpf, opf)
+    assert np.array_equal(gr["o"], orr["o"])
+    assert np.array_equal(gr["d"], orr["d"])  # sqrt and division are IEEE on both sides
+    assert np.array_equal(grx, orx)
+
+
+def _check_hits(g, o):
+    assert np.array_equal(g["prim"], o["prim"]), f"{np.count_nonzero(g['prim'] != o['prim'])} primitive ids differ"
+    hit = o["prim"] >= 0
+    for f in ("t", "b0", "b1", "b2"):
+        assert np.allclose(g[f][hit], o[f][hit], rtol=REL_TOL, atol=0)
+        assert np.array_equal(g[f][hit], o[f][hit]), f"{f} not bit-identical"
+
+
+@pytest.mark.parametrize("scene_name", ["cornell", "field_small", "terrain_small", "atrium_small"])
+def test_intersect_fixed_ray_sets(gpu, host, oracle, request, scene_name):
+    flat, cam = request.getfixturevalue(scene_name)
+    scene = gpu.RenderScene(flat)
+    bmin, bmax = flat.world_bound()
+    sets = {"coherent": host.coherent_rays(cam, 192), "incoherent": host.incoherent_rays(bmin, bmax, 42, 40000)}
+    for name, rays in sets.items():
+        g = scene.intersect(rays)
+        o, (nodes, tris) = oracle.intersect(flat, rays)
+        _check_hits(g, o)
+        gp = scene.intersect_p(rays)
+        op, _ = oracle.intersect_p(flat, rays)
+        assert np.array_equal(gp, op)
+        assert np.array_equal(gp != 0, o["prim"] >= 0)  # any-hit with t_max = inf agrees with closest-hit
+    scene.close()
+
+
+def test_intersect_edge_cases(gpu, host, oracle, cornell):
+    flat, cam = cornell
+    scene = gpu.RenderScene(flat)
+    assert scene.intersect(np.empty(0, dtype=host.RAY_DTYPE)).shape == (0,)
+    rays = np.zeros(7, dtype=host.RAY_DTYPE)
+    rays["o"] = [0, 1, 3]
+    rays["d"] = [[0, 0, -1], [0, 0, 1], [1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, -1], [1e-20, 0, -1]]
+    rays["t_max"] = [np.inf, np.inf, np.inf, np.inf, np.inf, 0.5, np.inf]  # axis-aligned (inf inverse components), short t_max
+    _check_hits(scene.intersect(rays), oracle.intersect(flat, rays)[0])
+    assert np.array_equal(scene.intersect_p(rays), oracle.intersect_p(flat, rays)[0])
+    # rays that start exactly on geometry and graze edges / vertices of the floor quad
+    v = flat.prim_vertices().reshape(-1, 3)
+    edge = np.zeros(len(v), dtype=host.RAY_DTYPE)
+    edge["o"] = [0.1, 1.0, 2.0]
+    edge["d"] = v - edge["o"]
+    edge["t_max"] = np.inf
+    _check_hits(scene.intersect(edge), oracle.intersect(flat, edge)[0])
+    scene.close()
+
+
+def test_traversal_counters_match_oracle(gpu, host, oracle, terrain_small):
+    import torch
+
+    flat, cam = terrain_small
+    scene = gpu.RenderScene(flat)
+    bmin, bmax = flat.world_bound()
+    rays = host.incoherent_rays(bmin, bmax, 7, 20000)
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).cuda()
+    d_hits = torch.empty(rays.shape[0] * 20, dtype=torch.uint8, device="cuda")
+    nodes, tris = scene.intersect_counted_device(d_rays.data_ptr(), rays.shape[0], d_hits.data_ptr())
+    _, (onodes, otris) = oracle.intersect(flat, rays)
+    assert (nodes, tris) == (onodes, otris)
+    g = d_hits.cpu().numpy().view(host.HIT_DTYPE)
+    _check_hits(g, oracle.intersect(flat, rays)[0])
+    scene.close()
+
+
+@pytest.mark.parametrize("scene_name,depth", [("cornell", 15), ("cornell_env", 15), ("field_small", 8), ("atrium_small", 8), ("terrain_small", 4)])
+def test_path_radiance(gpu, host, oracle, request, scene_name, depth):
+    """li() per camera path.  Identical Sobol numbers and bit-identical hits mean almost every path matches
+    to float rounding; a few diverge where a libm ulp flips a discrete decision."""
+    flat, cam = request.getfixturevalue(scene_name)
+    scene = gpu.RenderScene(flat)
+    params = host.default_render_params(spp=16, max_depth=depth)
+    px, sm = _pixels(cam, params, 20000, seed=11)
+    g = scene.path_radiance(cam, params, px, sm)
+    o = oracle.path_radiance(flat, cam, params, px, sm)
+    assert np.isfinite(g).all() == np.isfinite(o).all()
+    ok = np.isfinite(o).all(axis=1)
+    close = np.isclose(g[ok], o[ok], rtol=1e-3, atol=1e-5).all(axis=1)
+    assert close.mean() > 0.985, f"only {close.mean():.4f} of paths agree"
+    assert abs(g[ok].mean() - o[ok].mean()) <= 0.02 * abs(o[ok].mean()) + 1e-6
+    scene.close()
+
+
+@pytest.mark.parametrize("scene_name,spp,depth", [("cornell", 64, 15), ("cornell_env", 64, 15), ("field_small", 32, 8), ("atrium_small", 32, 8)])
+def test_render_image_matches_oracle(gpu, host, oracle, request, scene_name, spp, depth):
+    flat, cam = request.getfixturevalue(scene_name)
+    scene = gpu.RenderScene(flat)
+    integ = gpu.PathIntegrator(gpu.SamplerBuilder(spp), max_depth=depth)
+    integ.preprocess(scene)
+    film = gpu.Film(cam.width, cam.height)
+    st = integ.render(cam, scene, film)
+    img = film.to_channel_updates()
+    ofilm, ost = oracle.render(flat, cam, integ.params)
+    oimg = oracle.resolve(ofilm)
+    raw = film.download()
+    assert np.allclose(raw[..., 3], ofilm[..., 3], rtol=1e-4)  # filter weight sums: same samples, same table
+    assert st["camera_paths"] == ost["camera_paths"]
+    assert _rel_mse(img, oimg) < 1e-3  # north_star tolerance
+    for k in ("extension_rays", "shadow_rays", "mis_rays"):
+        assert abs(st[k] - ost[k]) <= 0.002 * ost[k] + 8, (k, st[k], ost[k])
+    scene.close()
+
+
+def test_film_is_additive_and_sharded_render_sums(gpu, host, cornell):
+    """The film is a plain sum (film.rs:213-228): rendering sample shards separately and adding the films
+    gives the full render (the multi-GPU decomposition), up to float summation order."""
+    flat, cam = cornell
+    scene = gpu.RenderScene(flat)
+    integ = gpu.PathIntegrator(gpu.SamplerBuilder(8), max_depth=6)
+    full = gpu.Film(cam.width, cam.height)
+    integ.render(cam, scene, full)
+    parts = gpu.Film(cam.width, cam.height)
+    integ.render(cam, scene, parts, sample_stride=(2, 0))
+    integ.render(cam, scene, parts, sample_stride=(2, 1))
+    a, b = full.download(), parts.download()
+    assert np.allclose(a, b, rtol=2e-5, atol=1e-6)
+    rng_film = gpu.Film(cam.width, cam.height)
+    integ.render(cam, scene, rng_film, sample_range=(0, 3))
+    integ.render(cam, scene, rng_film, sample_range=(3, 8))
+    assert np.allclose(a, rng_film.download(), rtol=2e-5, atol=1e-6)
+    full.clear()
+    assert not full.download().any()
+    scene.close()
+
+
+def test_render_is_deterministic_and_batch_size_independent(gpu, host, cornell_env):
+    flat, cam = cornell_env
+    scene = gpu.RenderScene(flat)
+    integ = gpu.PathIntegrator(gpu.SamplerBuilder(4), max_depth=8)
+    out = []
+    for batch in (0, 4096, 1000):
+        integ.params.paths_per_batch = batch
+        film = gpu.Film(cam.width, cam.height)
+        integ.render(cam, scene, film)
+        out.append(gpu.RenderScene.path_radiance(scene, cam, integ.params, [[10, 10], [40, 50]], [0, 3]))
+        out.append(film.download())
+    assert np.array_equal(out[0], out[2]) and np.array_equal(out[0], out[4])
+    assert np.allclose(out[1], out[3], rtol=2e-5, atol=1e-6) and np.allclose(out[1], out[5], rtol=2e-5, atol=1e-6)
+    scene.close()
+
+
+def test_error_behaviour(gpu, host, cornell):
+    flat, cam = cornell
+    scene = gpu.RenderScene(flat)
+    integ = gpu.PathIntegrator(gpu.SamplerBuilder(4), max_depth=500)
+    film = gpu.Film(cam.width, cam.height)
+    with pytest.raises(gpu.PtrsError) as e:
+        integ.render(cam, scene, film)
+    assert e.value.code == -3  # PTRS_ERR_UNSUPPORTED: beyond the 1024 Sobol dimensions (sobol.rs:178-183 panics)
+    bad = gpu.Film(cam.width + 1, cam.height)
+    with pytest.raises(gpu.PtrsError):
+        gpu.PathIntegrator(gpu.SamplerBuilder(4)).render(cam, scene, bad)
+    scene.close()

@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric (camera samples/s and Mrays/s of the path integrator) on
+BASELINE.json's configs[1]: Cornell box + environment map, 1024x1024, 64 spp, max_depth 15.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one full render of the workload (67.6 M camera paths) accumulated into a cleared film.
+  value     paths/s with scene and film resident in HBM (CUDA events on the launching stream)
+  e2e       the same through the C ABI with HOST buffers: ptrs_scene_create from host arrays, render,
+            ptrs_film_download — host<->device copies inside the timed region
+  roofline  extend kernel (closest-hit BVH traversal): algorithmic bytes (32 B x nodes tested + 36 B x
+            triangles tested + 28 B ray + 20 B hit) / its summed launch time, against the
+            measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the C++ oracle (a restatement of the reference's rayon integrator; the Rust crate cannot
+            be built in this image) on a bounded, strided sample of the same workload's 16x16 tiles
+Multi-GPU (weak scaling): rank g renders Sobol sample numbers {s : s mod N == g} of a 64*N-spp render of
+the same image, then one NCCL reduce of the film to rank 0 — the only collective on the path.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = {"name": "cornell+envmap 1024x1024 64spp depth15 (BASELINE configs[1])", "res": (1024, 1024), "spp": 64, "max_depth": 15}
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index, self.samples, self.stop_flag = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_sample_plan(oracle, flat, cam, params, target_s=12.0):
+    """Pick a tile stride so that the oracle renders a uniform subset of the workload's 16x16 tiles in
+    roughly target_s seconds on this host."""
+    n_tiles = oracle.tile_count(cam, params)
+    probe_stride = max(1, n_tiles // 64)
+    t0 = time.perf_counter()
+    _, st = oracle.render(flat, cam, params, tile_stride=probe_stride)
+    dt = time.perf_counter() - t0
+    per_tile = dt / max(1, (n_tiles + probe_stride - 1) // probe_stride)
+    want = max(16, int(target_s / max(per_tile, 1e-9)))
+    return n_tiles, max(1, n_tiles // want)
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU path (C++ oracle, tile-parallel like
+    integrator.rs:617-637, all host threads) on this arm's config; each step = a bounded tile sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import pathtracer_rs_b200.host as host
+    from oracle import oracle
+
+    w = WORKLOAD
+    flat, cam = host.make_scene(host.SCENE_CORNELL_ENV, seed=1, res=w["res"])
+    params = host.default_render_params(spp=w["spp"], max_depth=w["max_depth"])
+    n_tiles, stride = cpu_sample_plan(oracle, flat, cam, params, target_s=8.0)
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        oracle.render(flat, cam, params, tile_stride=stride * 8)
+    times, paths, rays = [], 0, 0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        _, st = oracle.render(flat, cam, params, tile_stride=stride)
+        times.append(time.perf_counter() - t0)
+        paths = st["camera_paths"]
+        rays = st["extension_rays"] + st["shadow_rays"] + st["mis_rays"]
+    t = float(np.mean(times))
+    value = paths / t
+    sample = f"every {stride}th of the {n_tiles} 16x16 tiles, all {w['spp']} spp ({paths} camera paths per step)"
+    line = {"impl": "reference", "metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "mrays_per_s": rays / t / 1e6,
+            "config": {"workload": w["name"], "resolution": list(w["res"]), "spp": w["spp"], "max_depth": w["max_depth"], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference = C++ restatement of the reference's rayon path integrator (oracle/); the Rust crate itself cannot be built in this image"}
+    print(json.dumps(line), flush=True)
+
+
+def bvh_microbench(gpu, host, torch, peak_gbs):
+    """BASELINE configs[3]: fixed-ray intersection microbenchmark on a synthetic 10 M-triangle mesh,
+    2^24 coherent and 2^24 incoherent rays; HBM-bound for incoherent rays."""
+    n_tris = int(os.environ.get("PTRS_BENCH_BVH_TRIS", "10000000"))
+    n_side = int(os.environ.get("PTRS_BENCH_BVH_SIDE", "4096"))
+    flat, cam = host.make_scene(host.SCENE_TERRAIN, seed=1, n_tris=n_tris, res=(n_side, n_side))
+    scene = gpu.RenderScene(flat)
+    bmin, bmax = flat.world_bound()
+    out = {"n_tris": flat.n_prims, "n_nodes": flat.n_nodes, "bvh_build_s": flat.bvh_seconds, "scene_mb": scene.device_bytes / 1e6}
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for name in ("coherent", "incoherent"):
+        rays = host.coherent_rays(cam, n_side) if name == "coherent" else host.incoherent_rays(bmin, bmax, 42, n_side * n_side)
+        n = rays.shape[0]
+        d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).cuda()
+        d_hits = torch.empty(n * 20, dtype=torch.uint8, device="cuda")
+        d_occ = torch.empty(n, dtype=torch.uint8, device="cuda")
+        for any_hit in (False, True):
+            d_out = d_occ if any_hit else d_hits
+            nodes, tris = scene.intersect_counted_device(d_rays.data_ptr(), n, d_out.data_ptr(), any_hit=any_hit, stream=stream)
+            alg_bytes = 32 * nodes + 36 * tris + n * (28 + (1 if any_hit else 20))
+            ms = []
+            for it in range(6):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                if any_hit:
+                    scene.intersect_p_device(d_rays.data_ptr(), n, d_occ.data_ptr(), stream)
+                else:
+                    scene.intersect_device(d_rays.data_ptr(), n, d_hits.data_ptr(), stream)
+                e1.record()
+                e1.synchronize()
+                if it >= 3:
+                    ms.append(e0.elapsed_time(e1))
+            t = float(np.mean(ms)) * 1e-3
+            key = f"{name}_{'any' if any_hit else 'closest'}"
+            out[key] = {"mrays_per_s": n / t / 1e6, "ms": t * 1e3, "nodes_per_ray": nodes / n, "tris_per_ray": tris / n,
+                        "achieved_gbs": alg_bytes / t / 1e9, "frac": alg_bytes / t / 1e9 / peak_gbs}
+        del d_rays, d_hits, d_occ
+    scene.close()
+    return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import pathtracer_rs_b200.gpu as gpu
+    import pathtracer_rs_b200.host as host
+    from pathtracer_rs_b200._abi import PtrsRenderParams
+    from pathtracer_rs_b200.dist import reduce_film, sample_shard
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: the rendering hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    gpu.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+    peak_gbs, peak_src = measured_peaks()
+
+    w = WORKLOAD
+    W, H = w["res"]
+    flat, cam = host.make_scene(host.SCENE_CORNELL_ENV, seed=1, res=w["res"])
+    scene = gpu.RenderScene(flat)
+    # weak scaling: the image is rendered at spp * N with rank g taking sample numbers s = g (mod N)
+    integ = gpu.PathIntegrator(gpu.SamplerBuilder(w["spp"] * n_gpus), max_depth=w["max_depth"])
+    integ.preprocess(scene)
+    film_t = torch.zeros(H, W, 4, dtype=torch.float32, device="cuda")
+    film = gpu.Film(W, H, device_ptr=film_t.data_ptr())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        film_t.zero_()
+        st = integ.render(cam, scene, film, stream=stream, sample_stride=sample_shard(rank, n_gpus))
+        reduce_film(film_t, dst=0)
+        return st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # one untimed pass with visit counters on: algorithmic bytes of the (deterministic) step
+    scene.set_stats_mode(True)
+    st_count = step()
+    scene.set_stats_mode(False)
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    step_ms, ext_ms, stats = [], [], None
+    for _ in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        stats = step()
+        e1.record()
+        barrier()
+        step_ms.append(e0.elapsed_time(e1))
+        ext_ms.append(stats["ms_extend"])
+    clocks = sampler.summary() if sampler else None
+    t_local = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)  # max over ranks
+    total_ms = float(t_local.item())
+    ms_per_step = total_ms / args.steps
+    paths_step = stats["camera_paths"] * n_gpus
+    rays_step = (stats["extension_rays"] + stats["shadow_rays"] + stats["mis_rays"]) * n_gpus
+    value = paths_step / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers -----------------------------------------------
+    host_film = np.empty((H, W, 4), dtype=np.float32)
+    e2e_ms = []
+    for it in range(max(2, min(args.steps, 3)) + 1):
+        barrier()
+        t0 = time.perf_counter()
+        sc2 = gpu.RenderScene(flat)  # ptrs_scene_create: H2D of the whole flattened scene
+        f2 = gpu.Film(W, H)
+        integ.render(cam, sc2, f2, sample_stride=sample_shard(rank, n_gpus))
+        if world > 1:
+            reduce_film(torch.as_tensor(_CudaArray(f2.device_ptr, (H, W, 4)), device="cuda"), dst=0)
+            torch.cuda.synchronize()
+        if rank == 0:
+            gpu._check(gpu.lib().ptrs_film_download(f2._h, host_film.ctypes.data_as(C.POINTER(C.c_float))))
+        sc2.close()
+        del f2
+        barrier()
+        if it > 0:
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    e2e_local = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_local, op=dist.ReduceOp.MAX)
+    e2e_value = paths_step / (float(e2e_local.item()) * 1e-3)
+    h2d = int(flat.host_bytes) + C.sizeof(type(cam)) + C.sizeof(PtrsRenderParams)
+    d2h = H * W * 16
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (extend) ---------------------------------------------------
+    ext_rays = st_count["extension_rays"]
+    alg_bytes = 32 * st_count["nodes_tested"] + 36 * st_count["tris_tested"] + ext_rays * (28 + 20)
+    ext_s = float(np.mean(ext_ms)) * 1e-3
+    achieved = alg_bytes / ext_s / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "extend_dram_bytes.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "extend_kernel<false> (closest-hit BVH traversal)", "achieved": achieved, "peak": peak_gbs,
+                "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_step": alg_bytes, "launches_per_step": stats["extend_launches"],
+                "avg_launch_ms": float(np.mean(ext_ms)) / max(1, stats["extend_launches"]),
+                "bytes_per_ray": alg_bytes / ext_rays, "nodes_per_ray": st_count["nodes_tested"] / ext_rays,
+                "tris_per_ray": st_count["tris_tested"] / ext_rays, "share_of_step": float(np.mean(ext_ms)) / (sum(step_ms) / len(step_ms)),
+                "note": "scene (36 triangles, 59 nodes) is L1/L2 resident: the HBM-bound case is bvh_microbench"}
+
+    # ---- CPU baseline: the oracle on a bounded sample of the same workload ----------------------------
+    cpu = None
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+
+        p1 = host.default_render_params(spp=w["spp"], max_depth=w["max_depth"])
+        n_tiles, stride = cpu_sample_plan(oracle, flat, cam, p1, target_s=12.0)
+        t0 = time.perf_counter()
+        _, ost = oracle.render(flat, cam, p1, tile_stride=stride)
+        dt = time.perf_counter() - t0
+        cpu = {"value": ost["camera_paths"] / dt, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"every {stride}th of the {n_tiles} 16x16 tiles, all {w['spp']} spp ({ost['camera_paths']} camera paths, {dt:.1f} s)",
+               "mrays_per_s": (ost["extension_rays"] + ost["shadow_rays"] + ost["mis_rays"]) / dt / 1e6}
+
+    micro = None
+    if n_gpus == 1 and not args.no_bvh_microbench:
+        del film, film_t
+        scene.close()
+        torch.cuda.empty_cache()
+        micro = bvh_microbench(gpu, host, torch, peak_gbs)
+
+    line = {"metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "mrays_per_s": rays_step / (ms_per_step * 1e-3) / 1e6,
+            "config": {"workload": w["name"], "resolution": [W, H], "spp_per_gpu": w["spp"], "max_depth": w["max_depth"],
+                       "camera_paths_per_step": paths_step, "rays_per_step": rays_step, "sharding": f"sample index mod {n_gpus}, film reduced with NCCL",
+                       "l2": "256 MiB buffer written between timed iterations (L2 flush)"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(e2e_local.item()), "includes": "ptrs_scene_create from host arrays + render + ptrs_film_download"},
+            "gpu_launches": int(stats["launches"]) * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "stage_ms": {k: stats[k] for k in ("ms_generate", "ms_extend", "ms_shade", "ms_shadow", "ms_accumulate", "ms_total")},
+            "rays": {k: stats[k] for k in ("extension_rays", "shadow_rays", "mis_rays")}, "bvh_microbench": micro}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ holder so torch can wrap a device pointer owned by the library."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bvh-microbench", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

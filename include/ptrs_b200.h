@@ -274,11 +274,15 @@ typedef struct PtrsStats {
   uint64_t extension_rays; /* closest-hit rays of the main path (integrator.rs:416) */
   uint64_t shadow_rays;    /* any-hit rays (light.rs:39-41) */
   uint64_t mis_rays;       /* closest-hit rays of estimate_direct's BSDF sample (integrator.rs:119) */
-  uint64_t nodes_tested;   /* only filled by the *_counted entry points / PTRS stats passes */
+  /* BVH nodes / triangles tested; filled only when ptrs_set_stats_mode(scene, 1) is on */
+  uint64_t nodes_tested;     /* by the extend kernel (extension rays) */
   uint64_t tris_tested;
+  uint64_t nee_nodes_tested; /* by the connect kernel (shadow + MIS rays) */
+  uint64_t nee_tris_tested;
   float ms_generate, ms_extend, ms_shade, ms_shadow, ms_accumulate, ms_total;
   uint32_t launches; /* kernels launched by the last call */
   uint32_t batches;
+  uint32_t extend_launches, connect_launches;
 } PtrsStats;
 
 typedef struct PtrsScene PtrsScene; /* opaque */

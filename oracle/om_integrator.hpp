@@ -162,7 +162,7 @@ struct RenderStats {
 // tile_begin/tile_end restrict the run to a range of tiles (bounded CPU-baseline samples);
 // tiles are merged in tile order, one fixed instance of the reference's nondeterministic merge.
 inline RenderStats render(const SobolTables& T, const PtrsSceneDesc* desc, const PtrsCamera& cam, const PtrsRenderParams& rp,
-                          float* film_rgbw, int n_threads, int64_t tile_begin, int64_t tile_end, bool count_visits) {
+                          float* film_rgbw, int n_threads, int64_t tile_begin, int64_t tile_end, int64_t tile_stride) {
   Scene sc{desc};
   IntegratorParams P;
   P.max_depth = rp.max_depth;
@@ -182,7 +182,9 @@ inline RenderStats render(const SobolTables& T, const PtrsSceneDesc* desc, const
   const int64_t n_tiles = (int64_t)ntx * nty;
   if (tile_end <= 0 || tile_end > n_tiles) tile_end = n_tiles;
   if (tile_begin < 0) tile_begin = 0;
-  std::vector<FilmTile> tiles((size_t)(tile_end - tile_begin));
+  if (tile_stride < 1) tile_stride = 1;
+  const int64_t n_run = tile_end > tile_begin ? (tile_end - tile_begin + tile_stride - 1) / tile_stride : 0;
+  std::vector<FilmTile> tiles((size_t)n_run);
   const float scale = 1.0f / std::sqrt((float)spp);
   RenderStats total;
   if (n_threads <= 0) n_threads = omp_get_max_threads();
@@ -190,13 +192,14 @@ inline RenderStats render(const SobolTables& T, const PtrsSceneDesc* desc, const
   {
     RenderStats st;
 #pragma omp for schedule(dynamic, 1)
-    for (int64_t ti = tile_begin; ti < tile_end; ++ti) {
+    for (int64_t tk = 0; tk < n_run; ++tk) {
+      const int64_t ti = tile_begin + tk * tile_stride;
       // render_tile_vec order: (0..num_tiles.x).cartesian_product(0..num_tiles.y) -> x outer
       const int tx = (int)(ti / nty), ty = (int)(ti % nty);
       SobolSampler sampler = proto;
       const int x0 = sb.x0 + tx * TILE, x1 = std::min(x0 + TILE, sb.x1);
       const int y0 = sb.y0 + ty * TILE, y1 = std::min(y0 + TILE, sb.y1);
-      FilmTile& ft = tiles[(size_t)(ti - tile_begin)];
+      FilmTile& ft = tiles[(size_t)tk];
       // Film::get_film_tile, film.rs:193-211
       Bounds2i b{f2i(std::ceil((float)x0 - 0.5f - rp.filter_radius[0])), f2i(std::ceil((float)y0 - 0.5f - rp.filter_radius[1])),
                  f2i(std::floor((float)x1 - 0.5f + rp.filter_radius[0])) + 1, f2i(std::floor((float)y1 - 0.5f + rp.filter_radius[1])) + 1};
@@ -242,7 +245,6 @@ inline RenderStats render(const SobolTables& T, const PtrsSceneDesc* desc, const
       total.tris += st.tris;
     }
   }
-  (void)count_visits;
   for (const FilmTile& ft : tiles) {  // Film::merge_film_tile, film.rs:213-228
     const int w = ft.pb.x1 - ft.pb.x0;
     for (int x = ft.pb.x0; x < ft.pb.x1; ++x)

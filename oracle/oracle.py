@@ -39,7 +39,7 @@ def lib():
         L.oracle_intersect.argtypes = [descp, C.POINTER(PtrsRay), C.c_size_t, C.POINTER(PtrsHit), u64p, C.c_int]
         L.oracle_intersect_p.argtypes = [descp, C.POINTER(PtrsRay), C.c_size_t, C.POINTER(C.c_uint8), u64p, C.c_int]
         L.oracle_path_radiance.argtypes = [descp, camp, rpp, i32p, i32p, C.c_size_t, fp, C.c_int]
-        L.oracle_render.argtypes = [descp, camp, rpp, fp, C.c_int, C.c_int64, C.c_int64, u64p]
+        L.oracle_render.argtypes = [descp, camp, rpp, fp, C.c_int, C.c_int64, C.c_int64, C.c_int64, u64p]
         L.oracle_tile_count.restype = C.c_int64
         L.oracle_tile_count.argtypes = [camp, rpp]
         L.oracle_film_resolve.argtypes = [fp, C.c_int, C.c_int, fp]
@@ -128,13 +128,13 @@ def tile_count(cam, params):
     return lib().oracle_tile_count(C.byref(cam), C.byref(params))
 
 
-def render(scene, cam, params, n_threads=0, tile_begin=0, tile_end=0, film=None):
+def render(scene, cam, params, n_threads=0, tile_begin=0, tile_end=0, tile_stride=1, film=None):
     """Returns (film_rgbw (H, W, 4) raw sums, stats dict)."""
     if film is None:
         film = np.zeros((cam.height, cam.width, 4), dtype=np.float32)
     st = np.zeros(6, dtype=np.uint64)
     rc = lib().oracle_render(scene.desc, C.byref(cam), C.byref(params), _p(film, C.c_float), n_threads, tile_begin, tile_end,
-                             _p(st, C.c_uint64))
+                             tile_stride, _p(st, C.c_uint64))
     if rc != 0:
         raise RuntimeError(lib().oracle_last_error().decode())
     keys = ["camera_paths", "extension_rays", "shadow_rays", "mis_rays", "nodes_tested", "tris_tested"]

@@ -159,9 +159,9 @@ int oracle_path_radiance(const PtrsSceneDesc* desc, const PtrsCamera* cam, const
 
 // stats8: camera_paths, extension, shadow, mis, nodes, tris
 int oracle_render(const PtrsSceneDesc* desc, const PtrsCamera* cam, const PtrsRenderParams* rp, float* film_rgbw, int n_threads,
-                  int64_t tile_begin, int64_t tile_end, uint64_t* stats6) {
+                  int64_t tile_begin, int64_t tile_end, int64_t tile_stride, uint64_t* stats6) {
   try {
-    RenderStats st = render(g_tables, desc, *cam, *rp, film_rgbw, n_threads, tile_begin, tile_end, true);
+    RenderStats st = render(g_tables, desc, *cam, *rp, film_rgbw, n_threads, tile_begin, tile_end, tile_stride);
     if (stats6) {
       stats6[0] = st.camera_paths;
       stats6[1] = st.extension;

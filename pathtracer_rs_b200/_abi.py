@@ -86,8 +86,10 @@ class PtrsRenderParams(C.Structure):
 class PtrsStats(C.Structure):
     _fields_ = [("camera_paths", C.c_uint64), ("extension_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("mis_rays", C.c_uint64), ("nodes_tested", C.c_uint64), ("tris_tested", C.c_uint64),
+                ("nee_nodes_tested", C.c_uint64), ("nee_tris_tested", C.c_uint64),
                 ("ms_generate", C.c_float), ("ms_extend", C.c_float), ("ms_shade", C.c_float), ("ms_shadow", C.c_float),
-                ("ms_accumulate", C.c_float), ("ms_total", C.c_float), ("launches", C.c_uint32), ("batches", C.c_uint32)]
+                ("ms_accumulate", C.c_float), ("ms_total", C.c_float), ("launches", C.c_uint32), ("batches", C.c_uint32),
+                ("extend_launches", C.c_uint32), ("connect_launches", C.c_uint32)]
 
 
 # material / texture / light / wrap enums

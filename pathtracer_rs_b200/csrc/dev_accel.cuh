@@ -153,8 +153,11 @@ PT_DEV NodeLoad load_node(const float4* __restrict__ nodes, uint32_t i) {
   return n;
 }
 
-// bounds.rs:190-232
-PT_DEV bool box_test(const NodeLoad& n, V3 o, V3 inv_dir, bool nx, bool ny, bool nz, float t_ray_max) {
+// bounds.rs:190-232.  The slab arithmetic does not depend on the ray's current t_max except for the
+// final `t_min < r.t_max`, so it is split: box_geom() returns the geometric part and the entry distance,
+// and the caller applies `t_entry < t_max` with whatever t_max is current when the reference would have
+// run the test (immediately for the near child, at pop time for the far child).
+PT_DEV bool box_geom(const NodeLoad& n, V3 o, V3 inv_dir, bool nx, bool ny, bool nz, float* t_entry) {
   const float g = 1.0f + 2.0f * gamma_n(3);
   float t_min = ((nx ? n.a.w : n.a.x) - o.x) * inv_dir.x;
   float t_max = ((nx ? n.a.x : n.a.w) - o.x) * inv_dir.x;
@@ -171,12 +174,19 @@ PT_DEV bool box_test(const NodeLoad& n, V3 o, V3 inv_dir, bool nx, bool ny, bool
   if (t_min > tz_max || tz_min > t_max) return false;
   if (tz_min > t_min) t_min = tz_min;
   if (tz_max < t_max) t_max = tz_max;
-  return (t_min < t_ray_max) && (t_max > 0.0f);
+  *t_entry = t_min;
+  return t_max > 0.0f;
+}
+PT_DEV bool box_test(const NodeLoad& n, V3 o, V3 inv_dir, bool nx, bool ny, bool nz, float t_ray_max) {
+  float t_entry;
+  return box_geom(n, o, inv_dir, nx, ny, nz, &t_entry) && (t_entry < t_ray_max);
 }
 
 #define PT_STACK_SIZE 64
 
-// accelerator.rs:359-475.  ANY_HIT: returns at the first accepted triangle (hit->prim = that prim).
+// accelerator.rs:359-475 for ONE ray in ONE thread, in the reference's control flow.  Used where a single
+// ray is traced inline; the bulk kernels use trace_stream() below.  ANY_HIT: returns at the first
+// accepted triangle (hit->prim = that primitive).
 template <bool ANY_HIT, bool COUNT>
 PT_DEV bool traverse(const DevScene& sc, V3 o, V3 d, float t_max, DevHit* hit, uint32_t* n_nodes, uint32_t* n_tris) {
   hit->prim = -1;
@@ -234,6 +244,231 @@ PT_DEV bool traverse(const DevScene& sc, V3 o, V3 d, float t_max, DevHit* hit, u
     }
   }
   return found;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Streaming traversal engine for the bulk kernels.
+//
+// A warp owns 32 ray slots.  Each lane takes ITS ray through exactly the box-test / triangle-test
+// decisions of accelerator.rs:359-475 (hits, tie-breaks and visit counts are unchanged), but:
+//   refill   lanes whose ray has ended pull new work items with ONE atomicAdd for the whole warp
+//            (persistent threads, warp-aggregated fetch) as soon as PT_REFILL_IDLE lanes are idle —
+//            no lane waits for the slowest ray of a batch
+//   expand   a lane standing on an interior node loads BOTH children (two independent 32 B fetches in
+//            flight) and runs both slab tests.  The near child (dir_is_neg[axis]) is accepted against the
+//            current t_max, as the reference does immediately; the far child's geometric result and entry
+//            distance go on the stack, and `t_entry < t_max` is applied when it is popped — the very test
+//            the reference performs at that moment, since only that comparison depends on t_max.
+//            Far children that already fail are never pushed.
+//   leaves   lanes holding a leaf intersect its triangles together (phase B) once fewer than
+//            PT_SEARCH_MIN lanes are still descending
+// Stack entries are 16 B {node index, entry distance, offset, n_prims | axis << 16}: a pop needs no reload.
+//
+// Work is a functor object with
+//   bool begin(uint32_t item, LaneRay* r)                       first ray of a work item (false: nothing to trace)
+//   bool end(uint32_t item, const DevHit& h, bool found, LaneRay* r)   ray ended; true = trace *r next for the same item
+// ------------------------------------------------------------------------------------------------------
+struct LaneRay {
+  V3 o, d;
+  float t_max;
+  bool any_hit;
+};
+
+#ifndef PT_REFILL_IDLE
+#define PT_REFILL_IDLE 8
+#endif
+#ifndef PT_SEARCH_MIN
+#define PT_SEARCH_MIN 6
+#endif
+#define PT_NO_NODE 0xffffffffu
+
+template <bool COUNT, class Work>
+PT_DEV void trace_stream(const DevScene& sc, uint32_t n_items, uint32_t* ticket, Work& work, uint32_t* c_nodes, uint32_t* c_tris) {
+  const uint32_t FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  uint4 stack[PT_STACK_SIZE];
+  int sp_ = 0;
+  // current node (its box test already passed): index, offset, meta; PT_NO_NODE = need to pop
+  uint32_t cur = PT_NO_NODE, cur_off = 0, cur_meta = 0;
+  bool active = false, exhausted = false, done_ray = false;
+  bool any_hit = false, found = false;
+  uint32_t item = 0;
+  V3 o = mk3(0, 0, 0), inv_dir = mk3(0, 0, 0);
+  bool nx = false, ny = false, nz = false;
+  RayPre rp = ray_precompute(mk3(0, 0, 1));
+  float t_max = 0.f;
+  DevHit hit;
+  hit.prim = -1;
+  hit.t = hit.b0 = hit.b1 = hit.b2 = 0.f;
+  const DevHit miss = hit;
+
+  auto start_ray = [&](const LaneRay& r) {
+    o = r.o;
+    inv_dir = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    nx = inv_dir.x < 0.0f;
+    ny = inv_dir.y < 0.0f;
+    nz = inv_dir.z < 0.0f;
+    rp = ray_precompute(r.d);
+    t_max = r.t_max;
+    any_hit = r.any_hit;
+    found = false;
+    hit.prim = -1;
+    hit.t = r.t_max;
+    hit.b0 = hit.b1 = hit.b2 = 0.f;
+    sp_ = 0;
+    done_ray = false;
+    // root: tested like any other node (accelerator.rs:372-374)
+    const NodeLoad n = load_node(sc.nodes, 0);
+    if (COUNT) ++*c_nodes;
+    float te;
+    if (box_geom(n, o, inv_dir, nx, ny, nz, &te) && te < t_max) {
+      cur = 0;
+      cur_off = __float_as_uint(n.b.z);
+      cur_meta = __float_as_uint(n.b.w);
+    } else {
+      cur = PT_NO_NODE;
+      done_ray = true;
+    }
+  };
+
+  if (sc.n_nodes == 0) {  // empty accelerator: every ray misses (accelerator.rs:360-362)
+    for (;;) {
+      const uint32_t base = (lane == 0) ? atomicAdd(ticket, 32u) : 0u;
+      const uint32_t b = __shfl_sync(FULL, base, 0);
+      if (b >= n_items) return;
+      const uint32_t i = b + lane;
+      if (i < n_items) {
+        LaneRay r;
+        bool more = work.begin(i, &r);
+        while (more) more = work.end(i, miss, false, &r);
+      }
+    }
+  }
+  exhausted = n_items == 0;
+
+  for (;;) {
+    // ---- refill ------------------------------------------------------------------------------------
+    const uint32_t idle = __ballot_sync(FULL, !active);
+    if (!exhausted && (__popc(idle) >= PT_REFILL_IDLE)) {
+      const int leader = __ffs(idle) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(ticket, (uint32_t)__popc(idle));
+      base = __shfl_sync(FULL, base, leader);
+      if (base + (uint32_t)__popc(idle) >= n_items) exhausted = true;
+      if (!active) {
+        const uint32_t i = base + (uint32_t)__popc(idle & lane_lt);
+        if (i < n_items) {
+          LaneRay r;
+          if (work.begin(i, &r)) {
+            item = i;
+            active = true;
+            start_ray(r);
+          }
+        }
+      }
+    }
+    if (__ballot_sync(FULL, active) == 0) {
+      if (exhausted) break;
+      continue;
+    }
+
+    // ---- phase A: descend until a leaf is in hand ---------------------------------------------------
+    for (;;) {
+      // pop until an entry survives the t_max test (the reference's box test at pop time)
+      if (active && !done_ray && cur == PT_NO_NODE) {
+        for (;;) {
+          if (sp_ == 0) {
+            done_ray = true;
+            break;
+          }
+          --sp_;
+          const uint4 e = stack[sp_ < PT_STACK_SIZE ? sp_ : PT_STACK_SIZE - 1];
+          if (COUNT) ++*c_nodes;
+          if (__uint_as_float(e.y) < t_max) {
+            cur = e.x;
+            cur_off = e.z;
+            cur_meta = e.w;
+            break;
+          }
+        }
+      }
+      const bool is_leaf = (cur_meta & 0xffffu) != 0;
+      const bool search = active && !done_ray && cur != PT_NO_NODE && !is_leaf;
+      const uint32_t smask = __ballot_sync(FULL, search);
+      if (smask == 0) break;
+      const uint32_t lmask = __ballot_sync(FULL, active && !done_ray && cur != PT_NO_NODE && is_leaf);
+      if (lmask != 0 && __popc(smask) < PT_SEARCH_MIN) break;  // few lanes still descending: let the leaf holders go
+      if (search) {
+        const uint32_t li = cur + 1, ri = cur_off;
+        const NodeLoad L = load_node(sc.nodes, li);
+        const NodeLoad R = load_node(sc.nodes, ri);
+        const uint32_t axis = (cur_meta >> 16) & 0xffu;
+        const bool neg = axis == 0 ? nx : (axis == 1 ? ny : nz);
+        float tl, tr;
+        const bool gl = box_geom(L, o, inv_dir, nx, ny, nz, &tl);
+        const bool gr = box_geom(R, o, inv_dir, nx, ny, nz, &tr);
+        // near child first (accelerator.rs:393-404)
+        const bool gn = neg ? gr : gl, gf = neg ? gl : gr;
+        const float tn = neg ? tr : tl, tf = neg ? tl : tr;
+        const uint32_t ni = neg ? ri : li, fi = neg ? li : ri;
+        const float4 nb = neg ? R.b : L.b, fb = neg ? L.b : R.b;
+        if (COUNT) {
+          ++*c_nodes;  // the near child's test; the far child's is counted when it is popped
+          if (sp_ < PT_STACK_SIZE) stack[sp_] = make_uint4(fi, __float_as_uint(gf ? tf : CUDART_INF_F), __float_as_uint(fb.z), __float_as_uint(fb.w));
+          ++sp_;
+        } else if (gf && tf < t_max) {
+          if (sp_ < PT_STACK_SIZE) stack[sp_] = make_uint4(fi, __float_as_uint(tf), __float_as_uint(fb.z), __float_as_uint(fb.w));
+          ++sp_;
+        }
+        if (gn && tn < t_max) {
+          cur = ni;
+          cur_off = __float_as_uint(nb.z);
+          cur_meta = __float_as_uint(nb.w);
+        } else {
+          cur = PT_NO_NODE;
+        }
+      }
+    }
+
+    // ---- phase B: triangles of the leaf in hand ------------------------------------------------------
+    {
+      const bool have_leaf = active && !done_ray && cur != PT_NO_NODE && (cur_meta & 0xffffu) != 0;
+      uint32_t cnt = have_leaf ? (cur_meta & 0xffffu) : 0u;
+      for (uint32_t i = 0; __ballot_sync(FULL, i < cnt) != 0; ++i) {
+        if (i < cnt) {
+          const uint32_t prim = cur_off + i;
+          const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim);
+          const float4 v1 = __ldg(sc.tri_verts + 3 * (size_t)prim + 1);
+          const float4 v2 = __ldg(sc.tri_verts + 3 * (size_t)prim + 2);
+          if (COUNT) ++*c_tris;
+          float t, b0, b1, b2;
+          if (tri_core(mk3(v0), mk3(v1), mk3(v2), o, rp, t_max, &t, &b0, &b1, &b2) &&
+              !tri_post_reject(sc, (int)prim, mk3(v0), mk3(v1), mk3(v2), __float_as_uint(v2.w), b0, b1, b2, !any_hit)) {
+            found = true;
+            hit.prim = (int)prim;
+            hit.t = t;
+            hit.b0 = b0;
+            hit.b1 = b1;
+            hit.b2 = b2;
+            t_max = t;
+            if (any_hit) {  // intersect_p returns at the first hit (accelerator.rs:435-442)
+              cnt = 0;
+              done_ray = true;
+            }
+          }
+        }
+      }
+      if (have_leaf) cur = PT_NO_NODE;
+    }
+
+    // ---- rays that ran out of nodes --------------------------------------------------------------------
+    if (active && (done_ray || (cur == PT_NO_NODE && sp_ == 0))) {
+      LaneRay r;
+      if (work.end(item, hit, found, &r)) start_ray(r);
+      else active = false;
+    }
+  }
 }
 
 }  // namespace ptrs

@@ -2,34 +2,61 @@
 #include "launch.hpp"
 #include "wavefront.cuh"
 
+#ifndef PT_TRACE_MIN_BLOCKS
+#define PT_TRACE_MIN_BLOCKS 8
+#endif
+
 namespace ptrs {
 
-// ---- extend ----------------------------------------------------------------------------------------
-template <bool COUNT>
-__global__ void __launch_bounds__(128) extend_kernel(DevScene sc, PathArrays P, const int* __restrict__ q_ext, int* __restrict__ q_class,
-                                                      uint32_t cap, RoundCounters* ctr, GlobalCounters* g) {
-  const uint32_t n = ctr->n_ext;
+// Opportunistic warp aggregation for queue appends issued from divergent code: the lanes that are
+// converged here and target the same counter share one atomicAdd.
+PT_DEV uint32_t coalesced_slot(uint32_t* counter) {
+  const uint32_t m = __activemask();
+  const uint32_t grp = __match_any_sync(m, (unsigned long long)(uintptr_t)counter);
   const int lane = threadIdx.x & 31;
-  uint32_t c_nodes = 0, c_tris = 0;
-  for (;;) {
-    const uint32_t base = warp_fetch32(&ctr->t_ext);
-    if (base >= n) break;
-    const uint32_t i = base + lane;
-    int cls = -1;
-    int p = 0;
-    if (i < n) {
-      p = q_ext[i];
-      const float4 o4 = P.ray_o[p], d4 = P.ray_d[p];
-      DevHit hit;
-      traverse<false, COUNT>(sc, mk3(o4), mk3(d4), CUDART_INF_F, &hit, &c_nodes, &c_tris);
-      P.hit_prim[p] = hit.prim;
-      P.hit_tb[p] = make_float4(hit.t, hit.b0, hit.b1, hit.b2);
-      if (hit.prim < 0) cls = PT_CLASS_MISS;
-      else cls = sc.materials[__float_as_int(__ldg(&sc.tri_verts[3 * (size_t)hit.prim].w))].type;
-    }
-#pragma unroll
-    for (int c = 0; c < PT_N_CLASSES; ++c) warp_push(cls == c, (uint32_t)p, q_class + (size_t)c * cap, &ctr->n_class[c]);
+  const int leader = __ffs(grp) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(grp));
+  base = __shfl_sync(grp, base, leader);
+  return base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+}
+
+// ---- extend ----------------------------------------------------------------------------------------
+// Closest hit for every path of the round's extend queue (integrator.rs:416); the hit's material type
+// picks the shade queue the path is appended to (material sorting).
+struct ExtendWork {
+  const DevScene& sc;
+  const PathArrays& P;
+  const int* __restrict__ q_ext;
+  int* __restrict__ q_class;
+  uint32_t cap;
+  RoundCounters* ctr;
+  int p;
+  __device__ bool begin(uint32_t i, LaneRay* r) {
+    p = q_ext[i];
+    const float4 o4 = P.ray_o[p], d4 = P.ray_d[p];
+    r->o = mk3(o4);
+    r->d = mk3(d4);
+    r->t_max = CUDART_INF_F;
+    r->any_hit = false;
+    return true;
   }
+  __device__ bool end(uint32_t, const DevHit& h, bool found, LaneRay*) {
+    P.hit_prim[p] = found ? h.prim : -1;
+    P.hit_tb[p] = make_float4(h.t, h.b0, h.b1, h.b2);
+    const int cls = found ? sc.materials[__float_as_int(__ldg(&sc.tri_verts[3 * (size_t)h.prim].w))].type : PT_CLASS_MISS;
+    const uint32_t slot = coalesced_slot(&ctr->n_class[cls]);
+    q_class[(size_t)cls * cap + slot] = p;
+    return false;
+  }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) extend_kernel(DevScene sc, PathArrays P, const int* __restrict__ q_ext, int* __restrict__ q_class,
+                                                      uint32_t cap, RoundCounters* ctr, GlobalCounters* g) {
+  uint32_t c_nodes = 0, c_tris = 0;
+  ExtendWork w{sc, P, q_ext, q_class, cap, ctr, 0};
+  trace_stream<COUNT>(sc, ctr->n_ext, &ctr->t_ext, w, &c_nodes, &c_tris);
   if (COUNT) {
     warp_sum_add(c_nodes, &g->nodes_tested);
     warp_sum_add(c_tris, &g->tris_tested);
@@ -37,81 +64,117 @@ __global__ void __launch_bounds__(128) extend_kernel(DevScene sc, PathArrays P, 
 }
 
 // ---- connect ---------------------------------------------------------------------------------------
-// second half of estimate_direct: shadow test (integrator.rs:66-78), MIS ray (integrator.rs:113-135)
-template <bool COUNT>
-__global__ void __launch_bounds__(128) connect_kernel(DevScene sc, PathArrays P, const int* __restrict__ q_nee, RoundCounters* ctr,
-                                                       GlobalCounters* g) {
-  const uint32_t n = ctr->n_nee;
-  const int lane = threadIdx.x & 31;
-  uint32_t c_nodes = 0, c_tris = 0;
-  for (;;) {
-    const uint32_t base = warp_fetch32(&ctr->t_nee);
-    if (base >= n) break;
-    const uint32_t i = base + lane;
-    bool did_shadow = false, did_mis = false;
-    if (i < n) {
-      const int p = q_nee[i];
-      const float4 n0 = P.nee0[p], n1 = P.nee1[p], n2 = P.nee2[p], n3 = P.nee3[p];
-      const uint32_t nf = __float_as_uint(n3.w);
-      const int light_idx = (int)(nf & 0x3fffffffu);
-      Spec ld = sp(0.0f);
-      if (nf & PT_NEE_SHADOW) {
-        did_shadow = true;
-        DevHit h;
-        const bool occluded = traverse<true, COUNT>(sc, mk3(n0), mk3(n1), 1.0f - PT_SHADOW_EPSILON, &h, &c_nodes, &c_tris);
-        if (!occluded) ld = ld + sp(n0.w, n1.w, n2.w);
-      }
-      if (nf & PT_NEE_MIS) {
-        did_mis = true;
-        const float4 n4 = P.nee4[p];
-        const float scat_pdf = P.nee5[p].w;
-        const V3 md = mk3(n3);
-        DevHit h;
-        const bool found = traverse<false, COUNT>(sc, mk3(n2), md, CUDART_INF_F, &h, &c_nodes, &c_tris);
-        Spec li = sp(0.0f);
-        if (found) {
-          const int hl = __float_as_int(__ldg(&sc.tri_verts[3 * (size_t)h.prim + 1].w));
-          if (hl == light_idx) {
-            SurfInter si;
-            reconstruct_hit(sc, h.prim, h.b0, h.b1, h.b2, md, &si);
-            li = area_le(sc, hl, si, -md);
-          }
-        } else if (sc.lights[light_idx].type == PTRS_LIGHT_INFINITE) {
-          li = env_le(sc, sc.lights[light_idx], md);
-        }
-        if (!is_black(li)) ld = ld + sp(n4.x, n4.y, n4.z) * li * sp(1.0f) * n4.w / scat_pdf;
-      }
-      const float4 b5 = P.nee5[p];
-      const float4 l4 = P.L[p];
-      Spec L = sp(l4.x, l4.y, l4.z) + sp(b5.x, b5.y, b5.z) * ((float)sc.n_lights * ld);
-      P.L[p] = make_float4(L.r, L.g, L.b, 0.f);
-    }
-    warp_count(did_shadow, &g->shadow_rays);
-    warp_count(did_mis, &g->mis_rays);
+// Second half of estimate_direct for every path with a pending record: the shadow test
+// (integrator.rs:66-78, light.rs:39-41) and the BSDF-sampled MIS ray (integrator.rs:113-135), traced
+// back to back by ONE lane, which then adds beta * n_lights * (Ld_light + Ld_bsdf) to the path's
+// radiance — a single writer per path keeps the summation order of integrator.rs:443-447.
+struct ConnectWork {
+  const DevScene& sc;
+  const PathArrays& P;
+  const int* __restrict__ q_nee;
+  int p;
+  uint32_t nf;
+  int stage;  // 0 = shadow ray in flight, 1 = MIS ray in flight
+  Spec ld;
+  uint32_t n_shadow, n_mis;
+
+  __device__ void mis_ray(LaneRay* r) {
+    const float4 n2 = P.nee2[p], n3 = P.nee3[p];
+    r->o = mk3(n2);
+    r->d = mk3(n3);
+    r->t_max = CUDART_INF_F;
+    r->any_hit = false;
+    stage = 1;
+    ++n_mis;
   }
+  __device__ void finish() {
+    const float4 b5 = P.nee5[p];
+    const float4 l4 = P.L[p];
+    const Spec L = sp(l4.x, l4.y, l4.z) + sp(b5.x, b5.y, b5.z) * ((float)sc.n_lights * ld);
+    P.L[p] = make_float4(L.r, L.g, L.b, 0.f);
+  }
+  __device__ bool begin(uint32_t i, LaneRay* r) {
+    p = q_nee[i];
+    nf = __float_as_uint(P.nee3[p].w);
+    ld = sp(0.0f);
+    if (nf & PT_NEE_SHADOW) {
+      const float4 n0 = P.nee0[p], n1 = P.nee1[p];
+      r->o = mk3(n0);
+      r->d = mk3(n1);
+      r->t_max = 1.0f - PT_SHADOW_EPSILON;
+      r->any_hit = true;
+      stage = 0;
+      ++n_shadow;
+      return true;
+    }
+    if (nf & PT_NEE_MIS) {
+      mis_ray(r);
+      return true;
+    }
+    return false;
+  }
+  __device__ bool end(uint32_t, const DevHit& h, bool found, LaneRay* r) {
+    if (stage == 0) {
+      if (!found) ld = ld + sp(P.nee0[p].w, P.nee1[p].w, P.nee2[p].w);
+      if (nf & PT_NEE_MIS) {
+        mis_ray(r);
+        return true;
+      }
+      finish();
+      return false;
+    }
+    const int light_idx = (int)(nf & 0x3fffffffu);
+    const V3 md = mk3(P.nee3[p]);
+    Spec li = sp(0.0f);
+    if (found) {
+      const int hl = __float_as_int(__ldg(&sc.tri_verts[3 * (size_t)h.prim + 1].w));
+      if (hl == light_idx) {
+        SurfInter si;
+        reconstruct_hit(sc, h.prim, h.b0, h.b1, h.b2, md, &si);
+        li = area_le(sc, hl, si, -md);
+      }
+    } else if (sc.lights[light_idx].type == PTRS_LIGHT_INFINITE) {
+      li = env_le(sc, sc.lights[light_idx], md);
+    }
+    if (!is_black(li)) {
+      const float4 n4 = P.nee4[p];
+      ld = ld + sp(n4.x, n4.y, n4.z) * li * sp(1.0f) * n4.w / P.nee5[p].w;
+    }
+    finish();
+    return false;
+  }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) connect_kernel(DevScene sc, PathArrays P, const int* __restrict__ q_nee, RoundCounters* ctr,
+                                                       GlobalCounters* g) {
+  uint32_t c_nodes = 0, c_tris = 0;
+  ConnectWork w{sc, P, q_nee, 0, 0u, 0, sp(0.f), 0u, 0u};
+  trace_stream<COUNT>(sc, ctr->n_nee, &ctr->t_nee, w, &c_nodes, &c_tris);
+  warp_sum_add(w.n_shadow, &g->shadow_rays);
+  warp_sum_add(w.n_mis, &g->mis_rays);
   if (COUNT) {
-    warp_sum_add(c_nodes, &g->nodes_tested);
-    warp_sum_add(c_tris, &g->tris_tested);
+    warp_sum_add(c_nodes, &g->nee_nodes_tested);
+    warp_sum_add(c_tris, &g->nee_tris_tested);
   }
 }
 
 // ---- standalone traversal kernels (ptrs_intersect*, the BVH microbenchmark) --------------------------
-template <bool ANY_HIT, bool COUNT>
-__global__ void __launch_bounds__(128) intersect_kernel(DevScene sc, const PtrsRay* __restrict__ rays, uint32_t n, PtrsHit* __restrict__ hits,
-                                                         uint8_t* __restrict__ occluded, uint32_t* ticket, GlobalCounters* g) {
-  const int lane = threadIdx.x & 31;
-  uint32_t c_nodes = 0, c_tris = 0;
-  for (;;) {
-    const uint32_t base = warp_fetch32(ticket);
-    if (base >= n) break;
-    const uint32_t i = base + lane;
-    if (i >= n) continue;
-    const float* r = (const float*)(rays + i);
-    const V3 o = mk3(__ldg(r), __ldg(r + 1), __ldg(r + 2)), d = mk3(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5));
-    const float t_max = __ldg(r + 6);
-    DevHit h;
-    const bool found = traverse<ANY_HIT, COUNT>(sc, o, d, t_max, &h, &c_nodes, &c_tris);
-    if (ANY_HIT) {
+struct IntersectWork {
+  const PtrsRay* __restrict__ rays;
+  PtrsHit* __restrict__ hits;
+  uint8_t* __restrict__ occluded;
+  bool any_hit;
+  __device__ bool begin(uint32_t i, LaneRay* r) {
+    const float* q = (const float*)(rays + i);
+    r->o = mk3(__ldg(q), __ldg(q + 1), __ldg(q + 2));
+    r->d = mk3(__ldg(q + 3), __ldg(q + 4), __ldg(q + 5));
+    r->t_max = __ldg(q + 6);
+    r->any_hit = any_hit;
+    return true;
+  }
+  __device__ bool end(uint32_t i, const DevHit& h, bool found, LaneRay*) {
+    if (any_hit) {
       occluded[i] = found ? 1 : 0;
     } else {
       PtrsHit out;
@@ -122,13 +185,21 @@ __global__ void __launch_bounds__(128) intersect_kernel(DevScene sc, const PtrsR
       out.b2 = h.b2;
       hits[i] = out;
     }
+    return false;
   }
+};
+
+template <bool ANY_HIT, bool COUNT>
+__global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) intersect_kernel(DevScene sc, const PtrsRay* __restrict__ rays, uint32_t n, PtrsHit* __restrict__ hits,
+                                                         uint8_t* __restrict__ occluded, uint32_t* ticket, GlobalCounters* g) {
+  uint32_t c_nodes = 0, c_tris = 0;
+  IntersectWork w{rays, hits, occluded, ANY_HIT};
+  trace_stream<COUNT>(sc, n, ticket, w, &c_nodes, &c_tris);
   if (COUNT) {
     warp_sum_add(c_nodes, &g->nodes_tested);
     warp_sum_add(c_tris, &g->tris_tested);
   }
 }
-
 
 // ---- launchers -----------------------------------------------------------------------------------------
 void launch_extend(cudaStream_t st, int sm, bool count, const DevScene& sc, const PathArrays& P, const int* q_ext, int* q_class, uint32_t cap,

@@ -335,6 +335,7 @@ int32_t run_batch(PtrsScene* s, const RenderConst& rc, uint64_t work_base, uint3
       int* q_out = w.q_ext[(round + 1) & 1].p;
       tm.begin(ST_EXTEND);
       launch_extend(st, sm, s->count_visits, s->dev, P, q_in, w.q_class.p, cap, c, w.gcount.p);
+      s->stats.extend_launches += 1;
       tm.end();
       tm.begin(ST_SHADE);
       if (s->dev.n_infinite_lights > 0) {
@@ -353,6 +354,7 @@ int32_t run_batch(PtrsScene* s, const RenderConst& rc, uint64_t work_base, uint3
       tm.begin(ST_CONNECT);
       if (s->dev.n_lights > 0) {
         launch_connect(st, sm, s->count_visits, s->dev, P, w.q_nee.p, c, w.gcount.p);
+        s->stats.connect_launches += 1;
         s->stats.launches += 1;
       }
       tm.end();
@@ -775,6 +777,8 @@ static int32_t render_impl(PtrsScene* s, const PtrsCamera* cam, const PtrsRender
   s->stats.mis_rays = g.mis_rays;
   s->stats.nodes_tested = g.nodes_tested;
   s->stats.tris_tested = g.tris_tested;
+  s->stats.nee_nodes_tested = g.nee_nodes_tested;
+  s->stats.nee_tris_tested = g.nee_tris_tested;
   s->stats.ms_generate = ms[ST_GENERATE];
   s->stats.ms_extend = ms[ST_EXTEND];
   s->stats.ms_shade = ms[ST_SHADE];

@@ -60,7 +60,7 @@ struct RoundCounters {
 };
 
 struct GlobalCounters {
-  unsigned long long shadow_rays, mis_rays, nodes_tested, tris_tested, ext_rays;
+  unsigned long long shadow_rays, mis_rays, nodes_tested, tris_tested, nee_nodes_tested, nee_tris_tested;
 };
 
 struct RenderConst {

@@ -2,7 +2,7 @@
 // (src/pathtracer/importer/mitsuba.rs:198-429, importer/gltf.rs:378-584) — transform meshes to world
 // space, create one GeometricPrimitive per triangle and one DiffuseAreaLight per emissive triangle,
 // build MIP pyramids and the env-map Distribution2D, run BVH::new(.., 4) — ending in the flat
-// PtrsSceneDesc the device library (and the test oracle) consume.
+// PtrsSceneDesc the device library consumes.
 #pragma once
 #include <cstdint>
 #include <string>

@@ -7,8 +7,12 @@
 NVCC      ?= /usr/local/cuda/bin/nvcc
 HOSTCXX   := /usr/bin/g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := -std=c++17 -O3 $(ARCH) -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
-             -ccbin $(HOSTCXX) -Xcompiler -fPIC -diag-suppress 177 -Xptxas -v
+NVCCBASE  := -std=c++17 -O3 $(ARCH) -lineinfo -ftz=false -ccbin $(HOSTCXX) -Xcompiler -fPIC -diag-suppress 177 -Xptxas -v
+# exact units: Sobol, camera rays, BVH traversal, triangle test — bit-identical to the CPU path
+NVCCFLAGS := $(NVCCBASE) -fmad=false -prec-div=true -prec-sqrt=true
+# shading units: everything downstream of sin/cos/exp is toleranced anyway, so FMA
+# contraction and the 2-ulp division / square root are allowed there
+SHADEFLAGS := $(NVCCBASE) -fmad=true -prec-div=false -prec-sqrt=false
 CXXFLAGS  := -std=c++17 -O2 -ffp-contract=off -fno-fast-math -fopenmp -fPIC -Wall -Wno-unused-function
 
 CS   := pathtracer_rs_b200/csrc
@@ -29,7 +33,7 @@ $(OBJ)/%.o: $(CS)/%.cu $(DEV_HDRS)
 
 $(OBJ)/k_shade_%.o: $(CS)/k_shade.cu $(DEV_HDRS)
 	@mkdir -p $(OBJ)
-	$(NVCC) $(NVCCFLAGS) -DPT_SHADE_MAT=$* -c $< -o $@ > $(OBJ)/k_shade_$*.ptxas.log 2>&1 || (cat $(OBJ)/k_shade_$*.ptxas.log; false)
+	$(NVCC) $(SHADEFLAGS) $(SHADE_EXTRA) -DPT_SHADE_MAT=$* -c $< -o $@ > $(OBJ)/k_shade_$*.ptxas.log 2>&1 || (cat $(OBJ)/k_shade_$*.ptxas.log; false)
 
 $(OBJ)/sobol_blob.o: $(CS)/sobol_blob.S $(BLOB)
 	@mkdir -p $(OBJ)

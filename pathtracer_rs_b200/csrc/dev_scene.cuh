@@ -39,7 +39,8 @@ struct DevScene {
   const PtrsLight* lights;
   const int* infinite_lights;
   const DevEnv* envs;
-  const uint32_t* sobol;  // SOBOL_MATRICES_32, 1024 x 52
+  const uint32_t* sobol;    // SOBOL_MATRICES_32, 1024 dimensions x 52 columns
+  const uint32_t* sobol_t;  // the same table bit-major: 52 x 1024
   uint32_t n_nodes, n_prims, n_lights, n_infinite_lights;
 };
 

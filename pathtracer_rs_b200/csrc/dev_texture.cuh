@@ -14,8 +14,10 @@ struct TexCoord {
 PT_DEV void mip_texel(const DevScene& sc, const PtrsMipMap& mm, int level, int s, int t, float* out) {  // texture.rs:245-273
   const int W = mm.width[level], H = mm.height[level], C = mm.channels;
   if (mm.wrap == PTRS_WRAP_REPEAT) {
-    s = abs_mod(s, W);
-    t = abs_mod(t, H);
+    // abs_mod(a, b) == a & (b - 1) for power-of-two b (MIP levels are powers of two after MIPMap::new's
+    // resample, texture.rs:285-295): avoids two integer divisions per texel
+    s = (W & (W - 1)) == 0 ? (s & (W - 1)) : abs_mod(s, W);
+    t = (H & (H - 1)) == 0 ? (t & (H - 1)) : abs_mod(t, H);
   } else if (mm.wrap == PTRS_WRAP_BLACK) {
     if (s < 0 || s >= W || t < 0 || t >= H) {
       out[0] = out[1] = out[2] = 0.f;
@@ -68,13 +70,9 @@ PT_DEVN void mip_lookup_width(const DevScene& sc, const PtrsMipMap& mm, float s,
   }
 }
 
-PT_DEVN void tex_eval(const DevScene& sc, int tex_id, const TexCoord& tc, float* out) {
+PT_DEVN void tex_eval_slow(const DevScene& sc, int tex_id, const TexCoord& tc, float* out) {
   const PtrsTexture& t = sc.textures[tex_id];
-  if (t.type == PTRS_TEX_CONSTANT) {
-    out[0] = t.v1[0];
-    out[1] = t.v1[1];
-    out[2] = t.v1[2];
-  } else if (t.type == PTRS_TEX_CHECKER) {
+  if (t.type == PTRS_TEX_CHECKER) {
     float s = t.su * tc.u + t.du, tt = t.sv * tc.v + t.dv;
     float s_idx = s - floorf(s), t_idx = tt - floorf(tt);
     bool second = (s_idx <= 0.5f && t_idx <= 0.5f) || (s_idx >= 0.5f && t_idx >= 0.5f);
@@ -87,6 +85,17 @@ PT_DEVN void tex_eval(const DevScene& sc, int tex_id, const TexCoord& tc, float*
     float width = fmaxf(fmaxf(fabsf(dsdx), fabsf(dtdx)), fmaxf(fabsf(dsdy), fabsf(dtdy)));  // MIPMap::lookup
     out[1] = out[2] = 0.f;
     mip_lookup_width(sc, sc.mipmaps[t.mip], s, tt, width, out);
+  }
+}
+// ConstantTexture (the common case: every Mitsuba rgb / float parameter) is resolved inline
+PT_DEV void tex_eval(const DevScene& sc, int tex_id, const TexCoord& tc, float* out) {
+  const PtrsTexture* t = sc.textures + tex_id;
+  if (__ldg(&t->type) == PTRS_TEX_CONSTANT) {
+    out[0] = __ldg(&t->v1[0]);
+    out[1] = __ldg(&t->v1[1]);
+    out[2] = __ldg(&t->v1[2]);
+  } else {
+    tex_eval_slow(sc, tex_id, tc, out);
   }
 }
 PT_DEV float tex_f32(const DevScene& sc, int id, const TexCoord& tc) {

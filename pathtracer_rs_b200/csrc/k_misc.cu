@@ -43,6 +43,8 @@ __global__ void __launch_bounds__(256) generate_kernel(const __grid_constant__ R
       ps.scramble = pixel_scramble(px, py);
       ps.index = sobol_interval_to_index(rc.sobol, (uint64_t)s, px - rc.sobol.bounds_min[0], py - rc.sobol.bounds_min[1]);
       ps.dimension = 0;
+  ps.win_base = 0xffffffffu;
+      ps.win_base = 0xffffffffu;
       V2 u = get_2d(rc.sobol, sobol, ps);
       const float fx = (float)px + u.x, fy = (float)py + u.y;  // get_camera_sample, sobol.rs:116-120
       V3 o, d;
@@ -128,6 +130,7 @@ __global__ void sobol_probe_kernel(const __grid_constant__ RenderConst rc, const
   ps.scramble = pixel_scramble(ps.px, ps.py);
   ps.index = sobol_interval_to_index(rc.sobol, (uint64_t)s[i], ps.px - rc.sobol.bounds_min[0], ps.py - rc.sobol.bounds_min[1]);
   ps.dimension = 0;
+  ps.win_base = 0xffffffffu;
   if (out_index) out_index[i] = ps.index;
   for (uint32_t k = 0; k < n_dims; ++k) out[(size_t)i * n_dims + k] = sample_dimension(rc.sobol, sobol, ps, (uint32_t)dims[k]);
 }
@@ -142,6 +145,7 @@ __global__ void ray_probe_kernel(const __grid_constant__ RenderConst rc, const u
   ps.scramble = pixel_scramble(ps.px, ps.py);
   ps.index = sobol_interval_to_index(rc.sobol, (uint64_t)s[i], ps.px - rc.sobol.bounds_min[0], ps.py - rc.sobol.bounds_min[1]);
   ps.dimension = 0;
+  ps.win_base = 0xffffffffu;
   V2 u = get_2d(rc.sobol, sobol, ps);
   const float fx = (float)ps.px + u.x, fy = (float)ps.py + u.y;
   V3 o, d, rx, ry;

@@ -108,16 +108,36 @@ PT_DEV void nee_prepare(const DevScene& sc, const SurfInter& si, const Bsdf& bsd
   *nee_flags = nf;
 }
 
+#ifndef PT_SHADE_MIN_BLOCKS
+#define PT_SHADE_MIN_BLOCKS 4
+#endif
+
+// both appends of a warp (connect queue, next extend queue) with their atomics in flight together
+PT_DEV void warp_push2(bool pa, int* qa, uint32_t* na, bool pb, int* qb, uint32_t* nb, uint32_t item) {
+  const uint32_t ma = __ballot_sync(0xffffffffu, pa), mb = __ballot_sync(0xffffffffu, pb);
+  const int lane = threadIdx.x & 31;
+  uint32_t ba = 0, bb = 0;
+  if (lane == 0) {
+    if (ma) ba = atomicAdd(na, (uint32_t)__popc(ma));
+    if (mb) bb = atomicAdd(nb, (uint32_t)__popc(mb));
+  }
+  ba = __shfl_sync(0xffffffffu, ba, 0);
+  bb = __shfl_sync(0xffffffffu, bb, 0);
+  const uint32_t lt = (1u << lane) - 1u;
+  if (pa) qa[ba + __popc(ma & lt)] = (int)item;
+  if (pb) qb[bb + __popc(mb & lt)] = (int)item;
+}
+
 template <int MAT>
-__global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ RenderConst rc, DevScene sc, PathArrays P,
+__global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ RenderConst rc, DevScene sc, PathArrays P,
                                                      const int* __restrict__ q, int* __restrict__ q_ext_next, int* __restrict__ q_nee,
                                                      RoundCounters* ctr, RoundCounters* ctr_next) {
   const uint32_t n = ctr->n_class[MAT];
   const int lane = threadIdx.x & 31;
   const uint32_t* __restrict__ sobol = sc.sobol;
-  for (;;) {
-    const uint32_t base = warp_fetch32(&ctr->t_class[MAT]);
-    if (base >= n) break;
+  // shade work is uniform per item (one material type per launch): static striding, no ticket atomic
+  const uint32_t warp_stride = (gridDim.x * blockDim.x) & ~31u;
+  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += warp_stride) {
     const uint32_t i = base + lane;
     bool push_ext = false, push_nee = false;
     int p = 0;
@@ -168,6 +188,7 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Rend
           ps.scramble = pixel_scramble(pix.x, pix.y);
           ps.index = P.sobol_index[p];
           ps.dimension = flags & 0xffffu;
+          sobol_window_fill(sc.sobol_t, ps, ps.dimension);
           // direct lighting (integrator.rs:443-447, 192-217)
           if (bsdf_num_components(bsdf, BSDF_ALL & ~BSDF_SPECULAR) > 0 && sc.n_lights > 0) {
             V2 u_light = get_2d(rc.sobol, sobol, ps);
@@ -231,8 +252,7 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Rend
         P.flags[p] = flags;
       }
     }
-    warp_push(push_nee, (uint32_t)p, q_nee, &ctr->n_nee);
-    warp_push(push_ext, (uint32_t)p, q_ext_next, &ctr_next->n_ext);
+    warp_push2(push_nee, q_nee, &ctr->n_nee, push_ext, q_ext_next, &ctr_next->n_ext, (uint32_t)p);
   }
 }
 

@@ -148,7 +148,7 @@ struct PtrsScene {
   DevBuf<int> infinite_lights;
   DevBuf<DevEnv> envs;
   std::vector<DevBuf<float>> env_arrays;
-  DevBuf<uint32_t> sobol;
+  DevBuf<uint32_t> sobol, sobol_t;
   DevBuf<uint32_t> ticket;
   DevBuf<GlobalCounters> gcount;
   float world_bound[6] = {0, 0, 0, 0, 0, 0};
@@ -508,6 +508,12 @@ int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) {
     CUDA_TRY(s->envs.upload(envs.data(), envs.size()));
   }
   CUDA_TRY(s->sobol.upload(sh.matrices, (size_t)sh.n_dims * sh.n_cols));
+  {
+    std::vector<uint32_t> t((size_t)sh.n_dims * sh.n_cols);
+    for (uint32_t d = 0; d < sh.n_dims; ++d)
+      for (uint32_t k = 0; k < sh.n_cols; ++k) t[(size_t)k * sh.n_dims + d] = sh.matrices[(size_t)d * sh.n_cols + k];
+    CUDA_TRY(s->sobol_t.upload(t.data(), t.size()));
+  }
   CUDA_TRY(s->ticket.alloc(4));
   CUDA_TRY(s->gcount.alloc(1));
   DevScene& v = s->dev;
@@ -526,6 +532,7 @@ int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) {
   v.infinite_lights = s->infinite_lights.p;
   v.envs = s->envs.p;
   v.sobol = s->sobol.p;
+  v.sobol_t = s->sobol_t.p;
   v.n_nodes = d->n_nodes;
   v.n_prims = d->n_prims;
   v.n_lights = d->n_lights;

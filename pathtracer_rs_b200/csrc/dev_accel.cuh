@@ -146,123 +146,74 @@ PT_DEVN bool tri_post_reject(const DevScene& sc, int prim, V3 p0, V3 p1, V3 p2, 
 struct NodeLoad {
   float4 a, b;  // a = (min.x, min.y, min.z, max.x)  b = (max.y, max.z, offset bits, n_prims | axis << 16)
 };
+// One 32 B node as a single 256-bit non-coherent load (LDG.E.256 on sm_100a).
 PT_DEV NodeLoad load_node(const float4* __restrict__ nodes, uint32_t i) {
   NodeLoad n;
-  n.a = __ldg(nodes + 2 * (size_t)i);
-  n.b = __ldg(nodes + 2 * (size_t)i + 1);
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(n.a.x), "=f"(n.a.y), "=f"(n.a.z), "=f"(n.a.w), "=f"(n.b.x), "=f"(n.b.y), "=f"(n.b.z), "=f"(n.b.w)
+      : "l"(nodes + 2 * (size_t)i));
   return n;
 }
 
 // bounds.rs:190-232.  The slab arithmetic does not depend on the ray's current t_max except for the
 // final `t_min < r.t_max`, so it is split: box_geom() returns the geometric part and the entry distance,
 // and the caller applies `t_entry < t_max` with whatever t_max is current when the reference would have
-// run the test (immediately for the near child, at pop time for the far child).
+// run the test.  Branch-free: the reference's early `return false`s only skip arithmetic whose results
+// are then unused, so evaluating everything and combining the predicates gives the same boolean; the
+// `if (a > b) x = a` updates are kept as compare+select (not fmaxf/fminf) so NaN operands behave as in
+// the reference.
 PT_DEV bool box_geom(const NodeLoad& n, V3 o, V3 inv_dir, bool nx, bool ny, bool nz, float* t_entry) {
   const float g = 1.0f + 2.0f * gamma_n(3);
   float t_min = ((nx ? n.a.w : n.a.x) - o.x) * inv_dir.x;
   float t_max = ((nx ? n.a.x : n.a.w) - o.x) * inv_dir.x;
-  float ty_min = ((ny ? n.b.x : n.a.y) - o.y) * inv_dir.y;
+  const float ty_min = ((ny ? n.b.x : n.a.y) - o.y) * inv_dir.y;
   float ty_max = ((ny ? n.a.y : n.b.x) - o.y) * inv_dir.y;
+  const float tz_min = ((nz ? n.b.y : n.a.z) - o.z) * inv_dir.z;
+  float tz_max = ((nz ? n.a.z : n.b.y) - o.z) * inv_dir.z;
   t_max *= g;
   ty_max *= g;
-  if (t_min > ty_max || ty_min > t_max) return false;
-  if (ty_min > t_min) t_min = ty_min;
-  if (ty_max < t_max) t_max = ty_max;
-  float tz_min = ((nz ? n.b.y : n.a.z) - o.z) * inv_dir.z;
-  float tz_max = ((nz ? n.a.z : n.b.y) - o.z) * inv_dir.z;
   tz_max *= g;
-  if (t_min > tz_max || tz_min > t_max) return false;
-  if (tz_min > t_min) t_min = tz_min;
-  if (tz_max < t_max) t_max = tz_max;
+  const bool miss_xy = (t_min > ty_max) | (ty_min > t_max);
+  t_min = ty_min > t_min ? ty_min : t_min;
+  t_max = ty_max < t_max ? ty_max : t_max;
+  const bool miss_z = (t_min > tz_max) | (tz_min > t_max);
+  t_min = tz_min > t_min ? tz_min : t_min;
+  t_max = tz_max < t_max ? tz_max : t_max;
   *t_entry = t_min;
-  return t_max > 0.0f;
-}
-PT_DEV bool box_test(const NodeLoad& n, V3 o, V3 inv_dir, bool nx, bool ny, bool nz, float t_ray_max) {
-  float t_entry;
-  return box_geom(n, o, inv_dir, nx, ny, nz, &t_entry) && (t_entry < t_ray_max);
+  return !miss_xy & !miss_z & (t_max > 0.0f);
 }
 
 #define PT_STACK_SIZE 64
-
-// accelerator.rs:359-475 for ONE ray in ONE thread, in the reference's control flow.  Used where a single
-// ray is traced inline; the bulk kernels use trace_stream() below.  ANY_HIT: returns at the first
-// accepted triangle (hit->prim = that primitive).
-template <bool ANY_HIT, bool COUNT>
-PT_DEV bool traverse(const DevScene& sc, V3 o, V3 d, float t_max, DevHit* hit, uint32_t* n_nodes, uint32_t* n_tris) {
-  hit->prim = -1;
-  hit->t = t_max;
-  hit->b0 = hit->b1 = hit->b2 = 0.f;
-  if (sc.n_nodes == 0) return false;
-  const V3 inv_dir = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-  const bool nx = inv_dir.x < 0.0f, ny = inv_dir.y < 0.0f, nz = inv_dir.z < 0.0f;
-  const RayPre rp = ray_precompute(d);
-  uint32_t stack[PT_STACK_SIZE];
-  int sp_ = 0;
-  uint32_t curr = 0;
-  bool found = false;
-  for (;;) {
-    const NodeLoad n = load_node(sc.nodes, curr);
-    if (COUNT) ++*n_nodes;
-    bool descend = false;
-    if (box_test(n, o, inv_dir, nx, ny, nz, t_max)) {
-      const uint32_t offset = __float_as_uint(n.b.z);
-      const uint32_t meta = __float_as_uint(n.b.w);
-      const uint32_t n_prims = meta & 0xffffu;
-      if (n_prims > 0) {
-        for (uint32_t i = 0; i < n_prims; ++i) {
-          const uint32_t prim = offset + i;
-          const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim);
-          const float4 v1 = __ldg(sc.tri_verts + 3 * (size_t)prim + 1);
-          const float4 v2 = __ldg(sc.tri_verts + 3 * (size_t)prim + 2);
-          if (COUNT) ++*n_tris;
-          float t, b0, b1, b2;
-          if (tri_core(mk3(v0), mk3(v1), mk3(v2), o, rp, t_max, &t, &b0, &b1, &b2)) {
-            if (tri_post_reject(sc, (int)prim, mk3(v0), mk3(v1), mk3(v2), __float_as_uint(v2.w), b0, b1, b2, !ANY_HIT)) continue;
-            found = true;
-            hit->prim = (int)prim;
-            hit->t = t;
-            hit->b0 = b0;
-            hit->b1 = b1;
-            hit->b2 = b2;
-            if (ANY_HIT) return true;
-            t_max = t;
-          }
-        }
-      } else {
-        const uint32_t axis = (meta >> 16) & 0xffu;
-        const bool neg = axis == 0 ? nx : (axis == 1 ? ny : nz);
-        if (sp_ < PT_STACK_SIZE) stack[sp_] = neg ? curr + 1 : offset;
-        ++sp_;
-        curr = neg ? offset : curr + 1;
-        descend = true;
-      }
-    }
-    if (!descend) {
-      if (sp_ == 0) break;
-      --sp_;
-      curr = stack[sp_ < PT_STACK_SIZE ? sp_ : PT_STACK_SIZE - 1];
-    }
-  }
-  return found;
-}
+#define PT_NO_NODE 0xffffffffu
 
 // ------------------------------------------------------------------------------------------------------
+// Device node order.  ptrs_scene_create() keeps the reference's 32-byte LinearBVHNode records but stores
+// the two children of every interior node SIDE BY SIDE (one 64-byte, 64-byte-aligned pair; the root sits
+// alone in slot 0, slot 1 is padding), pairs in depth-first order.  An interior node's `offset` is the
+// index of its first (left) child, the second child is offset + 1.  One traversal step therefore fetches
+// one contiguous 64 B block instead of two unrelated 32 B records.  Boxes, split axes, leaf ranges and
+// therefore the visit order are exactly those of accelerator.rs:348-357's flattened tree.
+//
 // Streaming traversal engine for the bulk kernels.
 //
-// A warp owns 32 ray slots.  Each lane takes ITS ray through exactly the box-test / triangle-test
-// decisions of accelerator.rs:359-475 (hits, tie-breaks and visit counts are unchanged), but:
-//   refill   lanes whose ray has ended pull new work items with ONE atomicAdd for the whole warp
-//            (persistent threads, warp-aggregated fetch) as soon as PT_REFILL_IDLE lanes are idle —
-//            no lane waits for the slowest ray of a batch
-//   expand   a lane standing on an interior node loads BOTH children (two independent 32 B fetches in
-//            flight) and runs both slab tests.  The near child (dir_is_neg[axis]) is accepted against the
-//            current t_max, as the reference does immediately; the far child's geometric result and entry
-//            distance go on the stack, and `t_entry < t_max` is applied when it is popped — the very test
-//            the reference performs at that moment, since only that comparison depends on t_max.
-//            Far children that already fail are never pushed.
-//   leaves   lanes holding a leaf intersect its triangles together (phase B) once fewer than
-//            PT_SEARCH_MIN lanes are still descending
-// Stack entries are 16 B {node index, entry distance, offset, n_prims | axis << 16}: a pop needs no reload.
+// A warp owns 32 ray slots.  Each lane takes ITS ray through the box-test / triangle-test decisions of
+// accelerator.rs:359-475, with:
+//   refill     lanes whose ray has ended pull new work items with ONE atomicAdd for the whole warp
+//              (persistent threads, warp-aggregated fetch) as soon as PT_REFILL_IDLE lanes are idle
+//   expand     a lane standing on an interior node loads BOTH children and runs both slab tests.  The
+//              near child (dir_is_neg[axis]) is accepted against t_max; the far child's entry distance goes
+//              on the stack, and `t_entry < t_max` is applied again when it is popped — the very test the
+//              reference performs at that moment, since only that comparison depends on t_max
+//   postpone   (fast variant) a lane that reaches a leaf parks it and keeps descending until it holds a
+//              second leaf; the warp switches to the triangle phase when fewer than PT_BOX_MIN lanes can
+//              still take a box step.  Exactness: with nested boxes the slab entry distance can only grow
+//              from a node to its descendants (float subtraction and multiplication are monotonic), so a
+//              node accepted under a stale (larger) t_max that the reference would have culled can only
+//              lead to leaves whose own entry distance fails the CURRENT t_max — and every parked node is
+//              re-validated with `t_entry < t_max` whenever a hit shrinks t_max, every stack entry when
+//              it is popped.  Leaves are processed first-in first-out, so each triangle is tested in the
+//              reference's order against the reference's t_max: hits, ties and barycentrics are identical.
+// Stack entries are 16 B {entry distance, offset, n_prims | axis << 16, -}: a pop needs no node reload.
 //
 // Work is a functor object with
 //   bool begin(uint32_t item, LaneRay* r)                       first ray of a work item (false: nothing to trace)
@@ -280,18 +231,48 @@ struct LaneRay {
 #ifndef PT_SEARCH_MIN
 #define PT_SEARCH_MIN 6
 #endif
-#define PT_NO_NODE 0xffffffffu
+#ifndef PT_BOX_MIN
+#define PT_BOX_MIN 12
+#endif
 
-template <bool COUNT, class Work>
-PT_DEV void trace_stream(const DevScene& sc, uint32_t n_items, uint32_t* ticket, Work& work, uint32_t* c_nodes, uint32_t* c_tris) {
+// empty accelerator: every ray misses (accelerator.rs:360-362)
+template <class Work>
+PT_DEV void trace_empty(uint32_t n_items, uint32_t* ticket, Work& work) {
+  DevHit miss;
+  miss.prim = -1;
+  miss.t = miss.b0 = miss.b1 = miss.b2 = 0.f;
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    const uint32_t base = (lane == 0) ? atomicAdd(ticket, 32u) : 0u;
+    const uint32_t b = __shfl_sync(0xffffffffu, base, 0);
+    if (b >= n_items) return;
+    const uint32_t i = b + lane;
+    if (i < n_items) {
+      LaneRay r;
+      bool more = work.begin(i, &r);
+      while (more) more = work.end(i, miss, false, &r);
+    }
+  }
+}
+
+// ---- fast variant (no visit counters) ------------------------------------------------------------------
+template <class Work>
+PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, Work& work) {
+  if (sc.n_nodes == 0) {
+    trace_empty(n_items, ticket, work);
+    return;
+  }
   const uint32_t FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const uint32_t lane_lt = (1u << lane) - 1u;
   uint4 stack[PT_STACK_SIZE];
   int sp_ = 0;
-  // current node (its box test already passed): index, offset, meta; PT_NO_NODE = need to pop
-  uint32_t cur = PT_NO_NODE, cur_off = 0, cur_meta = 0;
-  bool active = false, exhausted = false, done_ray = false;
+  // node in hand (its box test passed under the t_max current at that time): offset, meta, entry distance
+  uint32_t cur_off = 0, cur_meta = PT_NO_NODE;
+  float cur_t = 0.f;
+  // parked leaf: first primitive, count (0 = none), next triangle
+  uint32_t pl_off = 0, pl_cnt = 0, pl_i = 0;
+  bool live = false, exhausted = n_items == 0;
   bool any_hit = false, found = false;
   uint32_t item = 0;
   V3 o = mk3(0, 0, 0), inv_dir = mk3(0, 0, 0);
@@ -301,7 +282,186 @@ PT_DEV void trace_stream(const DevScene& sc, uint32_t n_items, uint32_t* ticket,
   DevHit hit;
   hit.prim = -1;
   hit.t = hit.b0 = hit.b1 = hit.b2 = 0.f;
-  const DevHit miss = hit;
+
+  auto start_ray = [&](const LaneRay& r) {
+    o = r.o;
+    inv_dir = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    nx = inv_dir.x < 0.0f;
+    ny = inv_dir.y < 0.0f;
+    nz = inv_dir.z < 0.0f;
+    rp = ray_precompute(r.d);
+    t_max = r.t_max;
+    any_hit = r.any_hit;
+    found = false;
+    hit.prim = -1;
+    hit.t = r.t_max;
+    hit.b0 = hit.b1 = hit.b2 = 0.f;
+    sp_ = 0;
+    pl_cnt = 0;
+    // root: tested like any other node (accelerator.rs:372-374)
+    const NodeLoad n = load_node(sc.nodes, 0);
+    float te;
+    if (box_geom(n, o, inv_dir, nx, ny, nz, &te) && te < t_max) {
+      cur_off = __float_as_uint(n.b.z);
+      cur_meta = __float_as_uint(n.b.w);
+      cur_t = te;
+    } else {
+      cur_meta = PT_NO_NODE;
+    }
+  };
+
+  for (;;) {
+    // ---- refill ------------------------------------------------------------------------------------
+    const uint32_t idle = __ballot_sync(FULL, !live);
+    if (!exhausted && (__popc(idle) >= PT_REFILL_IDLE)) {
+      const int leader = __ffs(idle) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(ticket, (uint32_t)__popc(idle));
+      base = __shfl_sync(FULL, base, leader);
+      if (base + (uint32_t)__popc(idle) >= n_items) exhausted = true;
+      if (!live) {
+        const uint32_t i = base + (uint32_t)__popc(idle & lane_lt);
+        if (i < n_items) {
+          LaneRay r;
+          if (work.begin(i, &r)) {
+            item = i;
+            live = true;
+            start_ray(r);
+          }
+        }
+      }
+    }
+    if (__ballot_sync(FULL, live) == 0) {
+      if (exhausted) break;
+      continue;
+    }
+
+    // ---- box phase: pop / park / expand ----------------------------------------------------------------
+    for (;;) {
+      const bool cur_leaf = cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0;
+      const bool can_box = live && ((cur_meta != PT_NO_NODE && !cur_leaf) || (cur_meta == PT_NO_NODE && sp_ > 0) || (cur_leaf && pl_cnt == 0));
+      const uint32_t bmask = __ballot_sync(FULL, can_box);
+      if (bmask == 0) break;
+      if (__popc(bmask) < PT_BOX_MIN && __ballot_sync(FULL, live && !can_box) != 0) break;
+      if (can_box) {
+        if (cur_meta == PT_NO_NODE) {  // pop one entry; the reference's box test at pop time
+          --sp_;
+          const uint4 e = stack[sp_];
+          if (__uint_as_float(e.x) < t_max) {
+            cur_t = __uint_as_float(e.x);
+            cur_off = e.y;
+            cur_meta = e.z;
+          }
+        }
+        if (cur_meta != PT_NO_NODE) {
+          if ((cur_meta & 0xffffu) != 0) {
+            if (pl_cnt == 0) {  // park the leaf, keep descending
+              pl_off = cur_off;
+              pl_cnt = cur_meta & 0xffffu;
+              pl_i = 0;
+              cur_meta = PT_NO_NODE;
+            }
+          } else {
+            const NodeLoad L = load_node(sc.nodes, cur_off);
+            const NodeLoad R = load_node(sc.nodes, cur_off + 1);
+            const uint32_t axis = (cur_meta >> 16) & 0xffu;
+            const bool neg = axis == 0 ? nx : (axis == 1 ? ny : nz);
+            float tl, tr;
+            const bool gl = box_geom(L, o, inv_dir, nx, ny, nz, &tl);
+            const bool gr = box_geom(R, o, inv_dir, nx, ny, nz, &tr);
+            // near child first (accelerator.rs:393-404)
+            const bool gn = neg ? gr : gl, gf = neg ? gl : gr;
+            const float tn = neg ? tr : tl, tf = neg ? tl : tr;
+            const float4 nb = neg ? R.b : L.b, fb = neg ? L.b : R.b;
+            if (gf && tf < t_max) {
+              if (sp_ < PT_STACK_SIZE) {
+                stack[sp_] = make_uint4(__float_as_uint(tf), __float_as_uint(fb.z), __float_as_uint(fb.w), 0u);
+                ++sp_;
+              }
+            }
+            if (gn && tn < t_max) {
+              cur_t = tn;
+              cur_off = __float_as_uint(nb.z);
+              cur_meta = __float_as_uint(nb.w);
+            } else {
+              cur_meta = PT_NO_NODE;
+            }
+          }
+        }
+      }
+    }
+
+    // ---- triangle phase: parked leaves, first in first out -----------------------------------------------
+    for (;;) {
+      if (live && pl_cnt == 0 && cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0) {  // second leaf moves up
+        pl_off = cur_off;
+        pl_cnt = cur_meta & 0xffffu;
+        pl_i = 0;
+        cur_meta = PT_NO_NODE;
+      }
+      const bool has = live && pl_cnt != 0;
+      if (__ballot_sync(FULL, has) == 0) break;
+      if (has) {
+        const uint32_t prim = pl_off + pl_i;
+        const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim);
+        const float4 v1 = __ldg(sc.tri_verts + 3 * (size_t)prim + 1);
+        const float4 v2 = __ldg(sc.tri_verts + 3 * (size_t)prim + 2);
+        ++pl_i;
+        if (pl_i == pl_cnt) pl_cnt = 0;
+        float t, b0, b1, b2;
+        if (tri_core(mk3(v0), mk3(v1), mk3(v2), o, rp, t_max, &t, &b0, &b1, &b2) &&
+            !tri_post_reject(sc, (int)prim, mk3(v0), mk3(v1), mk3(v2), __float_as_uint(v2.w), b0, b1, b2, !any_hit)) {
+          found = true;
+          hit.prim = (int)prim;
+          hit.t = t;
+          hit.b0 = b0;
+          hit.b1 = b1;
+          hit.b2 = b2;
+          t_max = t;
+          if (any_hit) {  // intersect_p returns at the first hit (accelerator.rs:435-442)
+            pl_cnt = 0;
+            sp_ = 0;
+            cur_meta = PT_NO_NODE;
+          } else if (cur_meta != PT_NO_NODE && !(cur_t < t_max)) {
+            cur_meta = PT_NO_NODE;  // the node in hand was accepted under the old t_max: re-validate
+          }
+        }
+      }
+    }
+
+    // ---- rays that ran out of nodes --------------------------------------------------------------------
+    if (live && cur_meta == PT_NO_NODE && sp_ == 0 && pl_cnt == 0) {
+      LaneRay r;
+      if (work.end(item, hit, found, &r)) start_ray(r);
+      else live = false;
+    }
+  }
+}
+
+// ---- counting variant: strictly the reference's node-test sequence (no postponed leaves), so that the
+// node / triangle test counters equal the CPU path's ------------------------------------------------------
+template <class Work>
+PT_DEV void trace_counted(const DevScene& sc, uint32_t n_items, uint32_t* ticket, Work& work, uint32_t* c_nodes, uint32_t* c_tris) {
+  if (sc.n_nodes == 0) {
+    trace_empty(n_items, ticket, work);
+    return;
+  }
+  const uint32_t FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  uint4 stack[PT_STACK_SIZE];
+  int sp_ = 0;
+  uint32_t cur_off = 0, cur_meta = PT_NO_NODE;
+  bool active = false, exhausted = n_items == 0, done_ray = false;
+  bool any_hit = false, found = false;
+  uint32_t item = 0;
+  V3 o = mk3(0, 0, 0), inv_dir = mk3(0, 0, 0);
+  bool nx = false, ny = false, nz = false;
+  RayPre rp = ray_precompute(mk3(0, 0, 1));
+  float t_max = 0.f;
+  DevHit hit;
+  hit.prim = -1;
+  hit.t = hit.b0 = hit.b1 = hit.b2 = 0.f;
 
   auto start_ray = [&](const LaneRay& r) {
     o = r.o;
@@ -318,37 +478,19 @@ PT_DEV void trace_stream(const DevScene& sc, uint32_t n_items, uint32_t* ticket,
     hit.b0 = hit.b1 = hit.b2 = 0.f;
     sp_ = 0;
     done_ray = false;
-    // root: tested like any other node (accelerator.rs:372-374)
     const NodeLoad n = load_node(sc.nodes, 0);
-    if (COUNT) ++*c_nodes;
+    ++*c_nodes;
     float te;
     if (box_geom(n, o, inv_dir, nx, ny, nz, &te) && te < t_max) {
-      cur = 0;
       cur_off = __float_as_uint(n.b.z);
       cur_meta = __float_as_uint(n.b.w);
     } else {
-      cur = PT_NO_NODE;
+      cur_meta = PT_NO_NODE;
       done_ray = true;
     }
   };
 
-  if (sc.n_nodes == 0) {  // empty accelerator: every ray misses (accelerator.rs:360-362)
-    for (;;) {
-      const uint32_t base = (lane == 0) ? atomicAdd(ticket, 32u) : 0u;
-      const uint32_t b = __shfl_sync(FULL, base, 0);
-      if (b >= n_items) return;
-      const uint32_t i = b + lane;
-      if (i < n_items) {
-        LaneRay r;
-        bool more = work.begin(i, &r);
-        while (more) more = work.end(i, miss, false, &r);
-      }
-    }
-  }
-  exhausted = n_items == 0;
-
   for (;;) {
-    // ---- refill ------------------------------------------------------------------------------------
     const uint32_t idle = __ballot_sync(FULL, !active);
     if (!exhausted && (__popc(idle) >= PT_REFILL_IDLE)) {
       const int leader = __ffs(idle) - 1;
@@ -372,68 +514,55 @@ PT_DEV void trace_stream(const DevScene& sc, uint32_t n_items, uint32_t* ticket,
       if (exhausted) break;
       continue;
     }
-
-    // ---- phase A: descend until a leaf is in hand ---------------------------------------------------
+    // phase A: descend until a leaf is in hand
     for (;;) {
-      // pop until an entry survives the t_max test (the reference's box test at pop time)
-      if (active && !done_ray && cur == PT_NO_NODE) {
-        for (;;) {
+      if (active && !done_ray && cur_meta == PT_NO_NODE) {
+        for (;;) {  // pop until an entry survives the t_max test (the reference's box test at pop time)
           if (sp_ == 0) {
             done_ray = true;
             break;
           }
           --sp_;
           const uint4 e = stack[sp_ < PT_STACK_SIZE ? sp_ : PT_STACK_SIZE - 1];
-          if (COUNT) ++*c_nodes;
-          if (__uint_as_float(e.y) < t_max) {
-            cur = e.x;
-            cur_off = e.z;
-            cur_meta = e.w;
+          ++*c_nodes;
+          if (__uint_as_float(e.x) < t_max) {
+            cur_off = e.y;
+            cur_meta = e.z;
             break;
           }
         }
       }
       const bool is_leaf = (cur_meta & 0xffffu) != 0;
-      const bool search = active && !done_ray && cur != PT_NO_NODE && !is_leaf;
+      const bool search = active && !done_ray && cur_meta != PT_NO_NODE && !is_leaf;
       const uint32_t smask = __ballot_sync(FULL, search);
       if (smask == 0) break;
-      const uint32_t lmask = __ballot_sync(FULL, active && !done_ray && cur != PT_NO_NODE && is_leaf);
-      if (lmask != 0 && __popc(smask) < PT_SEARCH_MIN) break;  // few lanes still descending: let the leaf holders go
+      const uint32_t lmask = __ballot_sync(FULL, active && !done_ray && cur_meta != PT_NO_NODE && is_leaf);
+      if (lmask != 0 && __popc(smask) < PT_SEARCH_MIN) break;
       if (search) {
-        const uint32_t li = cur + 1, ri = cur_off;
-        const NodeLoad L = load_node(sc.nodes, li);
-        const NodeLoad R = load_node(sc.nodes, ri);
+        const NodeLoad L = load_node(sc.nodes, cur_off);
+        const NodeLoad R = load_node(sc.nodes, cur_off + 1);
         const uint32_t axis = (cur_meta >> 16) & 0xffu;
         const bool neg = axis == 0 ? nx : (axis == 1 ? ny : nz);
         float tl, tr;
         const bool gl = box_geom(L, o, inv_dir, nx, ny, nz, &tl);
         const bool gr = box_geom(R, o, inv_dir, nx, ny, nz, &tr);
-        // near child first (accelerator.rs:393-404)
         const bool gn = neg ? gr : gl, gf = neg ? gl : gr;
         const float tn = neg ? tr : tl, tf = neg ? tl : tr;
-        const uint32_t ni = neg ? ri : li, fi = neg ? li : ri;
         const float4 nb = neg ? R.b : L.b, fb = neg ? L.b : R.b;
-        if (COUNT) {
-          ++*c_nodes;  // the near child's test; the far child's is counted when it is popped
-          if (sp_ < PT_STACK_SIZE) stack[sp_] = make_uint4(fi, __float_as_uint(gf ? tf : CUDART_INF_F), __float_as_uint(fb.z), __float_as_uint(fb.w));
-          ++sp_;
-        } else if (gf && tf < t_max) {
-          if (sp_ < PT_STACK_SIZE) stack[sp_] = make_uint4(fi, __float_as_uint(tf), __float_as_uint(fb.z), __float_as_uint(fb.w));
-          ++sp_;
-        }
+        ++*c_nodes;  // the near child's test; the far child's is counted when it is popped
+        if (sp_ < PT_STACK_SIZE) stack[sp_] = make_uint4(__float_as_uint(gf ? tf : CUDART_INF_F), __float_as_uint(fb.z), __float_as_uint(fb.w), 0u);
+        ++sp_;
         if (gn && tn < t_max) {
-          cur = ni;
           cur_off = __float_as_uint(nb.z);
           cur_meta = __float_as_uint(nb.w);
         } else {
-          cur = PT_NO_NODE;
+          cur_meta = PT_NO_NODE;
         }
       }
     }
-
-    // ---- phase B: triangles of the leaf in hand ------------------------------------------------------
+    // phase B: triangles of the leaf in hand
     {
-      const bool have_leaf = active && !done_ray && cur != PT_NO_NODE && (cur_meta & 0xffffu) != 0;
+      const bool have_leaf = active && !done_ray && cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0;
       uint32_t cnt = have_leaf ? (cur_meta & 0xffffu) : 0u;
       for (uint32_t i = 0; __ballot_sync(FULL, i < cnt) != 0; ++i) {
         if (i < cnt) {
@@ -441,7 +570,7 @@ PT_DEV void trace_stream(const DevScene& sc, uint32_t n_items, uint32_t* ticket,
           const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim);
           const float4 v1 = __ldg(sc.tri_verts + 3 * (size_t)prim + 1);
           const float4 v2 = __ldg(sc.tri_verts + 3 * (size_t)prim + 2);
-          if (COUNT) ++*c_tris;
+          ++*c_tris;
           float t, b0, b1, b2;
           if (tri_core(mk3(v0), mk3(v1), mk3(v2), o, rp, t_max, &t, &b0, &b1, &b2) &&
               !tri_post_reject(sc, (int)prim, mk3(v0), mk3(v1), mk3(v2), __float_as_uint(v2.w), b0, b1, b2, !any_hit)) {
@@ -452,23 +581,27 @@ PT_DEV void trace_stream(const DevScene& sc, uint32_t n_items, uint32_t* ticket,
             hit.b1 = b1;
             hit.b2 = b2;
             t_max = t;
-            if (any_hit) {  // intersect_p returns at the first hit (accelerator.rs:435-442)
+            if (any_hit) {
               cnt = 0;
               done_ray = true;
             }
           }
         }
       }
-      if (have_leaf) cur = PT_NO_NODE;
+      if (have_leaf) cur_meta = PT_NO_NODE;
     }
-
-    // ---- rays that ran out of nodes --------------------------------------------------------------------
-    if (active && (done_ray || (cur == PT_NO_NODE && sp_ == 0))) {
+    if (active && (done_ray || (cur_meta == PT_NO_NODE && sp_ == 0))) {
       LaneRay r;
       if (work.end(item, hit, found, &r)) start_ray(r);
       else active = false;
     }
   }
+}
+
+template <bool COUNT, class Work>
+PT_DEV void trace_stream(const DevScene& sc, uint32_t n_items, uint32_t* ticket, Work& work, uint32_t* c_nodes, uint32_t* c_tris) {
+  if (COUNT) trace_counted(sc, n_items, ticket, work, c_nodes, c_tris);
+  else trace_fast(sc, n_items, ticket, work);
 }
 
 }  // namespace ptrs

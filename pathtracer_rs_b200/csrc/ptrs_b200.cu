@@ -437,8 +437,39 @@ int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) {
     if (l.type == PTRS_LIGHT_INFINITE && (l.env < 0 || (uint32_t)l.env >= d->n_envs)) return fail(PTRS_ERR_INVALID_ARGUMENT, "env id out of range");
   }
 
-  // re-layout: nodes verbatim (32 B), triangles as 3 x float4 with metadata in .w
-  CUDA_TRY(s->nodes.upload(reinterpret_cast<const float4*>(d->nodes), (size_t)d->n_nodes * 2));
+  // re-layout: the 32 B node records are kept, but the two children of every interior node are placed side
+  // by side (64 B pairs in depth-first order, root alone in slot 0) so that one traversal step reads one
+  // contiguous 64 B block; triangles become 3 x float4 with metadata in .w
+  {
+    std::vector<PtrsBvhNode> dev_nodes;
+    if (d->n_nodes > 0) {
+      dev_nodes.reserve(2 * (size_t)d->n_nodes);
+      dev_nodes.resize(2);
+      std::memset(dev_nodes.data(), 0, 2 * sizeof(PtrsBvhNode));
+      dev_nodes[0] = d->nodes[0];
+      std::vector<std::pair<uint32_t, uint32_t>> todo;  // (reference index, device index) of interior nodes
+      if (d->nodes[0].n_prims == 0) todo.emplace_back(0u, 0u);
+      uint64_t placed = 1;
+      while (!todo.empty()) {
+        const auto [ri, di] = todo.back();
+        todo.pop_back();
+        const uint32_t left = ri + 1, right = d->nodes[ri].offset;
+        if (right <= left) return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH node (second child must follow the first child's subtree)");
+        placed += 2;
+        if (placed > d->n_nodes) return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH (nodes are shared between subtrees)");
+        const uint32_t k = (uint32_t)dev_nodes.size();
+        dev_nodes.push_back(d->nodes[left]);
+        dev_nodes.push_back(d->nodes[right]);
+        dev_nodes[di].offset = k;
+        // depth-first: the left subtree's pairs follow immediately, so push right first
+        if (d->nodes[right].n_prims == 0) todo.emplace_back(right, k + 1);
+        if (d->nodes[left].n_prims == 0) todo.emplace_back(left, k);
+      }
+    }
+    static_assert(sizeof(PtrsBvhNode) == 32, "LinearBVHNode is 32 bytes");
+    CUDA_TRY(s->nodes.upload(reinterpret_cast<const float4*>(dev_nodes.data()), dev_nodes.size() * 2));
+    s->scene_bytes += (uint64_t)dev_nodes.size() * 32;
+  }
   {
     std::vector<float4> tv((size_t)d->n_prims * 3);
     std::vector<uint4> ti(d->n_prims);
@@ -541,7 +572,7 @@ int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) {
     std::memcpy(s->world_bound, d->nodes[0].bounds_min, 12);
     std::memcpy(s->world_bound + 3, d->nodes[0].bounds_max, 12);
   }
-  s->scene_bytes += (uint64_t)d->n_nodes * 32 + (uint64_t)d->n_prims * 64 + (uint64_t)d->n_verts * 4 * ((d->normal ? 3 : 0) + (d->tangent ? 3 : 0) + (d->uv ? 2 : 0)) +
+  s->scene_bytes += (uint64_t)d->n_prims * 64 + (uint64_t)d->n_verts * 4 * ((d->normal ? 3 : 0) + (d->tangent ? 3 : 0) + (d->uv ? 2 : 0)) +
                     d->n_texels * 4 + (uint64_t)sh.n_dims * sh.n_cols * 4;
   CUDA_TRY(cudaEventCreate(&s->ev[0]));
   CUDA_TRY(cudaEventCreate(&s->ev[1]));

@@ -43,24 +43,37 @@ __global__ void __launch_bounds__(256) generate_kernel(const __grid_constant__ R
       ps.scramble = pixel_scramble(px, py);
       ps.index = sobol_interval_to_index(rc.sobol, (uint64_t)s, px - rc.sobol.bounds_min[0], py - rc.sobol.bounds_min[1]);
       ps.dimension = 0;
-  ps.win_base = 0xffffffffu;
       ps.win_base = 0xffffffffu;
       V2 u = get_2d(rc.sobol, sobol, ps);
       const float fx = (float)px + u.x, fy = (float)py + u.y;  // get_camera_sample, sobol.rs:116-120
       V3 o, d;
       camera_ray(rc.cam, fx, fy, rc.diff_scale, &o, &d, nullptr, nullptr);
-      P.ray_o[i] = make_float4(o.x, o.y, o.z, 0.f);
-      P.ray_d[i] = make_float4(d.x, d.y, d.z, 0.f);
-      P.beta[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+      PathRay r;
+      r.ox = o.x;
+      r.oy = o.y;
+      r.oz = o.z;
+      r.packed = pack_state(ps.dimension | PT_F_HAS_DIFF, 0);
+      r.dx = d.x;
+      r.dy = d.y;
+      r.dz = d.z;
+      r.eta_scale = 1.f;
+      PathAux a;
+      a.br = a.bg = a.bb = 1.f;
+      a.pixel = pack_pixel(px, py);
+      a.sobol_index = ps.index;
+      a.fx = fx;
+      a.fy = fy;
+      st256(&P.slot[i].r, r);
+      st256(&P.slot[i].a, a);
       P.L[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      P.sobol_index[i] = ps.index;
-      P.pixel[i] = make_int2(px, py);
-      P.bounces[i] = 0;
-      P.flags[i] = ps.dimension | PT_F_HAS_DIFF;
-      P.p_film[i] = make_float2(fx, fy);
     } else if (i < n_work) {
+      PathAux a;
+      a.br = a.bg = a.bb = 0.f;
+      a.pixel = 0u;
+      a.sobol_index = 0ull;
+      a.fx = a.fy = -1e30f;  // padding lane of an 8x4 block outside the sample bounds
+      st256(&P.slot[i].a, a);
       P.L[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      P.p_film[i] = make_float2(-1e30f, -1e30f);  // padding lane of an 8x4 block outside the sample bounds
     }
     warp_push(valid, i, q_ext, &ctr->n_ext);
   }
@@ -77,12 +90,12 @@ __global__ void __launch_bounds__(128) shade_miss_kernel(DevScene sc, PathArrays
     const uint32_t i = base + lane;
     if (i >= n) continue;
     const int p = q[i];
-    const uint32_t flags = P.flags[p];
-    if (P.bounces[p] == 0 || (flags & PT_F_SPECULAR)) {
-      const float4 b4 = P.beta[p];
+    const PathRay r = ld256(&P.slot[p].r);
+    if (packed_bounces(r.packed) == 0 || (r.packed & PT_F_SPECULAR)) {
+      const PathAux a = ld256(&P.slot[p].a);
       float4 l4 = P.L[p];
-      const V3 d = mk3(P.ray_d[p]);
-      Spec l = sp(l4.x, l4.y, l4.z), beta = sp(b4.x, b4.y, b4.z);
+      const V3 d = mk3(r.dx, r.dy, r.dz);
+      Spec l = sp(l4.x, l4.y, l4.z), beta = sp(a.br, a.bg, a.bb);
       for (uint32_t k = 0; k < sc.n_infinite_lights; ++k) l = l + beta * env_le(sc, sc.lights[sc.infinite_lights[k]], d);
       P.L[p] = make_float4(l.r, l.g, l.b, 0.f);
     }
@@ -96,7 +109,7 @@ __global__ void __launch_bounds__(256) accumulate_kernel(const __grid_constant__
   const uint32_t stride = gridDim.x * blockDim.x;
   const int W = rc.cam.width, H = rc.cam.height;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float2 pf = P.p_film[i];
+    const float2 pf = *reinterpret_cast<const float2*>(&P.slot[i].a.fx);
     if (pf.x < -1e29f) continue;
     const float4 l = P.L[i];
     const float dx = pf.x - 0.5f, dy = pf.y - 0.5f;

@@ -112,60 +112,68 @@ PT_DEV void nee_prepare(const DevScene& sc, const SurfInter& si, const Bsdf& bsd
 #define PT_SHADE_MIN_BLOCKS 4
 #endif
 
-// both appends of a warp (connect queue, next extend queue) with their atomics in flight together
-PT_DEV void warp_push2(bool pa, int* qa, uint32_t* na, bool pb, int* qb, uint32_t* nb, uint32_t item) {
-  const uint32_t ma = __ballot_sync(0xffffffffu, pa), mb = __ballot_sync(0xffffffffu, pb);
-  const int lane = threadIdx.x & 31;
-  uint32_t ba = 0, bb = 0;
-  if (lane == 0) {
-    if (ma) ba = atomicAdd(na, (uint32_t)__popc(ma));
-    if (mb) bb = atomicAdd(nb, (uint32_t)__popc(mb));
-  }
-  ba = __shfl_sync(0xffffffffu, ba, 0);
-  bb = __shfl_sync(0xffffffffu, bb, 0);
-  const uint32_t lt = (1u << lane) - 1u;
-  if (pa) qa[ba + __popc(ma & lt)] = (int)item;
-  if (pb) qb[bb + __popc(mb & lt)] = (int)item;
-}
-
 template <int MAT>
 __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ RenderConst rc, DevScene sc, PathArrays P,
-                                                     const int* __restrict__ q, int* __restrict__ q_ext_next, int* __restrict__ q_nee,
-                                                     RoundCounters* ctr, RoundCounters* ctr_next) {
+                                                     const int* __restrict__ q, const float4* __restrict__ q_hit, int* __restrict__ q_ext_next,
+                                                     int* __restrict__ q_nee, RoundCounters* ctr, RoundCounters* ctr_next) {
   const uint32_t n = ctr->n_class[MAT];
   const int lane = threadIdx.x & 31;
   const uint32_t* __restrict__ sobol = sc.sobol;
   // shade work is uniform per item (one material type per launch): static striding, no ticket atomic
   const uint32_t warp_stride = (gridDim.x * blockDim.x) & ~31u;
-  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += warp_stride) {
+  uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
+  // the item after this one is known one iteration ahead: its slot record and triangle are prefetched while
+  // the current item is shaded
+  int p_next = 0, prim_next = 0;
+  if (base + lane < n) {
+    p_next = q[base + lane];
+    prim_next = __float_as_int(q_hit[base + lane].x);
+  }
+  for (; base < n; base += warp_stride) {
     const uint32_t i = base + lane;
     bool push_ext = false, push_nee = false;
-    int p = 0;
+    const int p = p_next;
+    NeeRec nee;
     if (i < n) {
-      p = q[i];
-      const V3 ray_d = mk3(P.ray_d[p]);
-      const int prim = P.hit_prim[p];
-      const float4 tb = P.hit_tb[p];
+      const int prim = prim_next;
+      const float4 hb = q_hit[i];
+      const PathRay pr = ld256(&P.slot[p].r);
+      const PathAux pa = ld256(&P.slot[p].a);
+      const uint32_t i_next = i + warp_stride;
+      if (i_next < n) {
+        p_next = q[i_next];
+        prim_next = __float_as_int(q_hit[i_next].x);
+      }
+      const V3 ray_d = mk3(pr.dx, pr.dy, pr.dz);
       SurfInter si;
-      reconstruct_hit(sc, prim, tb.y, tb.z, tb.w, ray_d, &si);
-      uint32_t flags = P.flags[p];
-      int bounces = P.bounces[p];
-      const float4 b4 = P.beta[p];
-      Spec beta = sp(b4.x, b4.y, b4.z);
-      float eta_scale = b4.w;
-      const float4 l4 = P.L[p];
-      Spec L = sp(l4.x, l4.y, l4.z);
+      reconstruct_hit(sc, prim, hb.y, hb.z, hb.w, ray_d, &si);
+      if (i_next < n) {
+        prefetch_l1(&P.slot[p_next]);
+        prefetch_l1(sc.tri_verts + 3 * (size_t)prim_next);
+        prefetch_l1(sc.tri_verts + 3 * (size_t)prim_next + 2);
+        prefetch_l1(sc.tri_index + prim_next);
+      }
+      uint32_t flags = pr.packed & 0x00ffffffu;
+      int bounces = packed_bounces(pr.packed);
+      Spec beta = sp(pa.br, pa.bg, pa.bb);
+      float eta_scale = pr.eta_scale;
       const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim), v1 = __ldg(sc.tri_verts + 3 * (size_t)prim + 1);
       const int mat_id = __float_as_int(v0.w), light_id = __float_as_int(v1.w);
       // emitted radiance at the vertex (integrator.rs:418-422)
-      if (bounces == 0 || (flags & PT_F_SPECULAR)) L = L + beta * area_le(sc, light_id, si, -ray_d);
+      if (bounces == 0 || (flags & PT_F_SPECULAR)) {
+        const Spec add = beta * area_le(sc, light_id, si, -ray_d);
+        if (!is_black(add)) {  // L + 0 == L: the read-modify-write is skipped for the (common) non-emitter
+          const float4 l4 = P.L[p];
+          const Spec L = sp(l4.x, l4.y, l4.z) + add;
+          P.L[p] = make_float4(L.r, L.g, L.b, 0.f);
+        }
+      }
       bool alive = bounces < rc.max_depth;  // integrator.rs:429
       if (alive) {
         if (flags & PT_F_HAS_DIFF) {  // compute_scattering_functions -> compute_differentials
-          const float2 pf = P.p_film[p];
           RayDiff rd;
           V3 o, d;
-          camera_ray(rc.cam, pf.x, pf.y, rc.diff_scale, &o, &d, &rd.rx_d, &rd.ry_d);
+          camera_ray(rc.cam, pa.fx, pa.fy, rc.diff_scale, &o, &d, &rd.rx_d, &rd.ry_d);
           rd.rx_o = o;
           rd.ry_o = o;
           compute_differentials(&si, rd);
@@ -173,20 +181,23 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const _
         flags &= ~PT_F_HAS_DIFF;
         const PtrsMaterial& m = sc.materials[mat_id];
         Bsdf bsdf;
+        PathRay out = pr;
         if (!compute_scattering_functions<MAT>(sc, m, &si, &bsdf)) {
           // null BSDF: continue straight through; `bounces -= 1; continue` nets -1 (integrator.rs:434-439)
           V3 o;
           spawn_ray(si.g, ray_d, &o);
-          P.ray_o[p] = make_float4(o.x, o.y, o.z, 0.f);
+          out.ox = o.x;
+          out.oy = o.y;
+          out.oz = o.z;
           bounces -= 1;
           push_ext = true;
         } else {
           PathSampler ps;
-          const int2 pix = P.pixel[p];
+          const int2 pix = unpack_pixel(pa.pixel);
           ps.px = pix.x;
           ps.py = pix.y;
           ps.scramble = pixel_scramble(pix.x, pix.y);
-          ps.index = P.sobol_index[p];
+          ps.index = pa.sobol_index;
           ps.dimension = flags & 0xffffu;
           sobol_window_fill(sc.sobol_t, ps, ps.dimension);
           // direct lighting (integrator.rs:443-447, 192-217)
@@ -196,17 +207,11 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const _
             float u_idx = get_1d(rc.sobol, sobol, ps);
             unsigned long long li64 = (unsigned long long)floorf(u_idx * (float)sc.n_lights);
             int light_idx = (int)(li64 < (unsigned long long)(sc.n_lights - 1) ? li64 : (unsigned long long)(sc.n_lights - 1));
-            float4 n0, n1, n2, n3, n4;
             float scat_pdf;
             uint32_t nf;
-            nee_prepare(sc, si, bsdf, u_scattering, light_idx, u_light, &n0, &n1, &n2, &n3, &n4, &scat_pdf, &nf);
+            nee_prepare(sc, si, bsdf, u_scattering, light_idx, u_light, &nee.n0, &nee.n1, &nee.n2, &nee.n3, &nee.n4, &scat_pdf, &nf);
             if (nf & (PT_NEE_SHADOW | PT_NEE_MIS)) {
-              P.nee0[p] = n0;
-              P.nee1[p] = n1;
-              P.nee2[p] = n2;
-              P.nee3[p] = n3;
-              P.nee4[p] = n4;
-              P.nee5[p] = make_float4(beta.r, beta.g, beta.b, scat_pdf);
+              nee.n5 = make_float4(beta.r, beta.g, beta.b, scat_pdf);
               push_nee = true;
             }
           }
@@ -236,23 +241,51 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const _
               }
             }
             if (survive) {
-              P.ray_o[p] = make_float4(o.x, o.y, o.z, 0.f);
-              P.ray_d[p] = make_float4(wi.x, wi.y, wi.z, 0.f);
+              out.ox = o.x;
+              out.oy = o.y;
+              out.oz = o.z;
+              out.dx = wi.x;
+              out.dy = wi.y;
+              out.dz = wi.z;
               bounces += 1;
               push_ext = true;
             }
           }
           flags = (flags & 0xffff0000u) | (ps.dimension & 0xffffu);
         }
-      }
-      P.L[p] = make_float4(L.r, L.g, L.b, 0.f);
-      if (push_ext) {
-        P.beta[p] = make_float4(beta.r, beta.g, beta.b, eta_scale);
-        P.bounces[p] = bounces;
-        P.flags[p] = flags;
+        if (push_ext) {
+          out.packed = pack_state(flags, bounces);
+          out.eta_scale = eta_scale;
+          PathAux oa = pa;
+          oa.br = beta.r;
+          oa.bg = beta.g;
+          oa.bb = beta.b;
+          st256(&P.slot[p].r, out);
+          st256(&P.slot[p].a, oa);
+        }
       }
     }
-    warp_push2(push_nee, q_nee, &ctr->n_nee, push_ext, q_ext_next, &ctr_next->n_ext, (uint32_t)p);
+    // both appends of the warp (connect queue with its 96-byte record, next extend queue), atomics in flight together
+    {
+      const uint32_t ma = __ballot_sync(0xffffffffu, push_nee), mb = __ballot_sync(0xffffffffu, push_ext);
+      uint32_t ba = 0, bb = 0;
+      if (lane == 0) {
+        if (ma) ba = atomicAdd(&ctr->n_nee, (uint32_t)__popc(ma));
+        if (mb) bb = atomicAdd(&ctr_next->n_ext, (uint32_t)__popc(mb));
+      }
+      ba = __shfl_sync(0xffffffffu, ba, 0);
+      bb = __shfl_sync(0xffffffffu, bb, 0);
+      const uint32_t lt = (1u << lane) - 1u;
+      if (push_nee) {
+        const uint32_t k = ba + __popc(ma & lt);
+        q_nee[k] = p;
+        F8* dst = reinterpret_cast<F8*>(&P.nee[k]);
+        st256(dst, F8{nee.n0, nee.n1});
+        st256(dst + 1, F8{nee.n2, nee.n3});
+        st256(dst + 2, F8{nee.n4, nee.n5});
+      }
+      if (push_ext) q_ext_next[bb + __popc(mb & lt)] = p;
+    }
   }
 }
 
@@ -264,10 +297,10 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const _
 #define PT_CAT2(a, b) a##b
 #define PT_CAT(a, b) PT_CAT2(a, b)
 void PT_CAT(launch_shade_, PT_SHADE_MAT)(cudaStream_t st, int sm, const RenderConst& rc, const DevScene& sc, const PathArrays& P, const int* q,
-                                         int* q_next, int* q_nee, RoundCounters* ctr, RoundCounters* ctr_next) {
+                                         const float4* q_hit, int* q_next, int* q_nee, RoundCounters* ctr, RoundCounters* ctr_next) {
   static int grid = 0;
   if (!grid) grid = persistent_grid(shade_kernel<PT_SHADE_MAT>, 128, sm);
-  shade_kernel<PT_SHADE_MAT><<<grid, 128, 0, st>>>(rc, sc, P, q, q_next, q_nee, ctr, ctr_next);
+  shade_kernel<PT_SHADE_MAT><<<grid, 128, 0, st>>>(rc, sc, P, q, q_hit, q_next, q_nee, ctr, ctr_next);
 }
 
 }  // namespace ptrs

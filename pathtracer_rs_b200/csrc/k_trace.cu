@@ -34,19 +34,18 @@ struct ExtendWork {
   int p;
   __device__ bool begin(uint32_t i, LaneRay* r) {
     p = q_ext[i];
-    const float4 o4 = P.ray_o[p], d4 = P.ray_d[p];
-    r->o = mk3(o4);
-    r->d = mk3(d4);
+    const PathRay pr = ld256(&P.slot[p].r);
+    r->o = mk3(pr.ox, pr.oy, pr.oz);
+    r->d = mk3(pr.dx, pr.dy, pr.dz);
     r->t_max = CUDART_INF_F;
     r->any_hit = false;
     return true;
   }
   __device__ bool end(uint32_t, const DevHit& h, bool found, LaneRay*) {
-    P.hit_prim[p] = found ? h.prim : -1;
-    P.hit_tb[p] = make_float4(h.t, h.b0, h.b1, h.b2);
     const int cls = found ? sc.materials[__float_as_int(__ldg(&sc.tri_verts[3 * (size_t)h.prim].w))].type : PT_CLASS_MISS;
-    const uint32_t slot = coalesced_slot(&ctr->n_class[cls]);
-    q_class[(size_t)cls * cap + slot] = p;
+    const size_t slot = (size_t)cls * cap + coalesced_slot(&ctr->n_class[cls]);
+    q_class[slot] = p;
+    if (found) P.q_hit[slot] = make_float4(__int_as_float(h.prim), h.b0, h.b1, h.b2);
     return false;
   }
 };
@@ -72,14 +71,14 @@ struct ConnectWork {
   const DevScene& sc;
   const PathArrays& P;
   const int* __restrict__ q_nee;
-  int p;
+  uint32_t idx;  // queue position = index of the NeeRec
   uint32_t nf;
   int stage;  // 0 = shadow ray in flight, 1 = MIS ray in flight
   Spec ld;
   uint32_t n_shadow, n_mis;
 
   __device__ void mis_ray(LaneRay* r) {
-    const float4 n2 = P.nee2[p], n3 = P.nee3[p];
+    const float4 n2 = P.nee[idx].n2, n3 = P.nee[idx].n3;
     r->o = mk3(n2);
     r->d = mk3(n3);
     r->t_max = CUDART_INF_F;
@@ -88,19 +87,20 @@ struct ConnectWork {
     ++n_mis;
   }
   __device__ void finish() {
-    const float4 b5 = P.nee5[p];
+    const int p = q_nee[idx];
+    const float4 b5 = P.nee[idx].n5;
     const float4 l4 = P.L[p];
     const Spec L = sp(l4.x, l4.y, l4.z) + sp(b5.x, b5.y, b5.z) * ((float)sc.n_lights * ld);
     P.L[p] = make_float4(L.r, L.g, L.b, 0.f);
   }
   __device__ bool begin(uint32_t i, LaneRay* r) {
-    p = q_nee[i];
-    nf = __float_as_uint(P.nee3[p].w);
+    idx = i;
+    nf = __float_as_uint(P.nee[i].n3.w);
     ld = sp(0.0f);
     if (nf & PT_NEE_SHADOW) {
-      const float4 n0 = P.nee0[p], n1 = P.nee1[p];
-      r->o = mk3(n0);
-      r->d = mk3(n1);
+      const F8 n01 = ld256(reinterpret_cast<const F8*>(&P.nee[i].n0));
+      r->o = mk3(n01.a);
+      r->d = mk3(n01.b);
       r->t_max = 1.0f - PT_SHADOW_EPSILON;
       r->any_hit = true;
       stage = 0;
@@ -115,7 +115,7 @@ struct ConnectWork {
   }
   __device__ bool end(uint32_t, const DevHit& h, bool found, LaneRay* r) {
     if (stage == 0) {
-      if (!found) ld = ld + sp(P.nee0[p].w, P.nee1[p].w, P.nee2[p].w);
+      if (!found) ld = ld + sp(P.nee[idx].n0.w, P.nee[idx].n1.w, P.nee[idx].n2.w);
       if (nf & PT_NEE_MIS) {
         mis_ray(r);
         return true;
@@ -124,7 +124,7 @@ struct ConnectWork {
       return false;
     }
     const int light_idx = (int)(nf & 0x3fffffffu);
-    const V3 md = mk3(P.nee3[p]);
+    const V3 md = mk3(P.nee[idx].n3);
     Spec li = sp(0.0f);
     if (found) {
       const int hl = __float_as_int(__ldg(&sc.tri_verts[3 * (size_t)h.prim + 1].w));
@@ -137,8 +137,8 @@ struct ConnectWork {
       li = env_le(sc, sc.lights[light_idx], md);
     }
     if (!is_black(li)) {
-      const float4 n4 = P.nee4[p];
-      ld = ld + sp(n4.x, n4.y, n4.z) * li * sp(1.0f) * n4.w / P.nee5[p].w;
+      const float4 n4 = P.nee[idx].n4;
+      ld = ld + sp(n4.x, n4.y, n4.z) * li * sp(1.0f) * n4.w / P.nee[idx].n5.w;
     }
     finish();
     return false;
@@ -149,7 +149,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) connect_kernel(DevScene sc, PathArrays P, const int* __restrict__ q_nee, RoundCounters* ctr,
                                                        GlobalCounters* g) {
   uint32_t c_nodes = 0, c_tris = 0;
-  ConnectWork w{sc, P, q_nee, 0, 0u, 0, sp(0.f), 0u, 0u};
+  ConnectWork w{sc, P, q_nee, 0u, 0u, 0, sp(0.f), 0u, 0u};
   trace_stream<COUNT>(sc, ctr->n_nee, &ctr->t_nee, w, &c_nodes, &c_tris);
   warp_sum_add(w.n_shadow, &g->shadow_rays);
   warp_sum_add(w.n_mis, &g->mis_rays);

@@ -34,8 +34,8 @@ void launch_intersect(cudaStream_t st, int sm, bool any_hit, bool count, const D
 
 // k_shade.cu, built once per PtrsMaterialType
 #define PT_DECL_SHADE(M)                                                                                                              \
-  void launch_shade_##M(cudaStream_t st, int sm, const RenderConst& rc, const DevScene& sc, const PathArrays& P, const int* q, int* q_next, \
-                        int* q_nee, RoundCounters* ctr, RoundCounters* ctr_next);
+  void launch_shade_##M(cudaStream_t st, int sm, const RenderConst& rc, const DevScene& sc, const PathArrays& P, const int* q, const float4* q_hit, \
+                        int* q_next, int* q_nee, RoundCounters* ctr, RoundCounters* ctr_next);
 PT_DECL_SHADE(0) PT_DECL_SHADE(1) PT_DECL_SHADE(2) PT_DECL_SHADE(3) PT_DECL_SHADE(4) PT_DECL_SHADE(5)
 #undef PT_DECL_SHADE
 

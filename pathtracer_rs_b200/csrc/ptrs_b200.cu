@@ -97,38 +97,22 @@ struct DevBuf {
 
 struct Workspace {
   uint32_t cap = 0, rounds = 0;
-  DevBuf<float4> ray_o, ray_d, hit_tb, beta, L, nee[6];
-  DevBuf<int> hit_prim, bounces;
-  DevBuf<uint64_t> sobol_index;
-  DevBuf<int2> pixel;
-  DevBuf<uint32_t> flags;
-  DevBuf<float2> p_film;
+  DevBuf<PathSlot> slot;
+  DevBuf<float4> L, q_hit;
+  DevBuf<NeeRec> nee;
   DevBuf<int> q_ext[2], q_nee, q_class;
   DevBuf<RoundCounters> counters;
   DevBuf<GlobalCounters> gcount;
   PathArrays arrays() {
     PathArrays a;
-    a.ray_o = ray_o.p;
-    a.ray_d = ray_d.p;
-    a.hit_prim = hit_prim.p;
-    a.hit_tb = hit_tb.p;
-    a.beta = beta.p;
+    a.slot = slot.p;
     a.L = L.p;
-    a.sobol_index = sobol_index.p;
-    a.pixel = pixel.p;
-    a.bounces = bounces.p;
-    a.flags = flags.p;
-    a.p_film = p_film.p;
-    a.nee0 = nee[0].p;
-    a.nee1 = nee[1].p;
-    a.nee2 = nee[2].p;
-    a.nee3 = nee[3].p;
-    a.nee4 = nee[4].p;
-    a.nee5 = nee[5].p;
+    a.q_hit = q_hit.p;
+    a.nee = nee.p;
     return a;
   }
   uint64_t bytes() const {
-    return (uint64_t)cap * (16 * 11 + 4 * 2 + 8 + 8 + 4 + 8 + 4 * (3 + PT_N_CLASSES)) + (uint64_t)rounds * sizeof(RoundCounters);
+    return (uint64_t)cap * (sizeof(PathSlot) + 16 + sizeof(NeeRec) + 4 * 3 + (4 + 16) * PT_N_CLASSES) + (uint64_t)rounds * sizeof(RoundCounters);
   }
 };
 
@@ -238,6 +222,10 @@ int32_t build_render_const(const PtrsCamera* cam, const PtrsRenderParams* rp, Re
   rc->sb_min[1] = sby0;
   rc->sb_ext[0] = sbx1 - sbx0;
   rc->sb_ext[1] = sby1 - sby0;
+  if (sbx0 < -32768 || sby0 < -32768 || sbx1 > 32767 || sby1 > 32767) {  // pixel coordinates travel as two int16 in the path record
+    *why = "sample bounds outside the 16-bit pixel range of the path record";
+    return PTRS_ERR_UNSUPPORTED;
+  }
   const int stride = rp->sample_stride > 0 ? rp->sample_stride : 1;
   const int phase = ((rp->sample_phase % stride) + stride) % stride;
   const int s_lo = std::max(rp->sample_begin, 0);
@@ -257,18 +245,10 @@ int32_t ensure_workspace(PtrsScene* s, uint32_t cap, uint32_t rounds) {
   rounds = std::max(rounds, w.rounds);
 #define WS_ALLOC(buf, count) \
   if ((buf).alloc(count) != cudaSuccess) return fail(PTRS_ERR_OUT_OF_MEMORY, "workspace allocation failed")
-  WS_ALLOC(w.ray_o, cap);
-  WS_ALLOC(w.ray_d, cap);
-  WS_ALLOC(w.hit_tb, cap);
-  WS_ALLOC(w.beta, cap);
+  WS_ALLOC(w.slot, cap);
   WS_ALLOC(w.L, cap);
-  for (auto& b : w.nee) WS_ALLOC(b, cap);
-  WS_ALLOC(w.hit_prim, cap);
-  WS_ALLOC(w.bounces, cap);
-  WS_ALLOC(w.sobol_index, cap);
-  WS_ALLOC(w.pixel, cap);
-  WS_ALLOC(w.flags, cap);
-  WS_ALLOC(w.p_film, cap);
+  WS_ALLOC(w.nee, cap);
+  WS_ALLOC(w.q_hit, (size_t)cap * PT_N_CLASSES);
   WS_ALLOC(w.q_ext[0], cap);
   WS_ALLOC(w.q_ext[1], cap);
   WS_ALLOC(w.q_nee, cap);
@@ -344,7 +324,7 @@ int32_t run_batch(PtrsScene* s, const RenderConst& rc, uint64_t work_base, uint3
       }
 #define SHADE(M)                                                                                                               \
   if (s_has_mat[M]) {                                                                                                          \
-    launch_shade_##M(st, sm, rc, s->dev, P, w.q_class.p + (size_t)(M)*cap, q_out, w.q_nee.p, c, c + 1);                        \
+    launch_shade_##M(st, sm, rc, s->dev, P, w.q_class.p + (size_t)(M)*cap, w.q_hit.p + (size_t)(M)*cap, q_out, w.q_nee.p, c, c + 1);                        \
     s->stats.launches += 1;                                                                                                    \
   }
       const bool* s_has_mat = s->has_mat;
@@ -759,7 +739,7 @@ static int32_t render_impl(PtrsScene* s, const PtrsCamera* cam, const PtrsRender
   const uint32_t bw = ((uint32_t)rc.sb_ext[0] + 7u) >> 3, bh = ((uint32_t)rc.sb_ext[1] + 3u) >> 2;
   const uint64_t per_sample = (uint64_t)bw * bh * 32u;
   const uint64_t total = list_xy ? (uint64_t)n_list : per_sample * (uint64_t)rc.s_count;
-  uint32_t cap = rp->paths_per_batch > 0 ? (uint32_t)rp->paths_per_batch : (1u << 22);
+  uint32_t cap = rp->paths_per_batch > 0 ? (uint32_t)rp->paths_per_batch : (1u << 24);  // 16 Mi slots x 328 B = 5.5 GB of 180 GB HBM
   cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((cap + 31u) & ~31u, 32u), std::max<uint64_t>((total + 31) & ~31ull, 32));
   const uint32_t rounds = (uint32_t)rc.max_depth + 1 + 32;
   r = ensure_workspace(s, cap, rounds);

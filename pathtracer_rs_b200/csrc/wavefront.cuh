@@ -15,7 +15,7 @@
 //     launch keeps the float summation order of integrator.rs:443-447 (deterministic images)
 //   * per-round counters (queue lengths, tickets) live in one zero-initialised block per batch
 //
-// Path state is SoA in HBM, 16-byte fields, so every access is one 128-bit load/store.
+// Path state: 64-byte slot records + queue-ordered payloads, see PathArrays below.
 #pragma once
 #include "dev_shading.cuh"
 #include "dev_sobol.cuh"
@@ -25,30 +25,86 @@ namespace ptrs {
 #define PT_N_CLASSES (PTRS_MAT_COUNT + 1)  // material types + "miss"
 #define PT_CLASS_MISS PTRS_MAT_COUNT
 
+// ---- path state ---------------------------------------------------------------------------------------
+// Per path SLOT (indexed by p, gathered): one 64-byte, 64-byte-aligned record read / written with 256-bit
+// accesses, so a gather touches whole 32-byte sectors only.
+//   [0,32)   next ray + the words every bounce rewrites   (extend reads just this half)
+//   [32,64)  throughput + per-path constants
+// Per QUEUE ENTRY (indexed by queue position, coalesced): the producer's payload for the consumer —
+//   class queues   q_class[i] = slot, q_hit[i] = (primitive, b0, b1, b2)        extend -> shade
+//   connect queue  q_nee[i]   = slot, nee[i]   = 96-byte direct-lighting record  shade  -> connect
+// Radiance L is a separate float4 per slot: only connect (every bounce), shade (emitters) and
+// shade_miss touch it.
+struct __align__(32) PathRay {
+  float ox, oy, oz;
+  uint32_t packed;  // bits 0..15 Sobol dimension, PT_F_* (bits 16, 17), bits 24..31 bounces (signed 8 bit)
+  float dx, dy, dz;
+  float eta_scale;
+};
+struct __align__(32) PathAux {
+  float br, bg, bb;  // beta
+  uint32_t pixel;    // x | y << 16, two int16 (sample-bounds coordinates)
+  uint64_t sobol_index;
+  float fx, fy;  // p_film
+};
+struct __align__(64) PathSlot {
+  PathRay r;
+  PathAux a;
+};
+struct __align__(32) NeeRec {  // pending direct-lighting record of the current bounce (estimate_direct, integrator.rs:23-139)
+  float4 n0;  // shadow origin xyz,            A.r   (A = f * Li * w / light_pdf)
+  float4 n1;  // shadow segment xyz,           A.g
+  float4 n2;  // MIS ray origin xyz,           A.b
+  float4 n3;  // MIS ray dir xyz,              bits: light id | PT_NEE_*
+  float4 n4;  // f (already * |wi.ns|) rgb,     MIS weight
+  float4 n5;  // beta before the bounce rgb,   scattering pdf
+};
 struct PathArrays {
-  float4* ray_o;  // xyz
-  float4* ray_d;  // xyz
-  int* hit_prim;
-  float4* hit_tb;  // t, b0, b1, b2
-  float4* beta;    // rgb, eta_scale
-  float4* L;       // rgb
-  uint64_t* sobol_index;
-  int2* pixel;
-  int* bounces;
-  uint32_t* flags;  // bits 0..15 sobol dimension, PT_F_*
-  float2* p_film;
-  // pending direct-lighting record of the current bounce (estimate_direct, integrator.rs:23-139)
-  float4* nee0;  // shadow origin xyz,            A.r   (A = f * Li * w / light_pdf)
-  float4* nee1;  // shadow segment xyz,           A.g
-  float4* nee2;  // MIS ray origin xyz,           A.b
-  float4* nee3;  // MIS ray dir xyz,              bits: light id | PT_NEE_*
-  float4* nee4;  // f (already * |wi.ns|) rgb,     MIS weight
-  float4* nee5;  // beta before the bounce rgb,   scattering pdf
+  PathSlot* slot;
+  float4* L;      // rgb
+  float4* q_hit;  // PT_N_CLASSES x cap, aligned with the class queues
+  NeeRec* nee;    // cap, aligned with the connect queue
 };
 #define PT_F_SPECULAR (1u << 16)
 #define PT_F_HAS_DIFF (1u << 17)
 #define PT_NEE_SHADOW (1u << 30)
 #define PT_NEE_MIS (1u << 31)
+PT_DEV uint32_t pack_state(uint32_t dim_and_flags, int bounces) { return (dim_and_flags & 0x00ffffffu) | ((uint32_t)(bounces & 0xff) << 24); }
+PT_DEV int packed_bounces(uint32_t packed) { return (int)(int8_t)(packed >> 24); }
+PT_DEV uint32_t pack_pixel(int x, int y) { return ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16); }
+PT_DEV int2 unpack_pixel(uint32_t v) { return make_int2((int)(int16_t)(v & 0xffffu), (int)(int16_t)(v >> 16)); }
+
+// 256-bit accesses (LDG.E.256 / STG.E.256, sm_100a)
+template <class T>
+PT_DEV T ld256(const T* p) {
+  static_assert(sizeof(T) == 32, "32-byte record");
+  union {
+    T v;
+    uint32_t w[8];
+  } u;
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(u.w[0]), "=r"(u.w[1]), "=r"(u.w[2]), "=r"(u.w[3]), "=r"(u.w[4]), "=r"(u.w[5]), "=r"(u.w[6]), "=r"(u.w[7])
+               : "l"(p)
+               : "memory");
+  return u.v;
+}
+template <class T>
+PT_DEV void st256(T* p, const T& v) {
+  static_assert(sizeof(T) == 32, "32-byte record");
+  union {
+    T v;
+    uint32_t w[8];
+  } u;
+  u.v = v;
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(u.w[0]), "r"(u.w[1]), "r"(u.w[2]), "r"(u.w[3]), "r"(u.w[4]), "r"(u.w[5]),
+               "r"(u.w[6]), "r"(u.w[7])
+               : "memory");
+}
+struct __align__(32) F8 {
+  float4 a, b;
+};
+PT_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+PT_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // per-round device counters; one RoundCounters per extend/shade/connect round of a batch
 struct RoundCounters {

@@ -19,11 +19,13 @@ def main():
     ap.add_argument("--tris", type=int, default=1000000)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--out", default="")
+    ap.add_argument("--batch", type=int, default=0, help="paths per wavefront batch (0 = library default)")
     a = ap.parse_args()
     gpu.set_device(0)
     flat, cam = host.make_scene(a.scene, seed=1, n_tris=a.tris, res=tuple(a.res))
     scene = gpu.RenderScene(flat)
     integ = gpu.PathIntegrator(gpu.SamplerBuilder(a.spp), max_depth=a.depth)
+    integ.params.paths_per_batch = a.batch
     film = gpu.Film(cam.width, cam.height)
     for _ in range(a.reps):
         film.clear()

@@ -22,6 +22,12 @@ struct DevEnv {
   const float* marg_cdf;
   float marg_func_int;
   float pad2;
+  // guide tables (built on the device at scene creation): guide[k] = number of cdf entries <= k / K, K a power
+  // of two >= n.  They bracket find_interval's partition point for any u in [k/K, (k+1)/K), so the binary
+  // search of math.rs:186-201 runs over (on average) one element instead of n; same result.
+  const uint32_t* cond_guide;  // nv rows x (ku + 1)
+  const uint32_t* marg_guide;  // kv + 1
+  uint32_t ku, kv;
 };
 
 struct DevScene {

@@ -274,8 +274,27 @@ PT_DEV size_t find_interval_cdf(const float* __restrict__ cdf, size_t size, floa
   size_t r = first - 1, hi = size - 2;
   return r > hi ? hi : r;
 }
-PT_DEV float dist1d_sample(const float* func, const float* cdf, float func_int, int n, float u, float* pdf, size_t* off) {  // sampling.rs:164-182
-  size_t offset = find_interval_cdf(cdf, (size_t)n + 1, u);
+// find_interval restricted to the guide bracket [lo, hi]: the predicate cdf[i] <= u is monotone in i, so the
+// partition point found inside the bracket is the one the full search finds
+PT_DEV size_t find_interval_guided(const float* __restrict__ cdf, size_t size, float u, const uint32_t* __restrict__ guide, uint32_t K) {
+  uint32_t k = (uint32_t)(u * (float)K);
+  if (k > K - 1u) k = K - 1u;
+  size_t first = __ldg(guide + k), len = __ldg(guide + k + 1) - first;
+  while (len > 0) {
+    size_t half = len >> 1, middle = first + half;
+    if (__ldg(cdf + middle) <= u) {
+      first = middle + 1;
+      len -= half + 1;
+    } else {
+      len = half;
+    }
+  }
+  size_t r = first - 1, hi = size - 2;
+  return r > hi ? hi : r;
+}
+PT_DEV float dist1d_sample(const float* func, const float* cdf, float func_int, int n, float u, float* pdf, size_t* off, const uint32_t* guide,
+                           uint32_t K) {  // sampling.rs:164-182
+  size_t offset = guide ? find_interval_guided(cdf, (size_t)n + 1, u, guide, K) : find_interval_cdf(cdf, (size_t)n + 1, u);
   *off = offset;
   float c0 = __ldg(cdf + offset), c1 = __ldg(cdf + offset + 1);
   float du = u - c0;
@@ -286,8 +305,9 @@ PT_DEV float dist1d_sample(const float* func, const float* cdf, float func_int, 
 PT_DEVN V2 dist2d_sample(const DevEnv& e, V2 u, float* pdf) {  // sampling.rs:211-221
   float p0, p1;
   size_t v, dummy;
-  float d1 = dist1d_sample(e.marg_func, e.marg_cdf, e.marg_func_int, e.nv, u.y, &p1, &v);
-  float d0 = dist1d_sample(e.cond_func + v * e.nu, e.cond_cdf + v * (e.nu + 1), __ldg(e.cond_func_int + v), e.nu, u.x, &p0, &dummy);
+  float d1 = dist1d_sample(e.marg_func, e.marg_cdf, e.marg_func_int, e.nv, u.y, &p1, &v, e.marg_guide, e.kv);
+  float d0 = dist1d_sample(e.cond_func + v * e.nu, e.cond_cdf + v * (e.nu + 1), __ldg(e.cond_func_int + v), e.nu, u.x, &p0, &dummy,
+                           e.cond_guide ? e.cond_guide + v * (e.ku + 1) : nullptr, e.ku);
   *pdf = p0 * p1;
   return V2{d0, d1};
 }

@@ -68,24 +68,33 @@ struct PathSampler {
   uint32_t win[PT_SOBOL_WINDOW];  // scramble ^ (xor of matrix columns), i.e. the u32 before the 2^-32 scale
 };
 
-// mt = SOBOL_MATRICES_32 transposed to [52 bits][1024 dimensions]
+// mt = SOBOL_MATRICES_32 transposed to [52 bits][1024 dimensions].
+// The bit loop is WARP-UNIFORM: it runs over the union of the set bits of the converged lanes' indices and
+// each lane masks the column in or out.  Lanes of a shade launch sit at (nearly) the same dimension, so every
+// load is a broadcast of one 36-byte row segment — one L1 wavefront instead of one per distinct bit.
 PT_DEV void sobol_window_fill(const uint32_t* __restrict__ mt, PathSampler& s, uint32_t base) {
   if (base > 1024u - PT_SOBOL_WINDOW) base = 1024u - PT_SOBOL_WINDOW;
   s.win_base = base;
 #pragma unroll
   for (int j = 0; j < PT_SOBOL_WINDOW; ++j) s.win[j] = s.scramble;
-  uint32_t lo = (uint32_t)s.index, hi = (uint32_t)(s.index >> 32);
-  while (lo) {
-    const uint32_t* row = mt + (uint32_t)(__ffs(lo) - 1) * 1024u + base;
+  const uint32_t lo = (uint32_t)s.index, hi = (uint32_t)(s.index >> 32);
+  const uint32_t grp = __activemask();
+  uint32_t all_lo = __reduce_or_sync(grp, lo), all_hi = __reduce_or_sync(grp, hi);
+  while (all_lo) {
+    const uint32_t b = (uint32_t)(__ffs(all_lo) - 1);
+    const uint32_t* row = mt + b * 1024u + base;
+    const uint32_t m = 0u - ((lo >> b) & 1u);
 #pragma unroll
-    for (int j = 0; j < PT_SOBOL_WINDOW; ++j) s.win[j] ^= __ldg(row + j);
-    lo &= lo - 1;
+    for (int j = 0; j < PT_SOBOL_WINDOW; ++j) s.win[j] ^= __ldg(row + j) & m;
+    all_lo &= all_lo - 1;
   }
-  while (hi) {
-    const uint32_t* row = mt + (uint32_t)(32 + __ffs(hi) - 1) * 1024u + base;
+  while (all_hi) {
+    const uint32_t b = (uint32_t)(__ffs(all_hi) - 1);
+    const uint32_t* row = mt + (32u + b) * 1024u + base;
+    const uint32_t m = 0u - ((hi >> b) & 1u);
 #pragma unroll
-    for (int j = 0; j < PT_SOBOL_WINDOW; ++j) s.win[j] ^= __ldg(row + j);
-    hi &= hi - 1;
+    for (int j = 0; j < PT_SOBOL_WINDOW; ++j) s.win[j] ^= __ldg(row + j) & m;
+    all_hi &= all_hi - 1;
   }
 }
 

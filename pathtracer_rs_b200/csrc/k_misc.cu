@@ -1,4 +1,6 @@
 // generate / shade_miss / accumulate / resolve / parity-probe kernels
+#include <algorithm>
+
 #include "launch.hpp"
 #include "wavefront.cuh"
 
@@ -130,6 +132,33 @@ __global__ void __launch_bounds__(256) accumulate_kernel(const __grid_constant__
       }
     }
   }
+}
+
+// ---- Distribution1D guide tables ----------------------------------------------------------------------
+// guide[row][k] = #{ i < size : cdf[row][i] <= k / K }, k = 0..K (see DevEnv)
+__global__ void build_guide_kernel(const float* __restrict__ cdf, uint32_t size, uint32_t rows, uint32_t K, uint32_t* __restrict__ guide) {
+  const uint64_t total = (uint64_t)rows * (K + 1);
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t row = (uint32_t)(t / (K + 1)), k = (uint32_t)(t % (K + 1));
+    const float* c = cdf + (size_t)row * size;
+    const float u = (float)k / (float)K;
+    uint32_t first = 0, len = size;
+    while (len > 0) {
+      const uint32_t half = len >> 1, middle = first + half;
+      if (c[middle] <= u) {
+        first = middle + 1;
+        len -= half + 1;
+      } else {
+        len = half;
+      }
+    }
+    guide[t] = first;
+  }
+}
+void launch_build_guide(cudaStream_t st, const float* cdf, uint32_t size, uint32_t rows, uint32_t K, uint32_t* guide) {
+  const uint64_t total = (uint64_t)rows * (K + 1);
+  const int grid = (int)std::min<uint64_t>((total + 255) / 256, 148 * 16);
+  build_guide_kernel<<<grid, 256, 0, st>>>(cdf, size, rows, K, guide);
 }
 
 // ---- parity probes -----------------------------------------------------------------------------------

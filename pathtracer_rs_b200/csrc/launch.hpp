@@ -18,6 +18,7 @@ void launch_generate(cudaStream_t st, int sm, const RenderConst& rc, const uint3
                      uint32_t n_work, const int* list_xy, const int* list_s, int* q_ext, RoundCounters* ctr);
 void launch_shade_miss(cudaStream_t st, int sm, const DevScene& sc, const PathArrays& P, const int* q, RoundCounters* ctr);
 void launch_accumulate(cudaStream_t st, int sm, const RenderConst& rc, const PathArrays& P, uint32_t n, float4* film);
+void launch_build_guide(cudaStream_t st, const float* cdf, uint32_t size, uint32_t rows, uint32_t K, uint32_t* guide);
 void launch_resolve(cudaStream_t st, const float4* film, uint32_t n, float* rgb, uint8_t* rgba8);
 void launch_sobol_probe(cudaStream_t st, const RenderConst& rc, const uint32_t* sobol, const int* xy, const int* s, uint32_t n,
                         const int* dims, uint32_t n_dims, float* out, uint64_t* out_index);

@@ -132,6 +132,7 @@ struct PtrsScene {
   DevBuf<int> infinite_lights;
   DevBuf<DevEnv> envs;
   std::vector<DevBuf<float>> env_arrays;
+  std::vector<DevBuf<uint32_t>> env_guides;
   DevBuf<uint32_t> sobol, sobol_t;
   DevBuf<uint32_t> ticket;
   DevBuf<GlobalCounters> gcount;
@@ -491,6 +492,7 @@ int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) {
   {
     std::vector<DevEnv> envs(d->n_envs);
     s->env_arrays.resize((size_t)d->n_envs * 5);
+    s->env_guides.resize((size_t)d->n_envs * 2);
     for (uint32_t i = 0; i < d->n_envs; ++i) {
       const PtrsEnvLight& e = d->envs[i];
       if (e.nu <= 0 || e.nv <= 0 || !e.cond_func || !e.cond_cdf || !e.cond_func_int || !e.marg_func || !e.marg_cdf || e.mip < 0 ||
@@ -514,9 +516,25 @@ int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) {
       o.cond_func_int = a[2].p;
       o.marg_func = a[3].p;
       o.marg_cdf = a[4].p;
+      auto pow2_ge = [](uint32_t n) {
+        uint32_t k = 1;
+        while (k < n) k <<= 1;
+        return k;
+      };
+      o.ku = pow2_ge((uint32_t)e.nu);
+      o.kv = pow2_ge((uint32_t)e.nv);
+      DevBuf<uint32_t>* g = &s->env_guides[(size_t)i * 2];
+      CUDA_TRY(g[0].alloc((size_t)e.nv * (o.ku + 1)));
+      CUDA_TRY(g[1].alloc((size_t)o.kv + 1));
+      launch_build_guide(0, a[1].p, (uint32_t)e.nu + 1, (uint32_t)e.nv, o.ku, g[0].p);
+      launch_build_guide(0, a[4].p, (uint32_t)e.nv + 1, 1u, o.kv, g[1].p);
+      o.cond_guide = g[0].p;
+      o.marg_guide = g[1].p;
+      s->scene_bytes += ((size_t)e.nv * (o.ku + 1) + o.kv + 1) * 4;
       s->scene_bytes += ((size_t)e.nu * e.nv * 2 + e.nv * 4 + 1) * 4;
     }
     CUDA_TRY(s->envs.upload(envs.data(), envs.size()));
+    if (d->n_envs > 0) CUDA_TRY(cudaDeviceSynchronize());  // guide tables built
   }
   CUDA_TRY(s->sobol.upload(sh.matrices, (size_t)sh.n_dims * sh.n_cols));
   {

@@ -251,17 +251,22 @@ def run_gpu(args):
         t0 = time.perf_counter()
         sc2 = gpu.RenderScene(flat)  # ptrs_scene_create: H2D of the whole flattened scene
         f2 = gpu.Film(W, H)
+        t1 = time.perf_counter()
         integ.render(cam, sc2, f2, sample_stride=sample_shard(rank, n_gpus))
+        t2 = time.perf_counter()
         if world > 1:
             reduce_film(torch.as_tensor(_CudaArray(f2.device_ptr, (H, W, 4)), device="cuda"), dst=0)
             torch.cuda.synchronize()
         if rank == 0:
             gpu._check(gpu.lib().ptrs_film_download(f2._h, host_film.ctypes.data_as(C.POINTER(C.c_float))))
+        t3 = time.perf_counter()
         sc2.close()
         del f2
         barrier()
         if it > 0:
             e2e_ms.append((time.perf_counter() - t0) * 1e3)
+            e2e_parts = {"scene_create_ms": (t1 - t0) * 1e3, "render_ms": (t2 - t1) * 1e3, "film_reduce_download_ms": (t3 - t2) * 1e3,
+                         "destroy_ms": (time.perf_counter() - t3) * 1e3}
     e2e_local = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_local, op=dist.ReduceOp.MAX)
@@ -321,7 +326,8 @@ def run_gpu(args):
                        "camera_paths_per_step": paths_step, "rays_per_step": rays_step, "sharding": f"sample index mod {n_gpus}, film reduced with NCCL",
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(e2e_local.item()), "includes": "ptrs_scene_create from host arrays + render + ptrs_film_download"},
+                    "ms_per_step": float(e2e_local.item()), "includes": "ptrs_scene_create from host arrays + render + ptrs_film_download + ptrs_scene_destroy",
+                    "parts_last_step": e2e_parts},
             "gpu_launches": int(stats["launches"]) * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "stage_ms": {k: stats[k] for k in ("ms_generate", "ms_extend", "ms_shade", "ms_shadow", "ms_accumulate", "ms_total")},
             "rays": {k: stats[k] for k in ("extension_rays", "shadow_rays", "mis_rays")}, "bvh_microbench": micro}

@@ -303,6 +303,9 @@ int32_t ptrs_scene_create(const PtrsSceneDesc* desc, PtrsScene** out);
 int32_t ptrs_scene_destroy(PtrsScene* scene);
 int32_t ptrs_scene_world_bound(const PtrsScene* scene, float out_min_max[6]); /* mod.rs:100-102 */
 uint64_t ptrs_scene_device_bytes(const PtrsScene* scene);
+/* Device memory of destroyed scenes / films / path workspaces stays reserved in the device's default memory pool
+ * for re-use by the next ptrs_scene_create / ptrs_render; this returns it to the driver. */
+int32_t ptrs_trim_memory(void);
 
 /* RenderScene::intersect / intersect_p over a batch (mod.rs:92-98; accelerator.rs:359-475).
  * Host-buffer forms copy in and out; *_device forms take device pointers and only enqueue. */

@@ -123,14 +123,8 @@ PT_DEV bool tri_partials(V3 p0, V3 p1, V3 p2, const V2 uv[3], V3* dpdu, V3* dpdv
 // partials (shape.rs:205-212) — only reachable for zero-area triangles — and the alpha mask
 // (shape.rs:228-244).  Slow path, taken only for primitives whose mesh has an alpha texture or
 // for closest-hit candidates (any-hit only evaluates partials under an alpha mask, shape.rs:471).
-PT_DEVN bool tri_post_reject(const DevScene& sc, int prim, V3 p0, V3 p1, V3 p2, uint32_t meta2, float b0, float b1, float b2, bool closest) {
+PT_DEVN bool tri_post_reject_slow(const DevScene& sc, int prim, V3 p0, V3 p1, V3 p2, uint32_t meta2, float b0, float b1, float b2) {
   const bool has_alpha = (meta2 & PT_TRI_ALPHA_BIT) != 0;
-  if (!closest && !has_alpha) return false;
-  // zero-area test is exact and cheap; the full partials are only needed with an alpha mask
-  if (!has_alpha) {
-    V3 ng = cross(p2 - p0, p1 - p0);
-    if (norm_squared(ng) != 0.0f) return false;
-  }
   uint4 idx = __ldg(sc.tri_index + prim);
   V2 uv[3];
   tri_uvs(sc, idx, meta2 & 0xffu, uv);
@@ -141,6 +135,16 @@ PT_DEVN bool tri_post_reject(const DevScene& sc, int prim, V3 p0, V3 p1, V3 p2, 
     if (tex_f32(sc, (int)(meta2 >> 9), tc) == 0.0f) return true;
   }
   return false;
+}
+// inline fast path: no alpha mask and a triangle of non-zero area can never be rejected here
+PT_DEV bool tri_post_reject(const DevScene& sc, int prim, V3 p0, V3 p1, V3 p2, uint32_t meta2, float b0, float b1, float b2, bool closest) {
+  const bool has_alpha = (meta2 & PT_TRI_ALPHA_BIT) != 0;
+  if (!closest && !has_alpha) return false;
+  if (!has_alpha) {
+    V3 ng = cross(p2 - p0, p1 - p0);
+    if (norm_squared(ng) != 0.0f) return false;
+  }
+  return tri_post_reject_slow(sc, prim, p0, p1, p2, meta2, b0, b1, b2);
 }
 
 struct NodeLoad {
@@ -232,7 +236,7 @@ struct LaneRay {
 #define PT_SEARCH_MIN 6
 #endif
 #ifndef PT_BOX_MIN
-#define PT_BOX_MIN 12
+#define PT_BOX_MIN 16
 #endif
 
 // empty accelerator: every ray misses (accelerator.rs:360-362)
@@ -255,7 +259,7 @@ PT_DEV void trace_empty(uint32_t n_items, uint32_t* ticket, Work& work) {
   }
 }
 
-// ---- fast variant (no visit counters) ------------------------------------------------------------------
+// ---- fast variant (no visit counters): box loop, then triangle loop, then service ------------------------------------------------------------------
 template <class Work>
 PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, Work& work) {
   if (sc.n_nodes == 0) {

@@ -104,6 +104,48 @@ __global__ void __launch_bounds__(128) shade_miss_kernel(DevScene sc, PathArrays
   }
 }
 
+// ---- connect_resolve ---------------------------------------------------------------------------------
+// Second half of estimate_direct at full warp width, in connect-queue order: Ld_light (unoccluded shadow
+// segment, integrator.rs:66-80) + Ld_bsdf (emitted radiance found by the MIS ray, integrator.rs:113-135), then
+// L += beta * n_lights * Ld (integrator.rs:443-447, uniform_sample_one_light :216).  One thread per record =
+// one writer per path, so the per-path summation order is the reference's.
+__global__ void __launch_bounds__(256) connect_resolve_kernel(DevScene sc, PathArrays P, const int* __restrict__ q_nee, RoundCounters* ctr) {
+  const uint32_t n = ctr->n_nee;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const NeeRec* rec = P.nee + i;
+    const float4 n3 = rec->n3;
+    const uint32_t nf = __float_as_uint(n3.w);
+    const NeeRes res = ld256(P.nee_res + i);
+    Spec ld = sp(0.0f);
+    if ((nf & PT_NEE_SHADOW) && !res.occluded) ld = ld + sp(rec->n0.w, rec->n1.w, rec->n2.w);
+    const float4 n5 = rec->n5;
+    if (nf & PT_NEE_MIS) {
+      const int light_idx = (int)(nf & 0x3fffffffu);
+      const V3 md = mk3(n3);
+      Spec li = sp(0.0f);
+      if (res.prim >= 0) {
+        const int hl = __float_as_int(__ldg(&sc.tri_verts[3 * (size_t)res.prim + 1].w));
+        if (hl == light_idx) {
+          SurfInter si;
+          reconstruct_hit(sc, res.prim, res.b0, res.b1, res.b2, md, &si);
+          li = area_le(sc, hl, si, -md);
+        }
+      } else if (sc.lights[light_idx].type == PTRS_LIGHT_INFINITE) {
+        li = env_le(sc, sc.lights[light_idx], md);
+      }
+      if (!is_black(li)) {
+        const float4 n4 = rec->n4;
+        ld = ld + sp(n4.x, n4.y, n4.z) * li * sp(1.0f) * n4.w / n5.w;
+      }
+    }
+    const int p = q_nee[i];
+    const float4 l4 = P.L[p];
+    const Spec L = sp(l4.x, l4.y, l4.z) + sp(n5.x, n5.y, n5.z) * ((float)sc.n_lights * ld);
+    P.L[p] = make_float4(L.r, L.g, L.b, 0.f);
+  }
+}
+
 // ---- accumulate ------------------------------------------------------------------------------------
 // FilmTile::add_sample + merge_film_tile (film.rs:60-106, 213-228) straight into the film with
 // 128-bit float atomics (red.global.add.v4.f32, sm_90+).
@@ -237,6 +279,11 @@ void launch_shade_miss(cudaStream_t st, int sm, const DevScene& sc, const PathAr
   static int grid = 0;
   if (!grid) grid = persistent_grid(shade_miss_kernel, 128, sm);
   shade_miss_kernel<<<grid, 128, 0, st>>>(sc, P, q, ctr);
+}
+void launch_connect_resolve(cudaStream_t st, int sm, const DevScene& sc, const PathArrays& P, const int* q_nee, RoundCounters* ctr) {
+  static int grid = 0;
+  if (!grid) grid = persistent_grid(connect_resolve_kernel, 256, sm);
+  connect_resolve_kernel<<<grid, 256, 0, st>>>(sc, P, q_nee, ctr);
 }
 void launch_accumulate(cudaStream_t st, int sm, const RenderConst& rc, const PathArrays& P, uint32_t n, float4* film) {
   static int grid = 0;

@@ -63,94 +63,48 @@ __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) extend_kernel(DevSce
 }
 
 // ---- connect ---------------------------------------------------------------------------------------
-// Second half of estimate_direct for every path with a pending record: the shadow test
-// (integrator.rs:66-78, light.rs:39-41) and the BSDF-sampled MIS ray (integrator.rs:113-135), traced
-// back to back by ONE lane, which then adds beta * n_lights * (Ld_light + Ld_bsdf) to the path's
-// radiance — a single writer per path keeps the summation order of integrator.rs:443-447.
+// Rays of estimate_direct for every pending record: work item 2i is the shadow segment of record i
+// (integrator.rs:66-78, light.rs:39-41, any-hit), item 2i+1 its BSDF-sampled MIS ray (integrator.rs:113-135,
+// closest hit).  The kernel only traces: what was found goes to nee_res[i], and connect_resolve_kernel
+// (k_misc.cu) evaluates emitted radiance and adds the bounce's direct lighting at full warp width.
 struct ConnectWork {
-  const DevScene& sc;
   const PathArrays& P;
-  const int* __restrict__ q_nee;
-  uint32_t idx;  // queue position = index of the NeeRec
-  uint32_t nf;
-  int stage;  // 0 = shadow ray in flight, 1 = MIS ray in flight
-  Spec ld;
   uint32_t n_shadow, n_mis;
-
-  __device__ void mis_ray(LaneRay* r) {
-    const float4 n2 = P.nee[idx].n2, n3 = P.nee[idx].n3;
-    r->o = mk3(n2);
-    r->d = mk3(n3);
-    r->t_max = CUDART_INF_F;
-    r->any_hit = false;
-    stage = 1;
-    ++n_mis;
-  }
-  __device__ void finish() {
-    const int p = q_nee[idx];
-    const float4 b5 = P.nee[idx].n5;
-    const float4 l4 = P.L[p];
-    const Spec L = sp(l4.x, l4.y, l4.z) + sp(b5.x, b5.y, b5.z) * ((float)sc.n_lights * ld);
-    P.L[p] = make_float4(L.r, L.g, L.b, 0.f);
-  }
   __device__ bool begin(uint32_t i, LaneRay* r) {
-    idx = i;
-    nf = __float_as_uint(P.nee[i].n3.w);
-    ld = sp(0.0f);
-    if (nf & PT_NEE_SHADOW) {
-      const F8 n01 = ld256(reinterpret_cast<const F8*>(&P.nee[i].n0));
+    const uint32_t rec = i >> 1;
+    const uint32_t nf = __float_as_uint(P.nee[rec].n3.w);
+    if (i & 1u) {
+      if (!(nf & PT_NEE_MIS)) return false;
+      const F8 n23 = ld256(reinterpret_cast<const F8*>(&P.nee[rec].n2));
+      r->o = mk3(n23.a);
+      r->d = mk3(n23.b);
+      r->t_max = CUDART_INF_F;
+      r->any_hit = false;
+      ++n_mis;
+    } else {
+      if (!(nf & PT_NEE_SHADOW)) return false;
+      const F8 n01 = ld256(reinterpret_cast<const F8*>(&P.nee[rec].n0));
       r->o = mk3(n01.a);
       r->d = mk3(n01.b);
       r->t_max = 1.0f - PT_SHADOW_EPSILON;
       r->any_hit = true;
-      stage = 0;
       ++n_shadow;
-      return true;
     }
-    if (nf & PT_NEE_MIS) {
-      mis_ray(r);
-      return true;
-    }
-    return false;
+    return true;
   }
-  __device__ bool end(uint32_t, const DevHit& h, bool found, LaneRay* r) {
-    if (stage == 0) {
-      if (!found) ld = ld + sp(P.nee[idx].n0.w, P.nee[idx].n1.w, P.nee[idx].n2.w);
-      if (nf & PT_NEE_MIS) {
-        mis_ray(r);
-        return true;
-      }
-      finish();
-      return false;
-    }
-    const int light_idx = (int)(nf & 0x3fffffffu);
-    const V3 md = mk3(P.nee[idx].n3);
-    Spec li = sp(0.0f);
-    if (found) {
-      const int hl = __float_as_int(__ldg(&sc.tri_verts[3 * (size_t)h.prim + 1].w));
-      if (hl == light_idx) {
-        SurfInter si;
-        reconstruct_hit(sc, h.prim, h.b0, h.b1, h.b2, md, &si);
-        li = area_le(sc, hl, si, -md);
-      }
-    } else if (sc.lights[light_idx].type == PTRS_LIGHT_INFINITE) {
-      li = env_le(sc, sc.lights[light_idx], md);
-    }
-    if (!is_black(li)) {
-      const float4 n4 = P.nee[idx].n4;
-      ld = ld + sp(n4.x, n4.y, n4.z) * li * sp(1.0f) * n4.w / P.nee[idx].n5.w;
-    }
-    finish();
+  __device__ bool end(uint32_t i, const DevHit& h, bool found, LaneRay*) {
+    NeeRes* res = P.nee_res + (i >> 1);
+    if (i & 1u) *reinterpret_cast<float4*>(res) = make_float4(__int_as_float(found ? h.prim : -1), h.b0, h.b1, h.b2);
+    else res->occluded = found ? 1u : 0u;
     return false;
   }
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) connect_kernel(DevScene sc, PathArrays P, const int* __restrict__ q_nee, RoundCounters* ctr,
-                                                       GlobalCounters* g) {
+__global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) connect_kernel(DevScene sc, PathArrays P, RoundCounters* ctr, GlobalCounters* g) {
   uint32_t c_nodes = 0, c_tris = 0;
-  ConnectWork w{sc, P, q_nee, 0u, 0u, 0, sp(0.f), 0u, 0u};
-  trace_stream<COUNT>(sc, ctr->n_nee, &ctr->t_nee, w, &c_nodes, &c_tris);
+  ConnectWork w{P, 0u, 0u};
+  trace_stream<COUNT>(sc, 2u * ctr->n_nee, &ctr->t_nee, w, &c_nodes, &c_tris);
   warp_sum_add(w.n_shadow, &g->shadow_rays);
   warp_sum_add(w.n_mis, &g->mis_rays);
   if (COUNT) {
@@ -212,15 +166,14 @@ void launch_extend(cudaStream_t st, int sm, bool count, const DevScene& sc, cons
   if (count) extend_kernel<true><<<grid[1], 128, 0, st>>>(sc, P, q_ext, q_class, cap, ctr, g);
   else extend_kernel<false><<<grid[0], 128, 0, st>>>(sc, P, q_ext, q_class, cap, ctr, g);
 }
-void launch_connect(cudaStream_t st, int sm, bool count, const DevScene& sc, const PathArrays& P, const int* q_nee, RoundCounters* ctr,
-                    GlobalCounters* g) {
+void launch_connect(cudaStream_t st, int sm, bool count, const DevScene& sc, const PathArrays& P, RoundCounters* ctr, GlobalCounters* g) {
   static int grid[2] = {0, 0};
   if (!grid[0]) {
     grid[0] = persistent_grid(connect_kernel<false>, 128, sm);
     grid[1] = persistent_grid(connect_kernel<true>, 128, sm);
   }
-  if (count) connect_kernel<true><<<grid[1], 128, 0, st>>>(sc, P, q_nee, ctr, g);
-  else connect_kernel<false><<<grid[0], 128, 0, st>>>(sc, P, q_nee, ctr, g);
+  if (count) connect_kernel<true><<<grid[1], 128, 0, st>>>(sc, P, ctr, g);
+  else connect_kernel<false><<<grid[0], 128, 0, st>>>(sc, P, ctr, g);
 }
 void launch_intersect(cudaStream_t st, int sm, bool any_hit, bool count, const DevScene& sc, const PtrsRay* rays, uint32_t n, PtrsHit* hits,
                       uint8_t* occluded, uint32_t* ticket, GlobalCounters* g) {

@@ -17,6 +17,7 @@ struct RenderConst;
 void launch_generate(cudaStream_t st, int sm, const RenderConst& rc, const uint32_t* sobol, const PathArrays& P, uint64_t work_base,
                      uint32_t n_work, const int* list_xy, const int* list_s, int* q_ext, RoundCounters* ctr);
 void launch_shade_miss(cudaStream_t st, int sm, const DevScene& sc, const PathArrays& P, const int* q, RoundCounters* ctr);
+void launch_connect_resolve(cudaStream_t st, int sm, const DevScene& sc, const PathArrays& P, const int* q_nee, RoundCounters* ctr);
 void launch_accumulate(cudaStream_t st, int sm, const RenderConst& rc, const PathArrays& P, uint32_t n, float4* film);
 void launch_build_guide(cudaStream_t st, const float* cdf, uint32_t size, uint32_t rows, uint32_t K, uint32_t* guide);
 void launch_resolve(cudaStream_t st, const float4* film, uint32_t n, float* rgb, uint8_t* rgba8);
@@ -28,8 +29,7 @@ void launch_ray_probe(cudaStream_t st, const RenderConst& rc, const uint32_t* so
 // k_trace.cu
 void launch_extend(cudaStream_t st, int sm, bool count, const DevScene& sc, const PathArrays& P, const int* q_ext, int* q_class, uint32_t cap,
                    RoundCounters* ctr, GlobalCounters* g);
-void launch_connect(cudaStream_t st, int sm, bool count, const DevScene& sc, const PathArrays& P, const int* q_nee, RoundCounters* ctr,
-                    GlobalCounters* g);
+void launch_connect(cudaStream_t st, int sm, bool count, const DevScene& sc, const PathArrays& P, RoundCounters* ctr, GlobalCounters* g);
 void launch_intersect(cudaStream_t st, int sm, bool any_hit, bool count, const DevScene& sc, const PtrsRay* rays, uint32_t n, PtrsHit* hits,
                       uint8_t* occluded, uint32_t* ticket, GlobalCounters* g);
 

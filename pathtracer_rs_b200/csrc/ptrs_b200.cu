@@ -72,6 +72,23 @@ const SobolHost& sobol_host() {
   return h;
 }
 
+// Device buffers come from the device's default stream-ordered memory pool (cudaMallocAsync on the legacy
+// stream) with the release threshold raised, so that freeing and re-creating a scene or a multi-GB path
+// workspace re-uses the reservation instead of unmapping / mapping it (cudaFree of the 6 GB workspace alone
+// costs ~0.3 s).  ptrs_trim_memory() hands the cached memory back to the driver.
+inline void keep_pool_reserved() {
+  static std::once_flag once[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  std::call_once(once[dev], [dev] {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  });
+}
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
@@ -80,7 +97,8 @@ struct DevBuf {
     release();
     n = count;
     if (count == 0) return cudaSuccess;
-    return cudaMalloc(&p, count * sizeof(T));
+    keep_pool_reserved();
+    return cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), (cudaStream_t)0);
   }
   cudaError_t upload(const T* src, size_t count) {
     cudaError_t e = alloc(count);
@@ -88,7 +106,7 @@ struct DevBuf {
     return cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice);
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, (cudaStream_t)0);
     p = nullptr;
     n = 0;
   }
@@ -100,6 +118,7 @@ struct Workspace {
   DevBuf<PathSlot> slot;
   DevBuf<float4> L, q_hit;
   DevBuf<NeeRec> nee;
+  DevBuf<NeeRes> nee_res;
   DevBuf<int> q_ext[2], q_nee, q_class;
   DevBuf<RoundCounters> counters;
   DevBuf<GlobalCounters> gcount;
@@ -109,10 +128,11 @@ struct Workspace {
     a.L = L.p;
     a.q_hit = q_hit.p;
     a.nee = nee.p;
+    a.nee_res = nee_res.p;
     return a;
   }
   uint64_t bytes() const {
-    return (uint64_t)cap * (sizeof(PathSlot) + 16 + sizeof(NeeRec) + 4 * 3 + (4 + 16) * PT_N_CLASSES) + (uint64_t)rounds * sizeof(RoundCounters);
+    return (uint64_t)cap * (sizeof(PathSlot) + 16 + sizeof(NeeRec) + sizeof(NeeRes) + 4 * 3 + (4 + 16) * PT_N_CLASSES) + (uint64_t)rounds * sizeof(RoundCounters);
   }
 };
 
@@ -249,6 +269,7 @@ int32_t ensure_workspace(PtrsScene* s, uint32_t cap, uint32_t rounds) {
   WS_ALLOC(w.slot, cap);
   WS_ALLOC(w.L, cap);
   WS_ALLOC(w.nee, cap);
+  WS_ALLOC(w.nee_res, cap);
   WS_ALLOC(w.q_hit, (size_t)cap * PT_N_CLASSES);
   WS_ALLOC(w.q_ext[0], cap);
   WS_ALLOC(w.q_ext[1], cap);
@@ -257,6 +278,7 @@ int32_t ensure_workspace(PtrsScene* s, uint32_t cap, uint32_t rounds) {
   WS_ALLOC(w.counters, rounds + 1);
   WS_ALLOC(w.gcount, 1);
 #undef WS_ALLOC
+  if (cudaStreamSynchronize((cudaStream_t)0) != cudaSuccess) return fail(PTRS_ERR_CUDA, "workspace allocation failed");  // allocations are ordered on the legacy stream; the render may use another
   w.cap = cap;
   w.rounds = rounds;
   return PTRS_OK;
@@ -334,7 +356,9 @@ int32_t run_batch(PtrsScene* s, const RenderConst& rc, uint64_t work_base, uint3
       tm.end();
       tm.begin(ST_CONNECT);
       if (s->dev.n_lights > 0) {
-        launch_connect(st, sm, s->count_visits, s->dev, P, w.q_nee.p, c, w.gcount.p);
+        launch_connect(st, sm, s->count_visits, s->dev, P, c, w.gcount.p);
+        launch_connect_resolve(st, sm, s->dev, P, w.q_nee.p, c);
+        s->stats.launches += 1;
         s->stats.connect_launches += 1;
         s->stats.launches += 1;
       }
@@ -584,6 +608,16 @@ int32_t ptrs_scene_destroy(PtrsScene* scene) {
   cudaSetDevice(scene->device);
   cudaDeviceSynchronize();
   delete scene;
+  return PTRS_OK;
+}
+
+int32_t ptrs_trim_memory(void) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceSynchronize());
+  cudaMemPool_t pool;
+  CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+  CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
   return PTRS_OK;
 }
 

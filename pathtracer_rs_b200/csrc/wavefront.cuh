@@ -59,11 +59,18 @@ struct __align__(32) NeeRec {  // pending direct-lighting record of the current 
   float4 n4;  // f (already * |wi.ns|) rgb,     MIS weight
   float4 n5;  // beta before the bounce rgb,   scattering pdf
 };
+struct __align__(32) NeeRes {  // what connect_trace found for NeeRec i
+  int prim;  // MIS ray: closest primitive or -1
+  float b0, b1, b2;
+  uint32_t occluded;  // shadow segment blocked
+  uint32_t pad[3];
+};
 struct PathArrays {
   PathSlot* slot;
-  float4* L;      // rgb
-  float4* q_hit;  // PT_N_CLASSES x cap, aligned with the class queues
-  NeeRec* nee;    // cap, aligned with the connect queue
+  float4* L;        // rgb
+  float4* q_hit;    // PT_N_CLASSES x cap, aligned with the class queues
+  NeeRec* nee;      // cap, aligned with the connect queue
+  NeeRes* nee_res;  // cap, aligned with the connect queue
 };
 #define PT_F_SPECULAR (1u << 16)
 #define PT_F_HAS_DIFF (1u << 17)

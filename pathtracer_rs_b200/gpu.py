@@ -28,7 +28,7 @@ EXPORTS = [
     "ptrs_intersect_p_device", "ptrs_intersect_counted_device", "ptrs_film_create", "ptrs_film_wrap_device", "ptrs_film_destroy",
     "ptrs_film_clear", "ptrs_film_download", "ptrs_film_resolve", "ptrs_film_resolve_srgb8", "ptrs_film_device_ptr",
     "ptrs_film_sample_bounds", "ptrs_render_params_default", "ptrs_render", "ptrs_path_radiance", "ptrs_stats",
-    "ptrs_set_stats_mode", "ptrs_sobol_samples", "ptrs_generate_rays",
+    "ptrs_set_stats_mode", "ptrs_sobol_samples", "ptrs_generate_rays", "ptrs_trim_memory",
 ]
 
 
@@ -100,6 +100,11 @@ def device_count():
 
 def set_device(i):
     _check(lib().ptrs_set_device(i))
+
+
+def trim_memory():
+    """Return the device memory cached from destroyed scenes / workspaces to the driver."""
+    _check(lib().ptrs_trim_memory())
 
 
 class Film:

@@ -115,8 +115,40 @@ struct Lobe {
   int disney_g;  // separable G (DisneyMicrofacetDistribution, disney.rs:160-162)
 };
 
+// A shade<MAT> translation unit (k_shade.cu, -DPT_SHADE_MAT=<type>) only ever sees the lobes that material
+// type creates (dev_shading.cuh compute_scattering_functions), so the lobe switches fold at compile time and
+// the lobe functions can be inlined: the BSDF then lives in registers instead of local memory.
+#ifdef PT_SHADE_MAT
+#define PT_LOBE_FN __device__ __forceinline__
+#if PT_SHADE_MAT == 0
+#define PT_LOBE_MASK (1u << LOBE_LAMBERT)
+#elif PT_SHADE_MAT == 1
+#define PT_LOBE_MASK (1u << LOBE_SPEC_REFL)
+#elif PT_SHADE_MAT == 2
+#define PT_LOBE_MASK (1u << LOBE_FRESNEL_SPEC)
+#elif PT_SHADE_MAT == 3
+#define PT_LOBE_MASK (1u << LOBE_MF_REFL)
+#elif PT_SHADE_MAT == 4
+#define PT_LOBE_MASK (1u << LOBE_FRESNEL_BLEND)
+#else
+#define PT_LOBE_MASK ((1u << LOBE_DISNEY_DIFFUSE) | (1u << LOBE_MF_REFL))
+#endif
+#else
+#define PT_LOBE_FN static __device__ __noinline__
+#define PT_LOBE_MASK 0xffu
+#endif
+__host__ __device__ constexpr int pt_ctz(uint32_t m) { return (m & 1u) ? 0 : 1 + pt_ctz(m >> 1); }
+__host__ __device__ constexpr int pt_popc(uint32_t m) { return m ? (int)(m & 1u) + pt_popc(m >> 1) : 0; }
+__host__ __device__ constexpr int pt_top(uint32_t m) { return m > 1u ? 1 + pt_top(m >> 1) : 0; }
+PT_DEV int lobe_kind(const Lobe& l) {
+  constexpr uint32_t m = PT_LOBE_MASK;
+  if (pt_popc(m) == 1) return pt_ctz(m);
+  if (pt_popc(m) == 2) return l.kind == pt_ctz(m) ? pt_ctz(m) : pt_top(m);
+  return l.kind;
+}
+
 PT_DEV uint32_t lobe_type(const Lobe& l) {
-  switch (l.kind) {
+  switch (lobe_kind(l)) {
     case LOBE_LAMBERT: case LOBE_DISNEY_DIFFUSE: return BSDF_REFLECTION | BSDF_DIFFUSE;
     case LOBE_SPEC_REFL: return BSDF_REFLECTION | BSDF_SPECULAR;
     case LOBE_SPEC_TRANS: return BSDF_TRANSMISSION | BSDF_SPECULAR;
@@ -214,8 +246,8 @@ PT_DEV float roughness_to_alpha(float roughness) {  // microfacet.rs:119-128
 }
 PT_DEV float pow5(float v) { return (v * v) * (v * v) * v; }
 
-PT_DEVN Spec lobe_f(const Lobe& l, V3 wo, V3 wi) {
-  switch (l.kind) {
+PT_LOBE_FN Spec lobe_f(const Lobe& l, V3 wo, V3 wi) {
+  switch (lobe_kind(l)) {
     case LOBE_LAMBERT: return l.r * PT_FRAC_1_PI;
     case LOBE_DISNEY_DIFFUSE: {
       float fo = schlick_weight(abs_cos_theta(wo)), fi = schlick_weight(abs_cos_theta(wi));
@@ -259,8 +291,8 @@ PT_DEVN Spec lobe_f(const Lobe& l, V3 wo, V3 wi) {
   }
 }
 
-PT_DEVN float lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
-  switch (l.kind) {
+PT_LOBE_FN float lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
+  switch (lobe_kind(l)) {
     case LOBE_LAMBERT: case LOBE_DISNEY_DIFFUSE: return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * PT_FRAC_1_PI : 0.0f;
     case LOBE_MF_REFL: {
       if (!same_hemisphere(wo, wi)) return 0.f;
@@ -287,8 +319,8 @@ PT_DEVN float lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
 }
 
 // BxDFInterface::sample_f; *sampled_type only changes for FresnelSpecular (fresnel.rs:254-288)
-PT_DEVN Spec lobe_sample_f(const Lobe& l, V3 wo, V3* wi, V2 u, float* pdf, uint32_t* sampled_type) {
-  switch (l.kind) {
+PT_LOBE_FN Spec lobe_sample_f(const Lobe& l, V3 wo, V3* wi, V2 u, float* pdf, uint32_t* sampled_type) {
+  switch (lobe_kind(l)) {
     case LOBE_LAMBERT: case LOBE_DISNEY_DIFFUSE: {
       *wi = cosine_sample_hemisphere(u);
       if (wo.z < 0.0f) wi->z *= -1.0f;

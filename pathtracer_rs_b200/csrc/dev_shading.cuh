@@ -24,6 +24,12 @@ PT_DEV void spawn_ray_to_it(const Inter& a, const Inter& b, V3* o, V3* d) {
   *d = target - origin;
 }
 
+#ifdef PT_SHADE_MAT
+#define PT_RECON_FN __device__ __forceinline__
+#else
+#define PT_RECON_FN static __device__ __noinline__
+#endif
+
 struct SurfInter {  // the fields of SurfaceMediumInteraction the path integrator reads
   Inter g;          // general {p, p_error, n}
   V3 wo;
@@ -37,7 +43,7 @@ struct SurfInter {  // the fields of SurfaceMediumInteraction the path integrato
 PT_DEV V3 load3(const float* base, uint32_t i) { return mk3(__ldg(base + 3 * (size_t)i), __ldg(base + 3 * (size_t)i + 1), __ldg(base + 3 * (size_t)i + 2)); }
 
 // Rebuilds what Triangle::intersect stored for the accepted hit (prim, b0, b1, b2).
-PT_DEVN void reconstruct_hit(const DevScene& sc, int prim, float b0, float b1, float b2, V3 ray_d, SurfInter* si) {
+PT_RECON_FN void reconstruct_hit(const DevScene& sc, int prim, float b0, float b1, float b2, V3 ray_d, SurfInter* si) {
   const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim), v1 = __ldg(sc.tri_verts + 3 * (size_t)prim + 1),
                v2 = __ldg(sc.tri_verts + 3 * (size_t)prim + 2);
   const V3 p0 = mk3(v0), p1 = mk3(v1), p2 = mk3(v2);

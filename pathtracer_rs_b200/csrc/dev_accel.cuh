@@ -10,32 +10,32 @@
 
 namespace ptrs {
 
-struct RayPre {  // per-ray constants of the triangle test (shape.rs:94-110)
-  int kx, ky, kz;
+struct RayPre {  // per-ray constants of the triangle test (shape.rs:94-110); kx = kz+1 mod 3, ky = kx+1 mod 3
+  int kz;
   float sx, sy, sz;
 };
-PT_DEV float pick(V3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+// (v[kx], v[ky], v[kz]) — a cyclic rotation selected by kz
+PT_DEV V3 permute(V3 v, int kz) {
+  const bool z0 = kz == 0, z1 = kz == 1;
+  return mk3(z0 ? v.y : (z1 ? v.z : v.x), z0 ? v.z : (z1 ? v.x : v.y), z0 ? v.x : (z1 ? v.y : v.z));
+}
 
 PT_DEV RayPre ray_precompute(V3 d) {
   RayPre p;
   p.kz = max_dimension(vabs(d));
-  p.kx = p.kz + 1;
-  if (p.kx == 3) p.kx = 0;
-  p.ky = p.kx + 1;
-  if (p.ky == 3) p.ky = 0;
-  float dx = pick(d, p.kx), dy = pick(d, p.ky), dz = pick(d, p.kz);
-  p.sx = -dx / dz;
-  p.sy = -dy / dz;
-  p.sz = 1.0f / dz;
+  const V3 dp = permute(d, p.kz);
+  p.sx = -dp.x / dp.z;
+  p.sy = -dp.y / dp.z;
+  p.sz = 1.0f / dp.z;
   return p;
 }
 
 // shape.rs:85-185.  Returns true and (t, b0, b1, b2) if the triangle is hit within (0, t_max].
 PT_DEV bool tri_core(V3 p0, V3 p1, V3 p2, V3 o, const RayPre& rp, float t_max, float* t_out, float* b0o, float* b1o, float* b2o) {
-  V3 q0 = p0 - o, q1 = p1 - o, q2 = p2 - o;
-  float p0x = pick(q0, rp.kx), p0y = pick(q0, rp.ky), p0z = pick(q0, rp.kz);
-  float p1x = pick(q1, rp.kx), p1y = pick(q1, rp.ky), p1z = pick(q1, rp.kz);
-  float p2x = pick(q2, rp.kx), p2y = pick(q2, rp.ky), p2z = pick(q2, rp.kz);
+  const V3 q0 = permute(p0 - o, rp.kz), q1 = permute(p1 - o, rp.kz), q2 = permute(p2 - o, rp.kz);
+  float p0x = q0.x, p0y = q0.y, p0z = q0.z;
+  float p1x = q1.x, p1y = q1.y, p1z = q1.z;
+  float p2x = q2.x, p2y = q2.y, p2z = q2.z;
   p0x += rp.sx * p0z;
   p0y += rp.sy * p0z;
   p1x += rp.sx * p1z;
@@ -259,7 +259,16 @@ PT_DEV void trace_empty(uint32_t n_items, uint32_t* ticket, Work& work) {
   }
 }
 
-// ---- fast variant (no visit counters): box loop, then triangle loop, then service ------------------------------------------------------------------
+// ---- fast variant (no visit counters): box loop, then triangle loop, then service -------------------------
+// Register diet (the kernels run at 64 registers / 32 warps per SM): the per-ray booleans and the triangle
+// test's axis live in ONE word, the hit distance is t_max itself, "found" is hit_prim >= 0, and the parked
+// leaf is (next primitive, triangles left).
+#define PT_RB_NX 1u
+#define PT_RB_NY 2u
+#define PT_RB_NZ 4u
+#define PT_RB_KZ_SHIFT 3
+#define PT_RB_ANY 32u
+#define PT_RB_LIVE 64u
 template <class Work>
 PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, Work& work) {
   if (sc.n_nodes == 0) {
@@ -267,45 +276,39 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
     return;
   }
   const uint32_t FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const uint32_t lane_lt = (1u << lane) - 1u;
   uint4 stack[PT_STACK_SIZE];
   int sp_ = 0;
   // node in hand (its box test passed under the t_max current at that time): offset, meta, entry distance
   uint32_t cur_off = 0, cur_meta = PT_NO_NODE;
   float cur_t = 0.f;
-  // parked leaf: first primitive, count (0 = none), next triangle
-  uint32_t pl_off = 0, pl_cnt = 0, pl_i = 0;
-  bool live = false, exhausted = n_items == 0;
-  bool any_hit = false, found = false;
+  uint32_t pl_off = 0, pl_cnt = 0;  // parked leaf: next primitive, triangles left (0 = none)
+  uint32_t rbits = 0;               // PT_RB_*
+  bool exhausted = n_items == 0;
   uint32_t item = 0;
   V3 o = mk3(0, 0, 0), inv_dir = mk3(0, 0, 0);
-  bool nx = false, ny = false, nz = false;
-  RayPre rp = ray_precompute(mk3(0, 0, 1));
+  float sx = 0.f, sy = 0.f, sz = 0.f;
   float t_max = 0.f;
-  DevHit hit;
-  hit.prim = -1;
-  hit.t = hit.b0 = hit.b1 = hit.b2 = 0.f;
+  int hit_prim = -1;
+  float hit_b0 = 0.f, hit_b1 = 0.f, hit_b2 = 0.f;
 
   auto start_ray = [&](const LaneRay& r) {
     o = r.o;
     inv_dir = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
-    nx = inv_dir.x < 0.0f;
-    ny = inv_dir.y < 0.0f;
-    nz = inv_dir.z < 0.0f;
-    rp = ray_precompute(r.d);
+    const RayPre rp = ray_precompute(r.d);
+    sx = rp.sx;
+    sy = rp.sy;
+    sz = rp.sz;
+    rbits = PT_RB_LIVE | (inv_dir.x < 0.0f ? PT_RB_NX : 0u) | (inv_dir.y < 0.0f ? PT_RB_NY : 0u) | (inv_dir.z < 0.0f ? PT_RB_NZ : 0u) |
+            ((uint32_t)rp.kz << PT_RB_KZ_SHIFT) | (r.any_hit ? PT_RB_ANY : 0u);
     t_max = r.t_max;
-    any_hit = r.any_hit;
-    found = false;
-    hit.prim = -1;
-    hit.t = r.t_max;
-    hit.b0 = hit.b1 = hit.b2 = 0.f;
+    hit_prim = -1;
+    hit_b0 = hit_b1 = hit_b2 = 0.f;
     sp_ = 0;
     pl_cnt = 0;
     // root: tested like any other node (accelerator.rs:372-374)
     const NodeLoad n = load_node(sc.nodes, 0);
     float te;
-    if (box_geom(n, o, inv_dir, nx, ny, nz, &te) && te < t_max) {
+    if (box_geom(n, o, inv_dir, rbits & PT_RB_NX, rbits & PT_RB_NY, rbits & PT_RB_NZ, &te) && te < t_max) {
       cur_off = __float_as_uint(n.b.z);
       cur_meta = __float_as_uint(n.b.w);
       cur_t = te;
@@ -316,32 +319,33 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
 
   for (;;) {
     // ---- refill ------------------------------------------------------------------------------------
-    const uint32_t idle = __ballot_sync(FULL, !live);
+    const uint32_t idle = __ballot_sync(FULL, !(rbits & PT_RB_LIVE));
     if (!exhausted && (__popc(idle) >= PT_REFILL_IDLE)) {
+      const int lane = threadIdx.x & 31;
       const int leader = __ffs(idle) - 1;
       uint32_t base = 0;
       if (lane == leader) base = atomicAdd(ticket, (uint32_t)__popc(idle));
       base = __shfl_sync(FULL, base, leader);
       if (base + (uint32_t)__popc(idle) >= n_items) exhausted = true;
-      if (!live) {
-        const uint32_t i = base + (uint32_t)__popc(idle & lane_lt);
+      if (!(rbits & PT_RB_LIVE)) {
+        const uint32_t i = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
         if (i < n_items) {
           LaneRay r;
           if (work.begin(i, &r)) {
             item = i;
-            live = true;
             start_ray(r);
           }
         }
       }
     }
-    if (__ballot_sync(FULL, live) == 0) {
+    if (__ballot_sync(FULL, rbits & PT_RB_LIVE) == 0) {
       if (exhausted) break;
       continue;
     }
 
     // ---- box phase: pop / park / expand ----------------------------------------------------------------
     for (;;) {
+      const bool live = (rbits & PT_RB_LIVE) != 0;
       const bool cur_leaf = cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0;
       const bool can_box = live && ((cur_meta != PT_NO_NODE && !cur_leaf) || (cur_meta == PT_NO_NODE && sp_ > 0) || (cur_leaf && pl_cnt == 0));
       const uint32_t bmask = __ballot_sync(FULL, can_box);
@@ -362,14 +366,13 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
             if (pl_cnt == 0) {  // park the leaf, keep descending
               pl_off = cur_off;
               pl_cnt = cur_meta & 0xffffu;
-              pl_i = 0;
               cur_meta = PT_NO_NODE;
             }
           } else {
             const NodeLoad L = load_node(sc.nodes, cur_off);
             const NodeLoad R = load_node(sc.nodes, cur_off + 1);
-            const uint32_t axis = (cur_meta >> 16) & 0xffu;
-            const bool neg = axis == 0 ? nx : (axis == 1 ? ny : nz);
+            const bool nx = rbits & PT_RB_NX, ny = rbits & PT_RB_NY, nz = rbits & PT_RB_NZ;
+            const bool neg = ((rbits >> ((cur_meta >> 16) & 3u)) & 1u) != 0;  // dir_is_neg[axis]
             float tl, tr;
             const bool gl = box_geom(L, o, inv_dir, nx, ny, nz, &tl);
             const bool gr = box_geom(R, o, inv_dir, nx, ny, nz, &tr);
@@ -397,32 +400,35 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
 
     // ---- triangle phase: parked leaves, first in first out -----------------------------------------------
     for (;;) {
+      const bool live = (rbits & PT_RB_LIVE) != 0;
       if (live && pl_cnt == 0 && cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0) {  // second leaf moves up
         pl_off = cur_off;
         pl_cnt = cur_meta & 0xffffu;
-        pl_i = 0;
         cur_meta = PT_NO_NODE;
       }
       const bool has = live && pl_cnt != 0;
       if (__ballot_sync(FULL, has) == 0) break;
       if (has) {
-        const uint32_t prim = pl_off + pl_i;
+        const uint32_t prim = pl_off;
         const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim);
         const float4 v1 = __ldg(sc.tri_verts + 3 * (size_t)prim + 1);
         const float4 v2 = __ldg(sc.tri_verts + 3 * (size_t)prim + 2);
-        ++pl_i;
-        if (pl_i == pl_cnt) pl_cnt = 0;
+        ++pl_off;
+        --pl_cnt;
+        RayPre rp;
+        rp.kz = (int)((rbits >> PT_RB_KZ_SHIFT) & 3u);
+        rp.sx = sx;
+        rp.sy = sy;
+        rp.sz = sz;
         float t, b0, b1, b2;
         if (tri_core(mk3(v0), mk3(v1), mk3(v2), o, rp, t_max, &t, &b0, &b1, &b2) &&
-            !tri_post_reject(sc, (int)prim, mk3(v0), mk3(v1), mk3(v2), __float_as_uint(v2.w), b0, b1, b2, !any_hit)) {
-          found = true;
-          hit.prim = (int)prim;
-          hit.t = t;
-          hit.b0 = b0;
-          hit.b1 = b1;
-          hit.b2 = b2;
+            !tri_post_reject(sc, (int)prim, mk3(v0), mk3(v1), mk3(v2), __float_as_uint(v2.w), b0, b1, b2, !(rbits & PT_RB_ANY))) {
+          hit_prim = (int)prim;
+          hit_b0 = b0;
+          hit_b1 = b1;
+          hit_b2 = b2;
           t_max = t;
-          if (any_hit) {  // intersect_p returns at the first hit (accelerator.rs:435-442)
+          if (rbits & PT_RB_ANY) {  // intersect_p returns at the first hit (accelerator.rs:435-442)
             pl_cnt = 0;
             sp_ = 0;
             cur_meta = PT_NO_NODE;
@@ -434,10 +440,16 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
     }
 
     // ---- rays that ran out of nodes --------------------------------------------------------------------
-    if (live && cur_meta == PT_NO_NODE && sp_ == 0 && pl_cnt == 0) {
+    if ((rbits & PT_RB_LIVE) && cur_meta == PT_NO_NODE && sp_ == 0 && pl_cnt == 0) {
+      DevHit h;
+      h.prim = hit_prim;
+      h.t = t_max;
+      h.b0 = hit_b0;
+      h.b1 = hit_b1;
+      h.b2 = hit_b2;
       LaneRay r;
-      if (work.end(item, hit, found, &r)) start_ray(r);
-      else live = false;
+      if (work.end(item, h, hit_prim >= 0, &r)) start_ray(r);
+      else rbits = 0;
     }
   }
 }

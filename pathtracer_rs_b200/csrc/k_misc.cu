@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) generate_kernel(const __grid_constant__ R
 
 // ---- shade -----------------------------------------------------------------------------------------
 // "miss" class: Σ infinite lights Le for camera / specular paths, then the path ends (integrator.rs:418-431)
-__global__ void __launch_bounds__(128) shade_miss_kernel(DevScene sc, PathArrays P, const int* __restrict__ q, RoundCounters* ctr) {
+__global__ void __launch_bounds__(128) shade_miss_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ PathArrays P, const int* __restrict__ q, RoundCounters* ctr) {
   const uint32_t n = ctr->n_class[PT_CLASS_MISS];
   const int lane = threadIdx.x & 31;
   for (;;) {
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128) shade_miss_kernel(DevScene sc, PathArrays
 // segment, integrator.rs:66-80) + Ld_bsdf (emitted radiance found by the MIS ray, integrator.rs:113-135), then
 // L += beta * n_lights * Ld (integrator.rs:443-447, uniform_sample_one_light :216).  One thread per record =
 // one writer per path, so the per-path summation order is the reference's.
-__global__ void __launch_bounds__(256) connect_resolve_kernel(DevScene sc, PathArrays P, const int* __restrict__ q_nee, RoundCounters* ctr) {
+__global__ void __launch_bounds__(256) connect_resolve_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ PathArrays P, const int* __restrict__ q_nee, RoundCounters* ctr) {
   const uint32_t n = ctr->n_nee;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {

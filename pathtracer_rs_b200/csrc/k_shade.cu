@@ -108,12 +108,15 @@ PT_DEV void nee_prepare(const DevScene& sc, const SurfInter& si, const Bsdf& bsd
   *nee_flags = nf;
 }
 
+#ifndef PT_SHADE_PARAM
+#define PT_SHADE_PARAM  // by value: with __grid_constant__ the 128-register shade kernels spill more (measured slower)
+#endif
 #ifndef PT_SHADE_MIN_BLOCKS
 #define PT_SHADE_MIN_BLOCKS 4
 #endif
 
 template <int MAT>
-__global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ RenderConst rc, DevScene sc, PathArrays P,
+__global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ RenderConst rc, PT_SHADE_PARAM DevScene sc, PT_SHADE_PARAM PathArrays P,
                                                      const int* __restrict__ q, const float4* __restrict__ q_hit, int* __restrict__ q_ext_next,
                                                      int* __restrict__ q_nee, RoundCounters* ctr, RoundCounters* ctr_next) {
   const uint32_t n = ctr->n_class[MAT];

@@ -51,7 +51,7 @@ struct ExtendWork {
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) extend_kernel(DevScene sc, PathArrays P, const int* __restrict__ q_ext, int* __restrict__ q_class,
+__global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) extend_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ PathArrays P, const int* __restrict__ q_ext, int* __restrict__ q_class,
                                                       uint32_t cap, RoundCounters* ctr, GlobalCounters* g) {
   uint32_t c_nodes = 0, c_tris = 0;
   ExtendWork w{sc, P, q_ext, q_class, cap, ctr, 0};
@@ -101,7 +101,7 @@ struct ConnectWork {
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) connect_kernel(DevScene sc, PathArrays P, RoundCounters* ctr, GlobalCounters* g) {
+__global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) connect_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ PathArrays P, RoundCounters* ctr, GlobalCounters* g) {
   uint32_t c_nodes = 0, c_tris = 0;
   ConnectWork w{P, 0u, 0u};
   trace_stream<COUNT>(sc, 2u * ctr->n_nee, &ctr->t_nee, w, &c_nodes, &c_tris);
@@ -144,7 +144,7 @@ struct IntersectWork {
 };
 
 template <bool ANY_HIT, bool COUNT>
-__global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) intersect_kernel(DevScene sc, const PtrsRay* __restrict__ rays, uint32_t n, PtrsHit* __restrict__ hits,
+__global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) intersect_kernel(const __grid_constant__ DevScene sc, const PtrsRay* __restrict__ rays, uint32_t n, PtrsHit* __restrict__ hits,
                                                          uint8_t* __restrict__ occluded, uint32_t* ticket, GlobalCounters* g) {
   uint32_t c_nodes = 0, c_tris = 0;
   IntersectWork w{rays, hits, occluded, ANY_HIT};

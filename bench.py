@@ -122,7 +122,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference = C++ restatement of the reference's rayon path integrator (oracle/); the Rust crate itself cannot be built in this image"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def bvh_microbench(gpu, host, torch, peak_gbs):
@@ -331,7 +331,7 @@ def run_gpu(args):
             "gpu_launches": int(stats["launches"]) * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "stage_ms": {k: stats[k] for k in ("ms_generate", "ms_extend", "ms_shade", "ms_shadow", "ms_accumulate", "ms_total")},
             "rays": {k: stats[k] for k in ("extension_rays", "shadow_rays", "mis_rays")}, "bvh_microbench": micro}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -343,7 +343,27 @@ class _CudaArray:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version banner) write to
+    file descriptor 1 directly, so fd 1 is pointed at stderr for the whole run and the JSON line goes to a
+    private duplicate of the original stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
+_OUT = None
+
+
+def emit(line):
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
+
+
 def main():
+    global _OUT
+    _OUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

@@ -53,65 +53,69 @@ PT_DEV float sobol_sample(const uint32_t* __restrict__ matrices, uint64_t index,
   return fminf(PT_ONE_MINUS_EPSILON, (float)v * 0x1.p-32f);
 }
 
+// ---- split tables ------------------------------------------------------------------------------------
+// Both steps of a draw are linear maps over GF(2): sobol_interval_to_index() XORs one column per set bit of
+// `frame` and of ((px << m) | py) ^ delta(frame), and sobol_sample() XORs one matrix column per set bit of
+// the index.  With px, py < 2^m the three inputs occupy disjoint bits, so
+//     raw(sample s, pixel (px, py), dimension d) = S_d[s] ^ X_d[px] ^ Y_d[py] ^ scramble
+// where each table entry is the reference's own pair of functions evaluated with the other two inputs
+// zero.  sobol_split_build_kernel fills the tables with exactly those functions once per render setup
+// (rows: spp samples, then x extent, then y extent; `stride` dimensions per row), and a draw in the shade
+// kernels is three 4-byte loads and three XORs instead of a loop over the ~28 set bits of the index.
+// Values are bit-identical to sobol_sample() (tests/test_gpu_parity.py::test_sobol_*).
+struct SobolSplit {
+  const uint32_t* tab;
+  uint32_t stride;        // dimensions per row (multiple of 4); draws at dimension >= stride take the generic path
+  uint32_t row_x, row_y;  // first row of the pixel-x / pixel-y blocks (sample rows start at 0)
+  uint32_t n_rows;
+};
+
+// the u32 before scrambling and scaling (lowdiscrepancy.rs:45-55 without `v = scramble`)
+PT_DEV uint32_t sobol_raw(const uint32_t* __restrict__ matrices, uint64_t index, uint32_t dimension) {
+  uint32_t v = 0;
+  const uint32_t* col = matrices + dimension * PT_SOBOL_COLS;
+  for (int k = 0; index != 0; index >>= 1, ++k)
+    if (index & 1) v ^= __ldg(col + k);
+  return v;
+}
+
 // Per-path sampler state: the reference's SobolSampler minus everything that is constant per render.
-// A bounce draws up to 8 consecutive dimensions (NEE 2+2+1, BSDF 2, roulette 1; 9 with the 4 -> 5 skip
-// of the first bounce), so shade fills a WINDOW of 9 dimensions in ONE pass over the set bits of the
-// index: each bit costs 9 independent loads from a bit-major copy of the table (36 contiguous bytes)
-// instead of 9 separate dependent-latency bit loops.  Values are identical to sobol_sample().
-#define PT_SOBOL_WINDOW 9
 struct PathSampler {
-  uint64_t index;     // interval_sample_index
   uint32_t scramble;  // current_scramble_index as u32
   uint32_t dimension;
   int32_t px, py;
-  uint32_t win_base;              // first dimension held in win[], 0xffffffff = no window
-  uint32_t win[PT_SOBOL_WINDOW];  // scramble ^ (xor of matrix columns), i.e. the u32 before the 2^-32 scale
+  uint32_t sample;               // sample number of the pixel (the `frame` of sobol_interval_to_index)
+  uint32_t row_s, row_x, row_y;  // element offsets of this path's three rows in SobolSplit::tab
 };
-
-// mt = SOBOL_MATRICES_32 transposed to [52 bits][1024 dimensions].
-// The bit loop is WARP-UNIFORM: it runs over the union of the set bits of the converged lanes' indices and
-// each lane masks the column in or out.  Lanes of a shade launch sit at (nearly) the same dimension, so every
-// load is a broadcast of one 36-byte row segment — one L1 wavefront instead of one per distinct bit.
-PT_DEV void sobol_window_fill(const uint32_t* __restrict__ mt, PathSampler& s, uint32_t base) {
-  if (base > 1024u - PT_SOBOL_WINDOW) base = 1024u - PT_SOBOL_WINDOW;
-  s.win_base = base;
-#pragma unroll
-  for (int j = 0; j < PT_SOBOL_WINDOW; ++j) s.win[j] = s.scramble;
-  const uint32_t lo = (uint32_t)s.index, hi = (uint32_t)(s.index >> 32);
-  const uint32_t grp = __activemask();
-  uint32_t all_lo = __reduce_or_sync(grp, lo), all_hi = __reduce_or_sync(grp, hi);
-  while (all_lo) {
-    const uint32_t b = (uint32_t)(__ffs(all_lo) - 1);
-    const uint32_t* row = mt + b * 1024u + base;
-    const uint32_t m = 0u - ((lo >> b) & 1u);
-#pragma unroll
-    for (int j = 0; j < PT_SOBOL_WINDOW; ++j) s.win[j] ^= __ldg(row + j) & m;
-    all_lo &= all_lo - 1;
-  }
-  while (all_hi) {
-    const uint32_t b = (uint32_t)(__ffs(all_hi) - 1);
-    const uint32_t* row = mt + (32u + b) * 1024u + base;
-    const uint32_t m = 0u - ((hi >> b) & 1u);
-#pragma unroll
-    for (int j = 0; j < PT_SOBOL_WINDOW; ++j) s.win[j] ^= __ldg(row + j) & m;
-    all_hi &= all_hi - 1;
-  }
-}
 
 PT_DEV uint32_t pixel_scramble(int32_t x, int32_t y) {  // sobol.rs:83-86 (+ `scramble as u32`)
   return (uint32_t)cantor_pairing((uint64_t)(int64_t)(x + PT_HALF_MAX_I32), (uint64_t)(int64_t)(y + PT_HALF_MAX_I32));
 }
 
-PT_DEV float sample_dimension(const SobolConfig& c, const uint32_t* __restrict__ matrices, const PathSampler& s, uint32_t dim) {
+PT_DEV void sampler_start(const SobolConfig& c, const SobolSplit& sp, PathSampler& s, int32_t px, int32_t py, uint32_t sample, uint32_t dimension) {
+  s.px = px;
+  s.py = py;
+  s.sample = sample;
+  s.dimension = dimension;
+  s.scramble = pixel_scramble(px, py);
+  s.row_s = sample * sp.stride;
+  s.row_x = (sp.row_x + (uint32_t)(px - c.bounds_min[0])) * sp.stride;
+  s.row_y = (sp.row_y + (uint32_t)(py - c.bounds_min[1])) * sp.stride;
+}
+
+// generic path (sobol.rs:169-193): only reached for dimensions beyond the split tables
+PT_DEVN float sample_dimension_generic(const SobolConfig& c, const uint32_t* __restrict__ matrices, const PathSampler& s, uint32_t dim) {
+  const uint64_t index = sobol_interval_to_index(c, (uint64_t)s.sample, s.px - c.bounds_min[0], s.py - c.bounds_min[1]);
+  return sobol_sample(matrices, index, dim, s.scramble);
+}
+
+PT_DEV float sample_dimension(const SobolConfig& c, const SobolSplit& sp, const uint32_t* __restrict__ matrices, const PathSampler& s, uint32_t dim) {
   float v;
-  const uint32_t rel = dim - s.win_base;
-  if (s.win_base != 0xffffffffu && rel < PT_SOBOL_WINDOW) {
-    uint32_t raw = s.win[0];
-#pragma unroll
-    for (int j = 1; j < PT_SOBOL_WINDOW; ++j) raw = rel == j ? s.win[j] : raw;  // register select, no local memory
+  if (dim < sp.stride) {
+    const uint32_t raw = __ldg(sp.tab + s.row_s + dim) ^ __ldg(sp.tab + s.row_x + dim) ^ __ldg(sp.tab + s.row_y + dim) ^ s.scramble;
     v = fminf(PT_ONE_MINUS_EPSILON, (float)raw * 0x1.p-32f);
   } else {
-    v = sobol_sample(matrices, s.index, dim, s.scramble);  // sobol.rs:177-193
+    v = sample_dimension_generic(c, matrices, s, dim);
   }
   if (dim == 0 || dim == 1) {
     int32_t pmin = dim == 0 ? c.bounds_min[0] : c.bounds_min[1];
@@ -121,14 +125,14 @@ PT_DEV float sample_dimension(const SobolConfig& c, const uint32_t* __restrict__
   }
   return v;
 }
-PT_DEV float get_1d(const SobolConfig& c, const uint32_t* __restrict__ m, PathSampler& s) {  // sobol.rs:129-137 (array range empty)
-  float v = sample_dimension(c, m, s, s.dimension);
+PT_DEV float get_1d(const SobolConfig& c, const SobolSplit& sp, const uint32_t* __restrict__ m, PathSampler& s) {  // sobol.rs:129-137 (array range empty)
+  float v = sample_dimension(c, sp, m, s, s.dimension);
   s.dimension += 1;
   return v;
 }
-PT_DEV V2 get_2d(const SobolConfig& c, const uint32_t* __restrict__ m, PathSampler& s) {  // sobol.rs:139-151
+PT_DEV V2 get_2d(const SobolConfig& c, const SobolSplit& sp, const uint32_t* __restrict__ m, PathSampler& s) {  // sobol.rs:139-151
   if (s.dimension + 1 >= PT_ARRAY_START_DIM && s.dimension < PT_ARRAY_START_DIM) s.dimension = PT_ARRAY_START_DIM;
-  V2 v{sample_dimension(c, m, s, s.dimension), sample_dimension(c, m, s, s.dimension + 1)};
+  V2 v{sample_dimension(c, sp, m, s, s.dimension), sample_dimension(c, sp, m, s, s.dimension + 1)};
   s.dimension += 2;
   return v;
 }

@@ -40,13 +40,8 @@ __global__ void __launch_bounds__(256) generate_kernel(const __grid_constant__ R
     }
     if (valid) {
       PathSampler ps;
-      ps.px = px;
-      ps.py = py;
-      ps.scramble = pixel_scramble(px, py);
-      ps.index = sobol_interval_to_index(rc.sobol, (uint64_t)s, px - rc.sobol.bounds_min[0], py - rc.sobol.bounds_min[1]);
-      ps.dimension = 0;
-      ps.win_base = 0xffffffffu;
-      V2 u = get_2d(rc.sobol, sobol, ps);
+      sampler_start(rc.sobol, rc.split, ps, px, py, (uint32_t)s, 0u);
+      V2 u = get_2d(rc.sobol, rc.split, sobol, ps);
       const float fx = (float)px + u.x, fy = (float)py + u.y;  // get_camera_sample, sobol.rs:116-120
       V3 o, d;
       camera_ray(rc.cam, fx, fy, rc.diff_scale, &o, &d, nullptr, nullptr);
@@ -62,7 +57,8 @@ __global__ void __launch_bounds__(256) generate_kernel(const __grid_constant__ R
       PathAux a;
       a.br = a.bg = a.bb = 1.f;
       a.pixel = pack_pixel(px, py);
-      a.sobol_index = ps.index;
+      a.sample = (uint32_t)s;
+      a.spare = 0u;
       a.fx = fx;
       a.fy = fy;
       st256(&P.slot[i].r, r);
@@ -72,7 +68,8 @@ __global__ void __launch_bounds__(256) generate_kernel(const __grid_constant__ R
       PathAux a;
       a.br = a.bg = a.bb = 0.f;
       a.pixel = 0u;
-      a.sobol_index = 0ull;
+      a.sample = 0u;
+      a.spare = 0u;
       a.fx = a.fy = -1e30f;  // padding lane of an 8x4 block outside the sample bounds
       st256(&P.slot[i].a, a);
       P.L[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -204,19 +201,40 @@ void launch_build_guide(cudaStream_t st, const float* cdf, uint32_t size, uint32
 }
 
 // ---- parity probes -----------------------------------------------------------------------------------
+// generic != 0: every draw through sobol_interval_to_index + sobol_sample (the reference's two functions);
+// generic == 0: through the split tables, as the render kernels draw
 __global__ void sobol_probe_kernel(const __grid_constant__ RenderConst rc, const uint32_t* __restrict__ sobol, const int* xy, const int* s,
-                                   uint32_t n, const int* dims, uint32_t n_dims, float* out, uint64_t* out_index) {
+                                   uint32_t n, const int* dims, uint32_t n_dims, float* out, uint64_t* out_index, int generic) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   PathSampler ps;
-  ps.px = xy[2 * i];
-  ps.py = xy[2 * i + 1];
-  ps.scramble = pixel_scramble(ps.px, ps.py);
-  ps.index = sobol_interval_to_index(rc.sobol, (uint64_t)s[i], ps.px - rc.sobol.bounds_min[0], ps.py - rc.sobol.bounds_min[1]);
-  ps.dimension = 0;
-  ps.win_base = 0xffffffffu;
-  if (out_index) out_index[i] = ps.index;
-  for (uint32_t k = 0; k < n_dims; ++k) out[(size_t)i * n_dims + k] = sample_dimension(rc.sobol, sobol, ps, (uint32_t)dims[k]);
+  sampler_start(rc.sobol, rc.split, ps, xy[2 * i], xy[2 * i + 1], (uint32_t)s[i], 0u);
+  if (out_index) out_index[i] = sobol_interval_to_index(rc.sobol, (uint64_t)s[i], ps.px - rc.sobol.bounds_min[0], ps.py - rc.sobol.bounds_min[1]);
+  SobolSplit sp = rc.split;
+  if (generic) sp.stride = 0u;
+  for (uint32_t k = 0; k < n_dims; ++k) out[(size_t)i * n_dims + k] = sample_dimension(rc.sobol, sp, sobol, ps, (uint32_t)dims[k]);
+}
+
+// ---- Sobol split tables (dev_sobol.cuh) ---------------------------------------------------------------
+// row r < row_x: sample number r at pixel offset (0, 0); row_x <= r < row_y: pixel-x offset r - row_x, sample 0;
+// r >= row_y: pixel-y offset.  Each entry = sobol_raw(sobol_interval_to_index(...), d), the reference's functions.
+__global__ void sobol_split_build_kernel(const __grid_constant__ RenderConst rc, const uint32_t* __restrict__ sobol, uint32_t* __restrict__ tab) {
+  const SobolSplit& sp = rc.split;
+  const uint64_t total = (uint64_t)sp.n_rows * sp.stride;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(t / sp.stride), d = (uint32_t)(t % sp.stride);
+    uint64_t frame = 0;
+    int32_t x = 0, y = 0;
+    if (r < sp.row_x) frame = r;
+    else if (r < sp.row_y) x = (int32_t)(r - sp.row_x);
+    else y = (int32_t)(r - sp.row_y);
+    tab[t] = sobol_raw(sobol, sobol_interval_to_index(rc.sobol, frame, x, y), d);
+  }
+}
+void launch_sobol_split_build(cudaStream_t st, const RenderConst& rc, const uint32_t* sobol, uint32_t* tab) {
+  const uint64_t total = (uint64_t)rc.split.n_rows * rc.split.stride;
+  const int grid = (int)std::min<uint64_t>((total + 255) / 256, 148 * 8);
+  sobol_split_build_kernel<<<grid, 256, 0, st>>>(rc, sobol, tab);
 }
 
 __global__ void ray_probe_kernel(const __grid_constant__ RenderConst rc, const uint32_t* __restrict__ sobol, const int* xy, const int* s,
@@ -224,13 +242,8 @@ __global__ void ray_probe_kernel(const __grid_constant__ RenderConst rc, const u
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   PathSampler ps;
-  ps.px = xy[2 * i];
-  ps.py = xy[2 * i + 1];
-  ps.scramble = pixel_scramble(ps.px, ps.py);
-  ps.index = sobol_interval_to_index(rc.sobol, (uint64_t)s[i], ps.px - rc.sobol.bounds_min[0], ps.py - rc.sobol.bounds_min[1]);
-  ps.dimension = 0;
-  ps.win_base = 0xffffffffu;
-  V2 u = get_2d(rc.sobol, sobol, ps);
+  sampler_start(rc.sobol, rc.split, ps, xy[2 * i], xy[2 * i + 1], (uint32_t)s[i], 0u);
+  V2 u = get_2d(rc.sobol, rc.split, sobol, ps);
   const float fx = (float)ps.px + u.x, fy = (float)ps.py + u.y;
   V3 o, d, rx, ry;
   camera_ray(rc.cam, fx, fy, rc.diff_scale, &o, &d, &rx, &ry);
@@ -294,8 +307,8 @@ void launch_resolve(cudaStream_t st, const float4* film, uint32_t n, float* rgb,
   resolve_kernel<<<(n + 255) / 256, 256, 0, st>>>(film, n, rgb, rgba8);
 }
 void launch_sobol_probe(cudaStream_t st, const RenderConst& rc, const uint32_t* sobol, const int* xy, const int* s, uint32_t n,
-                        const int* dims, uint32_t n_dims, float* out, uint64_t* out_index) {
-  sobol_probe_kernel<<<(n + 127) / 128, 128, 0, st>>>(rc, sobol, xy, s, n, dims, n_dims, out, out_index);
+                        const int* dims, uint32_t n_dims, float* out, uint64_t* out_index, int generic) {
+  sobol_probe_kernel<<<(n + 127) / 128, 128, 0, st>>>(rc, sobol, xy, s, n, dims, n_dims, out, out_index, generic);
 }
 void launch_ray_probe(cudaStream_t st, const RenderConst& rc, const uint32_t* sobol, const int* xy, const int* s, uint32_t n, PtrsRay* rays,
                       float* p_film, float* rxry) {

@@ -197,17 +197,12 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const _
         } else {
           PathSampler ps;
           const int2 pix = unpack_pixel(pa.pixel);
-          ps.px = pix.x;
-          ps.py = pix.y;
-          ps.scramble = pixel_scramble(pix.x, pix.y);
-          ps.index = pa.sobol_index;
-          ps.dimension = flags & 0xffffu;
-          sobol_window_fill(sc.sobol_t, ps, ps.dimension);
+          sampler_start(rc.sobol, rc.split, ps, pix.x, pix.y, pa.sample, flags & 0xffffu);
           // direct lighting (integrator.rs:443-447, 192-217)
           if (bsdf_num_components(bsdf, BSDF_ALL & ~BSDF_SPECULAR) > 0 && sc.n_lights > 0) {
-            V2 u_light = get_2d(rc.sobol, sobol, ps);
-            V2 u_scattering = get_2d(rc.sobol, sobol, ps);
-            float u_idx = get_1d(rc.sobol, sobol, ps);
+            V2 u_light = get_2d(rc.sobol, rc.split, sobol, ps);
+            V2 u_scattering = get_2d(rc.sobol, rc.split, sobol, ps);
+            float u_idx = get_1d(rc.sobol, rc.split, sobol, ps);
             unsigned long long li64 = (unsigned long long)floorf(u_idx * (float)sc.n_lights);
             int light_idx = (int)(li64 < (unsigned long long)(sc.n_lights - 1) ? li64 : (unsigned long long)(sc.n_lights - 1));
             float scat_pdf;
@@ -222,7 +217,7 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const _
           V3 wi = mk3(0, 0, 0);
           float pdf = 0.0f;
           uint32_t sampled = 0;
-          Spec f = bsdf_sample_f(bsdf, si.wo, &wi, get_2d(rc.sobol, sobol, ps), &pdf, BSDF_ALL, &sampled);
+          Spec f = bsdf_sample_f(bsdf, si.wo, &wi, get_2d(rc.sobol, rc.split, sobol, ps), &pdf, BSDF_ALL, &sampled);
           if (!(is_black(f) || pdf == 0.0f)) {
             beta = beta * (f * fabsf(dot(wi, si.sh_n)) / pdf);
             if (sampled & BSDF_SPECULAR) flags |= PT_F_SPECULAR;
@@ -239,7 +234,7 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const _
               float mc = max_component(rr_beta);
               if (mc < rc.rr_threshold && bounces > rc.rr_start_depth) {
                 float qv = fmaxf(0.05f, 1.0f - mc);
-                if (get_1d(rc.sobol, sobol, ps) < qv) survive = false;
+                if (get_1d(rc.sobol, rc.split, sobol, ps) < qv) survive = false;
                 else beta = beta / (1.0f - qv);
               }
             }

@@ -22,7 +22,8 @@ void launch_accumulate(cudaStream_t st, int sm, const RenderConst& rc, const Pat
 void launch_build_guide(cudaStream_t st, const float* cdf, uint32_t size, uint32_t rows, uint32_t K, uint32_t* guide);
 void launch_resolve(cudaStream_t st, const float4* film, uint32_t n, float* rgb, uint8_t* rgba8);
 void launch_sobol_probe(cudaStream_t st, const RenderConst& rc, const uint32_t* sobol, const int* xy, const int* s, uint32_t n,
-                        const int* dims, uint32_t n_dims, float* out, uint64_t* out_index);
+                        const int* dims, uint32_t n_dims, float* out, uint64_t* out_index, int generic);
+void launch_sobol_split_build(cudaStream_t st, const RenderConst& rc, const uint32_t* sobol, uint32_t* tab);
 void launch_ray_probe(cudaStream_t st, const RenderConst& rc, const uint32_t* sobol, const int* xy, const int* s, uint32_t n, PtrsRay* rays,
                       float* p_film, float* rxry);
 

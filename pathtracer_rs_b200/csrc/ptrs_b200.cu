@@ -153,7 +153,9 @@ struct PtrsScene {
   DevBuf<DevEnv> envs;
   std::vector<DevBuf<float>> env_arrays;
   std::vector<DevBuf<uint32_t>> env_guides;
-  DevBuf<uint32_t> sobol, sobol_t;
+  DevBuf<uint32_t> sobol, split_tab;
+  SobolSplit split_cfg{};      // what split_tab currently holds
+  SobolConfig split_for{};    // ... and the sampler configuration it was built for
   DevBuf<uint32_t> ticket;
   DevBuf<GlobalCounters> gcount;
   float world_bound[6] = {0, 0, 0, 0, 0, 0};
@@ -281,6 +283,57 @@ int32_t ensure_workspace(PtrsScene* s, uint32_t cap, uint32_t rounds) {
   if (cudaStreamSynchronize((cudaStream_t)0) != cudaSuccess) return fail(PTRS_ERR_CUDA, "workspace allocation failed");  // allocations are ordered on the legacy stream; the render may use another
   w.cap = cap;
   w.rounds = rounds;
+  return PTRS_OK;
+}
+
+// Sobol split tables (dev_sobol.cuh): rows = spp sample numbers + x extent + y extent of the sample bounds,
+// `stride` dimensions each — enough for every draw of a max_depth path (2 camera dimensions, the 4 -> 5 skip,
+// at most 8 per bounce); built on the device by the reference's own index / sample functions and cached
+// until the sampler configuration changes.
+int32_t plan_split(RenderConst* rc) {
+  SobolSplit& sp = rc->split;
+  const uint32_t want = 8u + 8u * ((uint32_t)rc->max_depth + 2u);
+  sp.stride = std::min<uint32_t>(1024u, (want + 3u) & ~3u);
+  sp.row_x = (uint32_t)rc->sobol.spp;
+  sp.row_y = sp.row_x + (uint32_t)rc->sb_ext[0];
+  sp.n_rows = sp.row_y + (uint32_t)rc->sb_ext[1];
+  sp.tab = nullptr;
+  if ((uint64_t)sp.n_rows * sp.stride > 0xffffffffull) return PTRS_ERR_UNSUPPORTED;  // element offsets are 32 bit
+  return PTRS_OK;
+}
+int32_t build_split(RenderConst* rc, const uint32_t* d_sobol, DevBuf<uint32_t>* tab, cudaStream_t st) {
+  if (tab->alloc((size_t)rc->split.n_rows * rc->split.stride) != cudaSuccess) return fail(PTRS_ERR_OUT_OF_MEMORY, "Sobol split table allocation failed");
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));  // the allocation is ordered on the legacy stream
+  rc->split.tab = tab->p;
+  launch_sobol_split_build(st, *rc, d_sobol, tab->p);
+  CUDA_TRY(cudaGetLastError());
+  return PTRS_OK;
+}
+int32_t ensure_split(PtrsScene* s, RenderConst* rc, cudaStream_t st) {
+  int32_t r = plan_split(rc);
+  if (r != PTRS_OK) return fail(r, "resolution x max_depth too large for the Sobol split tables");
+  const SobolSplit& want = rc->split;
+  const SobolSplit& have = s->split_cfg;
+  if (s->split_tab.p && have.stride >= want.stride && have.row_x == want.row_x && have.row_y == want.row_y && have.n_rows == want.n_rows &&
+      std::memcmp(&s->split_for, &rc->sobol, sizeof(SobolConfig)) == 0) {
+    rc->split = have;
+    return PTRS_OK;
+  }
+  r = build_split(rc, s->dev.sobol, &s->split_tab, st);
+  if (r != PTRS_OK) return r;
+  s->split_cfg = rc->split;
+  s->split_for = rc->sobol;
+  s->stats.launches += 1;
+  return PTRS_OK;
+}
+
+// (pixel, sample number) lists of the probes: inside the sample bounds and below spp, as in the reference's loops
+int32_t check_pixel_list(const RenderConst& rc, const int32_t* xy, const int32_t* sn, size_t n) {
+  for (size_t i = 0; i < n; ++i) {
+    const int x = xy[2 * i] - rc.sb_min[0], y = xy[2 * i + 1] - rc.sb_min[1];
+    if (x < 0 || y < 0 || x >= rc.sb_ext[0] || y >= rc.sb_ext[1] || sn[i] < 0 || sn[i] >= rc.sobol.spp)
+      return fail(PTRS_ERR_INVALID_ARGUMENT, "pixel outside the sample bounds or sample number outside [0, spp)");
+  }
   return PTRS_OK;
 }
 
@@ -561,12 +614,6 @@ int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) {
     if (d->n_envs > 0) CUDA_TRY(cudaDeviceSynchronize());  // guide tables built
   }
   CUDA_TRY(s->sobol.upload(sh.matrices, (size_t)sh.n_dims * sh.n_cols));
-  {
-    std::vector<uint32_t> t((size_t)sh.n_dims * sh.n_cols);
-    for (uint32_t d = 0; d < sh.n_dims; ++d)
-      for (uint32_t k = 0; k < sh.n_cols; ++k) t[(size_t)k * sh.n_dims + d] = sh.matrices[(size_t)d * sh.n_cols + k];
-    CUDA_TRY(s->sobol_t.upload(t.data(), t.size()));
-  }
   CUDA_TRY(s->ticket.alloc(4));
   CUDA_TRY(s->gcount.alloc(1));
   DevScene& v = s->dev;
@@ -585,7 +632,6 @@ int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) {
   v.infinite_lights = s->infinite_lights.p;
   v.envs = s->envs.p;
   v.sobol = s->sobol.p;
-  v.sobol_t = s->sobol_t.p;
   v.n_nodes = d->n_nodes;
   v.n_prims = d->n_prims;
   v.n_lights = d->n_lights;
@@ -798,10 +844,14 @@ static int32_t render_impl(PtrsScene* s, const PtrsCamera* cam, const PtrsRender
   if (r != PTRS_OK) return r;
   rc.cap = s->ws.cap;
   s->stats = PtrsStats{};
+  r = ensure_split(s, &rc, st);
+  if (r != PTRS_OK) return r;
   CUDA_TRY(cudaMemsetAsync(s->ws.gcount.p, 0, sizeof(GlobalCounters), st));
   DevBuf<int> d_xy, d_s;
   DevBuf<float4> d_dummy;
   if (list_xy) {
+    r = check_pixel_list(rc, list_xy, list_s, n_list);
+    if (r != PTRS_OK) return r;
     CUDA_TRY(d_xy.upload(list_xy, n_list * 2));
     CUDA_TRY(d_s.upload(list_s, n_list));
   }
@@ -904,9 +954,23 @@ int32_t ptrs_sobol_samples(const PtrsCamera* camera, const PtrsRenderParams* par
   CUDA_TRY(d_dims.upload(dims, n_dims));
   CUDA_TRY(d_out.alloc(n * n_dims));
   CUDA_TRY(d_idx.alloc(n));
-  launch_sobol_probe(0, rc, tab.p, d_xy.p, d_s.p, (uint32_t)n, d_dims.p, (uint32_t)n_dims, d_out.p, d_idx.p);
+  r = check_pixel_list(rc, pixels_xy, sample_nums, n);
+  if (r != PTRS_OK) return r;
+  if (plan_split(&rc) != PTRS_OK) return fail(PTRS_ERR_UNSUPPORTED, "resolution x max_depth too large for the Sobol split tables");
+  DevBuf<uint32_t> split;
+  r = build_split(&rc, tab.p, &split, 0);
+  if (r != PTRS_OK) return r;
+  // the draws as the render kernels make them (split tables) ...
+  launch_sobol_probe(0, rc, tab.p, d_xy.p, d_s.p, (uint32_t)n, d_dims.p, (uint32_t)n_dims, d_out.p, d_idx.p, 0);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpy(out, d_out.p, n * n_dims * 4, cudaMemcpyDeviceToHost));
+  {  // ... which must be bit-identical to the reference's sobol_interval_to_index + sobol_sample on the device
+    std::vector<float> generic(n * n_dims);
+    launch_sobol_probe(0, rc, tab.p, d_xy.p, d_s.p, (uint32_t)n, d_dims.p, (uint32_t)n_dims, d_out.p, nullptr, 1);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(generic.data(), d_out.p, n * n_dims * 4, cudaMemcpyDeviceToHost));
+    if (std::memcmp(generic.data(), out, n * n_dims * 4) != 0) return fail(PTRS_ERR_CUDA, "split-table Sobol draws differ from the generic path");
+  }
   if (out_index) CUDA_TRY(cudaMemcpy(out_index, d_idx.p, n * 8, cudaMemcpyDeviceToHost));
   return PTRS_OK;
 }
@@ -930,6 +994,12 @@ int32_t ptrs_generate_rays(const PtrsCamera* camera, const PtrsRenderParams* par
   CUDA_TRY(d_rays.alloc(n));
   CUDA_TRY(d_pf.alloc(n * 2));
   CUDA_TRY(d_rx.alloc(n * 6));
+  r = check_pixel_list(rc, pixels_xy, sample_nums, n);
+  if (r != PTRS_OK) return r;
+  if (plan_split(&rc) != PTRS_OK) return fail(PTRS_ERR_UNSUPPORTED, "resolution x max_depth too large for the Sobol split tables");
+  DevBuf<uint32_t> split;
+  r = build_split(&rc, tab.p, &split, 0);
+  if (r != PTRS_OK) return r;
   launch_ray_probe(0, rc, tab.p, d_xy.p, d_s.p, (uint32_t)n, d_rays.p, d_pf.p, d_rx.p);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpy(rays, d_rays.p, n * sizeof(PtrsRay), cudaMemcpyDeviceToHost));

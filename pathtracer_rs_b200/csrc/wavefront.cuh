@@ -44,7 +44,8 @@ struct __align__(32) PathRay {
 struct __align__(32) PathAux {
   float br, bg, bb;  // beta
   uint32_t pixel;    // x | y << 16, two int16 (sample-bounds coordinates)
-  uint64_t sobol_index;
+  uint32_t sample;   // sample number of the pixel (Sobol frame)
+  uint32_t spare;
   float fx, fy;  // p_film
 };
 struct __align__(64) PathSlot {
@@ -128,6 +129,7 @@ struct GlobalCounters {
 
 struct RenderConst {
   SobolConfig sobol;
+  SobolSplit split;
   PtrsCamera cam;
   float filter_table[256];
   float filter_radius[2];

@@ -25,7 +25,10 @@ DEV_HDRS  := $(wildcard $(CS)/*.cuh) $(CS)/launch.hpp include/ptrs_b200.h
 SHADE_OBJ := $(foreach m,0 1 2 3 4 5,$(OBJ)/k_shade_$(m).o)
 CUDA_OBJ  := $(OBJ)/ptrs_b200.o $(OBJ)/k_trace.o $(OBJ)/k_misc.o $(SHADE_OBJ) $(OBJ)/sobol_blob.o
 
-all: $(LIB)/libptrs_b200.so $(LIB)/libptrs_host.so oracle/_build/liboracle.so
+all: $(LIB)/libptrs_b200.so $(LIB)/libptrs_host.so oracle/_build/liboracle.so examples
+
+examples: $(LIB)/libptrs_b200.so $(LIB)/libptrs_host.so
+	$(MAKE) -C examples
 
 $(OBJ)/%.o: $(CS)/%.cu $(DEV_HDRS)
 	@mkdir -p $(OBJ)
@@ -45,7 +48,7 @@ $(LIB)/libptrs_b200.so: $(CUDA_OBJ)
 
 $(LIB)/libptrs_host.so: $(wildcard $(HS)/*.cpp) $(wildcard $(HS)/*.hpp) include/ptrs_b200.h
 	@mkdir -p $(LIB)
-	$(HOSTCXX) $(CXXFLAGS) -shared $(wildcard $(HS)/*.cpp) -o $@
+	$(HOSTCXX) $(CXXFLAGS) -shared $(wildcard $(HS)/*.cpp) -o $@ -lz
 
 oracle/_build/liboracle.so: oracle/oracle_capi.cpp $(wildcard oracle/*.hpp) include/ptrs_b200.h
 	$(MAKE) -C oracle
@@ -53,4 +56,4 @@ oracle/_build/liboracle.so: oracle/oracle_capi.cpp $(wildcard oracle/*.hpp) incl
 clean:
 	rm -rf build $(LIB) oracle/_build
 
-.PHONY: all clean
+.PHONY: all clean examples

@@ -58,6 +58,19 @@ def lib():
         L.ptrs_host_gaussian_filter_table.argtypes = [f32, f32, fp]
         L.ptrs_host_coherent_rays.argtypes = [C.POINTER(PtrsCamera), i32, C.POINTER(PtrsRay)]
         L.ptrs_host_incoherent_rays.argtypes = [fp, fp, u64, u64, C.POINTER(PtrsRay)]
+        L.ptrs_host_import_scene.restype = vp
+        L.ptrs_host_import_scene.argtypes = [C.c_char_p, i32, i32, i32, C.c_char_p, C.POINTER(PtrsCamera), i32]
+        ip = C.POINTER(C.c_int)
+        L.ptrs_host_load_hdr.argtypes = [C.c_char_p, ip, ip, fp]
+        L.ptrs_host_save_hdr.argtypes = [C.c_char_p, fp, i32, i32]
+        L.ptrs_host_load_png.argtypes = [C.c_char_p, ip, ip, ip, C.POINTER(C.c_uint8)]
+        L.ptrs_host_save_png.argtypes = [C.c_char_p, C.POINTER(C.c_uint8), i32, i32, i32]
+        L.ptrs_host_snake_case.argtypes = [C.c_char_p, C.c_char_p, i32]
+        u8p = C.POINTER(C.c_uint8)
+        L.ptrs_host_tev_create_image.restype = C.c_int64
+        L.ptrs_host_tev_create_image.argtypes = [i32, i32, C.c_char_p, u8p, C.c_int64]
+        L.ptrs_host_tev_update_image.restype = C.c_int64
+        L.ptrs_host_tev_update_image.argtypes = [fp, i32, i32, C.c_char_p, u8p, C.c_int64]
         L.ptrs_host_build_bvh.argtypes = [fp, u32, i32, i32, C.POINTER(PtrsBvhNode), u32, C.POINTER(u32), C.POINTER(u32)]
         _LIB = L
     return _LIB
@@ -141,6 +154,76 @@ def make_scene(kind, seed=1, n_tris=0, res=(512, 512), n_threads=0):
     cam = PtrsCamera()
     h = lib().ptrs_host_make_scene(kind, seed, n_tris, res[0], res[1], C.byref(cam), n_threads)
     return FlatScene(h), cam
+
+
+def import_scene(path, res=(640, 480), default_lights=False, sunsky_hdr=None, n_threads=0):
+    """common::importer::import (src/common/importer/mod.rs:6-25): Mitsuba .xml or glTF .gltf/.glb -> (FlatScene, camera).
+    `res` is the CLI's -r WxH (default 640x480, common/mod.rs:14)."""
+    cam = PtrsCamera()
+    h = lib().ptrs_host_import_scene(os.fsencode(path), res[0], res[1], 1 if default_lights else 0,
+                                     os.fsencode(sunsky_hdr) if sunsky_hdr else None, C.byref(cam), n_threads)
+    return FlatScene(h), cam
+
+
+def _img_check(rc):
+    if rc != 0:
+        raise RuntimeError(lib().ptrs_host_last_error().decode())
+
+
+def load_hdr(path):
+    """Radiance RGBE -> (h, w, 3) float32, as image::hdr::HdrDecoder::read_image_hdr gives it to light.rs:331-346."""
+    w, h = C.c_int(0), C.c_int(0)
+    _img_check(lib().ptrs_host_load_hdr(os.fsencode(path), C.byref(w), C.byref(h), None))
+    out = np.empty((h.value, w.value, 3), dtype=np.float32)
+    _img_check(lib().ptrs_host_load_hdr(os.fsencode(path), C.byref(w), C.byref(h), _fp(out)))
+    return out
+
+
+def save_hdr(path, rgb):
+    img = _f32(rgb)
+    _img_check(lib().ptrs_host_save_hdr(os.fsencode(path), _fp(img), img.shape[1], img.shape[0]))
+
+
+def load_png(path):
+    w, h, c = C.c_int(0), C.c_int(0), C.c_int(0)
+    _img_check(lib().ptrs_host_load_png(os.fsencode(path), C.byref(w), C.byref(h), C.byref(c), None))
+    out = np.empty((h.value, w.value, c.value), dtype=np.uint8)
+    _img_check(lib().ptrs_host_load_png(os.fsencode(path), C.byref(w), C.byref(h), C.byref(c), out.ctypes.data_as(C.POINTER(C.c_uint8))))
+    return out
+
+
+def save_png(path, pixels):
+    """film.to_rgba_image().save(path) (src/headless.rs:222, 231): (h, w, 1..4) uint8 -> PNG."""
+    img = np.ascontiguousarray(pixels, dtype=np.uint8)
+    if img.ndim == 2:
+        img = img[:, :, None]
+    _img_check(lib().ptrs_host_save_png(os.fsencode(path), img.ctypes.data_as(C.POINTER(C.c_uint8)), img.shape[1], img.shape[0], img.shape[2]))
+
+
+def tev_create_image(width, height, name="render"):
+    """TevControlCreateImage::new_message (src/headless.rs:84-100) as bytes."""
+    n = lib().ptrs_host_tev_create_image(width, height, name.encode(), None, 0)
+    buf = np.empty(n, dtype=np.uint8)
+    lib().ptrs_host_tev_create_image(width, height, name.encode(), buf.ctypes.data_as(C.POINTER(C.c_uint8)), n)
+    return buf.tobytes()
+
+
+def tev_update_image(channels, name="render"):
+    """TevControlUpdateImage::new_message (src/headless.rs:127-163): channels = (H, W, 3) resolved film ->
+    the concatenated 100 x 100-tile messages."""
+    img = _f32(channels)
+    h, w, _ = img.shape
+    planar = np.ascontiguousarray(np.moveaxis(img, 2, 0))
+    n = lib().ptrs_host_tev_update_image(_fp(planar), w, h, name.encode(), None, 0)
+    buf = np.empty(n, dtype=np.uint8)
+    lib().ptrs_host_tev_update_image(_fp(planar), w, h, name.encode(), buf.ctypes.data_as(C.POINTER(C.c_uint8)), n)
+    return buf.tobytes()
+
+
+def snake_case(name):
+    buf = C.create_string_buffer(4 * len(name) + 8)
+    n = lib().ptrs_host_snake_case(name.encode(), buf, len(buf))
+    return buf.value[:n].decode()
 
 
 def default_render_params(spp=1, max_depth=15):

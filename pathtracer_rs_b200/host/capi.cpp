@@ -5,8 +5,11 @@
 #include <stdexcept>
 #include <string>
 
+#include "image_io.hpp"
+#include "importers.hpp"
 #include "procedural.hpp"
 #include "scene_builder.hpp"
+#include "tev.hpp"
 
 using namespace ptrs_host;
 
@@ -155,6 +158,77 @@ void* ptrs_host_make_scene(int kind, uint64_t seed, uint64_t n_tris, int res_w, 
     return nullptr;
   }
   return box;
+}
+
+// ---- scene files (importers.hpp) and image files (image_io.hpp) ----------------------------------
+// common::importer::import(log, path, resolution, default_lights), src/common/importer/mod.rs:6-25
+void* ptrs_host_import_scene(const char* path, int res_w, int res_h, int default_lights, const char* sunsky_hdr, PtrsCamera* cam,
+                             int n_threads) {
+  SceneBox* box = nullptr;
+  if (guard([&] {
+        SceneBuilder b;
+        ImportOptions opt;
+        opt.res_w = res_w;
+        opt.res_h = res_h;
+        opt.default_lights = default_lights != 0;
+        if (sunsky_hdr) opt.sunsky_hdr = sunsky_hdr;
+        const PtrsCamera c = import_scene(path, opt, b);
+        if (cam) *cam = c;
+        box = new SceneBox();
+        box->fs = b.finalize(4, n_threads);
+        box->desc = box->fs.desc();
+      })) {
+    delete box;
+    return nullptr;
+  }
+  return box;
+}
+// two-call pattern: out == NULL returns the shape only
+int ptrs_host_load_hdr(const char* path, int* w, int* h, float* out_rgb) {
+  return guard([&] {
+    const ImageF32 img = load_hdr(path);
+    *w = img.width;
+    *h = img.height;
+    if (out_rgb) std::memcpy(out_rgb, img.data.data(), img.data.size() * 4);
+  });
+}
+int ptrs_host_save_hdr(const char* path, const float* rgb, int w, int h) {
+  return guard([&] { save_hdr(path, rgb, w, h); });
+}
+int ptrs_host_load_png(const char* path, int* w, int* h, int* channels, uint8_t* out) {
+  return guard([&] {
+    const ImageU8 img = load_png(path);
+    *w = img.width;
+    *h = img.height;
+    *channels = img.channels;
+    if (out) std::memcpy(out, img.data.data(), img.data.size());
+  });
+}
+int ptrs_host_save_png(const char* path, const uint8_t* pixels, int w, int h, int channels) {
+  return guard([&] { save_png(path, pixels, w, h, channels); });
+}
+int ptrs_host_snake_case(const char* in, char* out, int cap) {
+  const std::string s = snake_case(in);
+  if ((int)s.size() + 1 > cap) return -1;
+  std::memcpy(out, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}
+
+// tev wire messages (tev.hpp); returns the byte count, copies when `out` has room
+int64_t ptrs_host_tev_create_image(int w, int h, const char* name, uint8_t* out, int64_t cap) {
+  const std::vector<uint8_t> m = tev_create_image(w, h, name);
+  if (out && (int64_t)m.size() <= cap) std::memcpy(out, m.data(), m.size());
+  return (int64_t)m.size();
+}
+// all UpdateImage messages of one film, concatenated in sending order
+int64_t ptrs_host_tev_update_image(const float* rgb_planar, int w, int h, const char* name, uint8_t* out, int64_t cap) {
+  const float* ch[3] = {rgb_planar, rgb_planar + (size_t)w * h, rgb_planar + 2 * (size_t)w * h};
+  int64_t total = 0;
+  for (const auto& m : tev_update_image(ch, w, h, name)) {
+    if (out && total + (int64_t)m.size() <= cap) std::memcpy(out + total, m.data(), m.size());
+    total += (int64_t)m.size();
+  }
+  return total;
 }
 
 void ptrs_host_synth_sky(int w, int h, uint64_t seed, float* out) {

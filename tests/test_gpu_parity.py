@@ -7,6 +7,8 @@ Parity protocol (BASELINE.json north_star / SURVEY.md §8c):
   * node / triangle test counts equal the oracle's (same traversal order)
   * per-path radiance and converged images: relative MSE < 1e-3 (device libm differs from glibc by ulps)
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -202,4 +204,27 @@ def test_error_behaviour(gpu, host, cornell):
     bad = gpu.Film(cam.width + 1, cam.height)
     with pytest.raises(gpu.PtrsError):
         gpu.PathIntegrator(gpu.SamplerBuilder(4)).render(cam, scene, bad)
+    scene.close()
+
+
+def test_headless_cli_renders_the_xml_scene(gpu, host, tmp_path):
+    """examples/headless (the stand-in for `pathtracer-rs SCENE -o out --headless -r WxH -s N -d D`, src/main.rs) on the
+    Cornell XML fixture == the same render through the Python mirror of the interface, byte for byte."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "headless")
+    assert os.path.exists(exe), "examples/headless missing: __graft_entry__.build() builds it"
+    xml = os.path.join(root, "tests", "golden", "cornell-box.xml")
+    r = subprocess.run([exe, xml, "-o", str(tmp_path), "--headless", "-r", "96x80", "-s", "8", "-d", "6", "--server", "127.0.0.1:1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    png = host.load_png(str(tmp_path / "render.png"))
+    flat, cam = host.import_scene(xml, res=(96, 80))
+    scene = gpu.RenderScene(flat)
+    integ = gpu.PathIntegrator(gpu.SamplerBuilder(8), max_depth=6)
+    film = gpu.Film(cam.width, cam.height)
+    integ.render(cam, scene, film)
+    assert png.shape == (80, 96, 4)
+    assert np.array_equal(png, film.to_rgba_image())
     scene.close()

@@ -300,6 +300,19 @@ int32_t ptrs_set_device(int32_t device); /* device used by handles created after
 
 /* RenderScene construction / teardown (replaces holding Box<BVH> + lights in RenderScene) */
 int32_t ptrs_scene_create(const PtrsSceneDesc* desc, PtrsScene** out);
+/* Same, but the accelerator is built on the device (replaces the host-side BVH::new, accelerator.rs:103-346, when
+ * start-up time matters: a linear BVH, leaves of at most 4 primitives).  desc->nodes / n_nodes are ignored and the
+ * primitive arrays may be in any order; PtrsLight.prim and the prim ids reported by ptrs_intersect* refer to the
+ * caller's order.  Closest hits (t, barycentrics) are those of ptrs_scene_create on the same geometry; only the
+ * traversal cost and the winner among hits within an ulp of each other can differ (the reference's traversal
+ * resolves those by visit order). */
+int32_t ptrs_scene_create_device_bvh(const PtrsSceneDesc* desc, PtrsScene** out);
+/* node count of the device-side tree (either constructor) and the device build time (0 for a host-built BVH) */
+int32_t ptrs_scene_bvh_info(const PtrsScene* scene, uint32_t* n_nodes, float* device_build_ms);
+/* The device-side tree for inspection: 32-byte LinearBVHNode records in the traversal layout (root in slot 0, slot 1
+ * unused, the two children of an interior node at offset and offset + 1); prim_order (optional, device-built trees
+ * only) maps BVH primitive positions to the caller's primitive indices. */
+int32_t ptrs_scene_download_nodes(const PtrsScene* scene, PtrsBvhNode* nodes, uint32_t capacity, uint32_t* prim_order);
 int32_t ptrs_scene_destroy(PtrsScene* scene);
 int32_t ptrs_scene_world_bound(const PtrsScene* scene, float out_min_max[6]); /* mod.rs:100-102 */
 uint64_t ptrs_scene_device_bytes(const PtrsScene* scene);

@@ -1,0 +1,378 @@
+// BVH construction on the device: replaces the host's recursive SAH build
+// (src/pathtracer/accelerator.rs:103-346) when the caller hands over unordered primitives.
+//
+// Linear BVH: 63-bit Morton codes of the primitive centroids -> radix sort -> Karras' binary radix tree built
+// in parallel (one thread per internal node) -> bottom-up bounds with one atomic per node -> subtrees of at most
+// 4 primitives collapse into leaves (the reference's max_prims_in_node) -> emission into the traversal layout of
+// dev_accel.cuh: 32-byte LinearBVHNode records, the two children of an interior node side by side (64-byte
+// pairs), pairs numbered depth-first so a subtree is contiguous in memory.  `axis` is the axis along which the
+// two children's box centres differ most and the first child is the lower one, which is what the traversal's
+// near-child rule dir_is_neg[axis] (accelerator.rs:393-404) assumes.
+//
+// Every kernel is a streaming pass over HBM-resident arrays (24-68 B per primitive); the sort is
+// cub::DeviceRadixSort (library code, like cuBLAS for a plain GEMM).  The tree differs from the reference's SAH
+// tree, so visit counts differ, but closest hits do not: the triangle test is the same code on the same vertices.
+#include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "launch.hpp"
+#include "wavefront.cuh"
+
+namespace ptrs {
+
+namespace {
+
+// order-preserving float <-> uint map for atomicMin / atomicMax on floats
+__device__ __forceinline__ uint32_t f2o(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float o2f(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
+
+struct BuildArrays {
+  // per primitive, caller order
+  float4* pb_min;  // xyz = bounds min, w unused
+  float4* pb_max;
+  // per primitive, sorted order
+  uint64_t* keys;
+  uint32_t* perm;  // sorted position -> caller's primitive index
+  // radix tree: internal nodes [0, n-1), leaves are addressed as (n - 1 + sorted position)
+  uint32_t* parent;     // 2n - 1
+  uint32_t* left;       // n - 1
+  uint32_t* right;      // n - 1
+  uint32_t* first;      // n - 1: sorted range covered
+  uint32_t* last;       // n - 1
+  float4* nb_min;       // 2n - 1
+  float4* nb_max;       // 2n - 1
+  uint32_t* arrivals;   // n - 1
+  uint32_t* n_interior;  // n - 1: emitted interior nodes in the subtree (0 when the subtree collapses into a leaf)
+  uint32_t* cbounds;    // 6 ordered uints: centroid bounds
+};
+
+__global__ void __launch_bounds__(256) prim_bounds_kernel(const uint32_t* __restrict__ prim_vertex, const float* __restrict__ pos, uint32_t n, BuildArrays A) {
+  float cmin[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, cmax[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float mn[3], mx[3];
+    for (int k = 0; k < 3; ++k) {
+      const uint32_t v = prim_vertex[3 * (size_t)i + k];
+      for (int a = 0; a < 3; ++a) {
+        const float x = __ldg(pos + 3 * (size_t)v + a);
+        mn[a] = k == 0 ? x : fminf(mn[a], x);
+        mx[a] = k == 0 ? x : fmaxf(mx[a], x);
+      }
+    }
+    A.pb_min[i] = make_float4(mn[0], mn[1], mn[2], 0.f);
+    A.pb_max[i] = make_float4(mx[0], mx[1], mx[2], 0.f);
+    for (int a = 0; a < 3; ++a) {
+      const float c = 0.5f * mn[a] + 0.5f * mx[a];
+      cmin[a] = fminf(cmin[a], c);
+      cmax[a] = fmaxf(cmax[a], c);
+    }
+  }
+  for (int a = 0; a < 3; ++a) {
+    for (int o = 16; o > 0; o >>= 1) {
+      cmin[a] = fminf(cmin[a], __shfl_xor_sync(0xffffffffu, cmin[a], o));
+      cmax[a] = fmaxf(cmax[a], __shfl_xor_sync(0xffffffffu, cmax[a], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&A.cbounds[a], f2o(cmin[a]));
+      atomicMax(&A.cbounds[3 + a], f2o(cmax[a]));
+    }
+  }
+}
+
+__device__ __forceinline__ uint64_t spread21(uint64_t x) {  // 21 bits -> every third bit
+  x &= 0x1fffffull;
+  x = (x | (x << 32)) & 0x1f00000000ffffull;
+  x = (x | (x << 16)) & 0x1f0000ff0000ffull;
+  x = (x | (x << 8)) & 0x100f00f00f00f00full;
+  x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
+  x = (x | (x << 2)) & 0x1249249249249249ull;
+  return x;
+}
+
+__global__ void __launch_bounds__(256) morton_kernel(uint32_t n, BuildArrays A) {
+  float lo[3], inv[3];
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = o2f(A.cbounds[a]);
+    const float ext = o2f(A.cbounds[3 + a]) - lo[a];
+    inv[a] = ext > 0.f ? 2097152.0f / ext : 0.f;  // 2^21 cells per axis
+  }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 mn = A.pb_min[i], mx = A.pb_max[i];
+    const float c[3] = {0.5f * mn.x + 0.5f * mx.x, 0.5f * mn.y + 0.5f * mx.y, 0.5f * mn.z + 0.5f * mx.z};
+    uint64_t q[3];
+    for (int a = 0; a < 3; ++a) q[a] = (uint64_t)fminf(fmaxf((c[a] - lo[a]) * inv[a], 0.f), 2097151.0f);
+    A.keys[i] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+    A.perm[i] = i;
+  }
+}
+
+// common-prefix length of sorted keys i and j, ties broken by position (Karras 2012, section 4)
+__device__ __forceinline__ int prefix_len(const uint64_t* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  const uint64_t a = keys[i], b = keys[j];
+  return a == b ? 64 + __clz((uint32_t)i ^ (uint32_t)j) : __clzll((long long)(a ^ b));
+}
+
+__global__ void __launch_bounds__(256) radix_tree_kernel(const uint64_t* __restrict__ keys, int n, BuildArrays A) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n - 1; i += gridDim.x * blockDim.x) {
+    const int d = prefix_len(keys, n, i, i + 1) - prefix_len(keys, n, i, i - 1) >= 0 ? 1 : -1;
+    const int dmin = prefix_len(keys, n, i, i - d);
+    int lmax = 2;
+    while (prefix_len(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+      if (prefix_len(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = prefix_len(keys, n, i, j);
+    int s = 0, t = l;
+    do {
+      t = (t + 1) >> 1;
+      if (prefix_len(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const uint32_t lc = lo == gamma ? (uint32_t)(n - 1 + gamma) : (uint32_t)gamma;
+    const uint32_t rc = hi == gamma + 1 ? (uint32_t)(n - 1 + gamma + 1) : (uint32_t)(gamma + 1);
+    A.left[i] = lc;
+    A.right[i] = rc;
+    A.first[i] = (uint32_t)lo;
+    A.last[i] = (uint32_t)hi;
+    A.parent[lc] = (uint32_t)i;
+    A.parent[rc] = (uint32_t)i;
+    if (i == 0) A.parent[0] = 0xffffffffu;
+  }
+}
+
+#define PT_BVH_MAX_LEAF 4u  // BVH::new(.., &4), importer/mitsuba.rs:362
+
+__global__ void __launch_bounds__(256) refit_kernel(uint32_t n, BuildArrays A) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const uint32_t prim = A.perm[j];
+    uint32_t node = n - 1 + j;
+    float4 mn = A.pb_min[prim], mx = A.pb_max[prim];
+    A.nb_min[node] = mn;
+    A.nb_max[node] = mx;
+    if (n == 1) return;
+    for (;;) {
+      const uint32_t p = A.parent[node];
+      if (p == 0xffffffffu) break;
+      __threadfence();
+      if (atomicAdd(&A.arrivals[p], 1u) == 0u) break;  // the sibling subtree is not finished: its thread continues
+      __threadfence();
+      const uint32_t l = A.left[p], r = A.right[p];
+      const uint32_t other = l == node ? r : l;
+      const float4 omn = __ldcg(A.nb_min + other), omx = __ldcg(A.nb_max + other);
+      mn = make_float4(fminf(mn.x, omn.x), fminf(mn.y, omn.y), fminf(mn.z, omn.z), 0.f);
+      mx = make_float4(fmaxf(mx.x, omx.x), fmaxf(mx.y, omx.y), fmaxf(mx.z, omx.z), 0.f);
+      A.nb_min[p] = mn;
+      A.nb_max[p] = mx;
+      uint32_t ni = 0;
+      if (A.last[p] - A.first[p] + 1u > PT_BVH_MAX_LEAF) {
+        ni = 1u;
+        if (l < n - 1) ni += __ldcg(A.n_interior + l);
+        if (r < n - 1) ni += __ldcg(A.n_interior + r);
+      }
+      A.n_interior[p] = ni;
+      node = p;
+    }
+  }
+}
+
+struct NodeRec {  // the reference's LinearBVHNode (accelerator.rs:83-95) as two float4
+  float4 a, b;
+};
+__device__ __forceinline__ NodeRec make_node(float4 mn, float4 mx, uint32_t offset, uint32_t n_prims, uint32_t axis) {
+  NodeRec r;
+  r.a = make_float4(mn.x, mn.y, mn.z, mx.x);
+  r.b = make_float4(mx.y, mx.z, __uint_as_float(offset), __uint_as_float((n_prims & 0xffffu) | (axis << 16)));
+  return r;
+}
+
+// one thread per emitted interior node: depth-first pair number from the path to the root, then the two child records
+__global__ void __launch_bounds__(256) emit_kernel(uint32_t n, BuildArrays A, float4* __restrict__ nodes) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n - 1; i += gridDim.x * blockDim.x) {
+    if (A.n_interior[i] == 0) continue;
+    uint32_t pair = 1;
+    for (uint32_t c = i; c != 0;) {
+      const uint32_t p = A.parent[c];
+      pair += 1;
+      if (A.right[p] == c) {
+        const uint32_t l = A.left[p];
+        if (l < n - 1) pair += A.n_interior[l];
+      }
+      c = p;
+    }
+    const uint32_t l = A.left[i], r = A.right[i];
+    const uint32_t l_int = l < n - 1 ? A.n_interior[l] : 0u, r_int = r < n - 1 ? A.n_interior[r] : 0u;
+    const float4 lmn = A.nb_min[l], lmx = A.nb_max[l], rmn = A.nb_min[r], rmx = A.nb_max[r];
+    // split axis: where the children's box centres differ most; the lower child goes first
+    const float dc[3] = {(rmn.x + rmx.x) - (lmn.x + lmx.x), (rmn.y + rmx.y) - (lmn.y + lmx.y), (rmn.z + rmx.z) - (lmn.z + lmx.z)};
+    uint32_t axis = 0;
+    if (fabsf(dc[1]) > fabsf(dc[axis])) axis = 1;
+    if (fabsf(dc[2]) > fabsf(dc[axis])) axis = 2;
+    const bool swap = dc[axis] < 0.f;
+    auto child = [&](uint32_t c, uint32_t c_int, uint32_t c_pair, float4 mn, float4 mx) {
+      if (c_int) {
+        const float4 gmn_l = A.nb_min[A.left[c]], gmx_l = A.nb_max[A.left[c]], gmn_r = A.nb_min[A.right[c]], gmx_r = A.nb_max[A.right[c]];
+        const float g[3] = {(gmn_r.x + gmx_r.x) - (gmn_l.x + gmx_l.x), (gmn_r.y + gmx_r.y) - (gmn_l.y + gmx_l.y), (gmn_r.z + gmx_r.z) - (gmn_l.z + gmx_l.z)};
+        uint32_t ax = 0;
+        if (fabsf(g[1]) > fabsf(g[ax])) ax = 1;
+        if (fabsf(g[2]) > fabsf(g[ax])) ax = 2;
+        return make_node(mn, mx, 2u * c_pair, 0u, ax);
+      }
+      const uint32_t f = c < n - 1 ? A.first[c] : c - (n - 1);
+      const uint32_t cnt = c < n - 1 ? A.last[c] - A.first[c] + 1u : 1u;
+      return make_node(mn, mx, f, cnt, 0u);
+    };
+    const NodeRec ln = child(l, l_int, pair + 1, lmn, lmx), rn = child(r, r_int, pair + 1 + l_int, rmn, rmx);
+    const NodeRec first = swap ? rn : ln, second = swap ? ln : rn;
+    nodes[4 * (size_t)pair] = first.a;
+    nodes[4 * (size_t)pair + 1] = first.b;
+    nodes[4 * (size_t)pair + 2] = second.a;
+    nodes[4 * (size_t)pair + 3] = second.b;
+    if (i == 0) {
+      const NodeRec root = make_node(A.nb_min[0], A.nb_max[0], 2u, 0u, axis);
+      nodes[0] = root.a;
+      nodes[1] = root.b;
+      nodes[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+      nodes[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// scene of at most PT_BVH_MAX_LEAF primitives: the root is the only node, a leaf
+__global__ void single_leaf_kernel(uint32_t n, BuildArrays A, float4* __restrict__ nodes) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  float4 mn = A.pb_min[0], mx = A.pb_max[0];
+  for (uint32_t i = 1; i < n; ++i) {
+    const float4 a = A.pb_min[i], b = A.pb_max[i];
+    mn = make_float4(fminf(mn.x, a.x), fminf(mn.y, a.y), fminf(mn.z, a.z), 0.f);
+    mx = make_float4(fmaxf(mx.x, b.x), fmaxf(mx.y, b.y), fmaxf(mx.z, b.z), 0.f);
+  }
+  const NodeRec root = make_node(mn, mx, 0u, n, 0u);
+  nodes[0] = root.a;
+  nodes[1] = root.b;
+  nodes[2] = nodes[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// triangles in BVH order: the same 3 x float4 (+ metadata in .w) and index records ptrs_scene_create lays out on the host
+__global__ void __launch_bounds__(256) assemble_tris_kernel(uint32_t n, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ prim_vertex,
+                                                            const float* __restrict__ pos, const int32_t* __restrict__ prim_mesh,
+                                                            const int32_t* __restrict__ prim_material, const int32_t* __restrict__ prim_area_light,
+                                                            const PtrsMesh* __restrict__ meshes, float4* __restrict__ tri_verts, uint4* __restrict__ tri_index,
+                                                            uint32_t* __restrict__ inv_perm) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint32_t i = perm[k];
+    inv_perm[i] = k;
+    const int32_t mesh = prim_mesh[i];
+    const PtrsMesh m = meshes[mesh];
+    uint32_t meta2 = m.flags & 0xffu;
+    if (m.alpha_tex >= 0) meta2 |= PT_TRI_ALPHA_BIT | ((uint32_t)m.alpha_tex << 9);
+    const int32_t w[3] = {prim_material[i], prim_area_light[i], (int32_t)meta2};
+    uint32_t v[3];
+    for (int c = 0; c < 3; ++c) {
+      v[c] = prim_vertex[3 * (size_t)i + c];
+      tri_verts[3 * (size_t)k + c] = make_float4(__ldg(pos + 3 * (size_t)v[c]), __ldg(pos + 3 * (size_t)v[c] + 1), __ldg(pos + 3 * (size_t)v[c] + 2), __int_as_float(w[c]));
+    }
+    tri_index[k] = make_uint4(v[0], v[1], v[2], (uint32_t)mesh);
+  }
+}
+
+__global__ void remap_light_prims_kernel(PtrsLight* lights, uint32_t n_lights, const uint32_t* __restrict__ inv_perm) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_lights && lights[i].type == PTRS_LIGHT_AREA) lights[i].prim = (int32_t)inv_perm[lights[i].prim];
+}
+
+template <class T>
+cudaError_t dev_alloc(T** p, size_t count, cudaStream_t st) {
+  return cudaMallocAsync(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T), st);
+}
+
+}  // namespace
+
+// Builds the BVH over n primitives given as device arrays in the caller's order.  On success *nodes_out holds
+// *n_nodes_out 32-byte records (as float4 pairs) and *perm_out the primitive order (BVH position -> caller index);
+// both are stream-ordered allocations the caller frees with cudaFreeAsync.  Returns a cudaError_t.
+int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vertex, const float* d_pos, float4** nodes_out, uint32_t* n_nodes_out,
+                        uint32_t** perm_out) {
+  *nodes_out = nullptr;
+  *perm_out = nullptr;
+  *n_nodes_out = 0;
+  if (n == 0) return cudaSuccess;
+  BuildArrays A{};
+  uint64_t* keys_sorted = nullptr;
+  uint32_t* perm_sorted = nullptr;
+  void* sort_tmp = nullptr;
+  float4* nodes = nullptr;
+  cudaError_t e = cudaSuccess;
+  auto ok = [&](cudaError_t r) {
+    if (e == cudaSuccess && r != cudaSuccess) e = r;
+    return e == cudaSuccess;
+  };
+  const size_t n_int = n > 1 ? n - 1 : 0;
+  ok(dev_alloc(&A.pb_min, n, st)) && ok(dev_alloc(&A.pb_max, n, st)) && ok(dev_alloc(&A.keys, n, st)) && ok(dev_alloc(&A.perm, n, st)) &&
+      ok(dev_alloc(&keys_sorted, n, st)) && ok(dev_alloc(&perm_sorted, n, st)) && ok(dev_alloc(&A.parent, 2 * (size_t)n, st)) &&
+      ok(dev_alloc(&A.left, n_int, st)) && ok(dev_alloc(&A.right, n_int, st)) && ok(dev_alloc(&A.first, n_int, st)) && ok(dev_alloc(&A.last, n_int, st)) &&
+      ok(dev_alloc(&A.nb_min, 2 * (size_t)n, st)) && ok(dev_alloc(&A.nb_max, 2 * (size_t)n, st)) && ok(dev_alloc(&A.arrivals, n_int, st)) &&
+      ok(dev_alloc(&A.n_interior, n_int, st)) && ok(dev_alloc(&A.cbounds, 6, st));
+  const int grid = 148 * 8;
+  uint32_t n_interior_root = 0;
+  if (e == cudaSuccess) {
+    const uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    ok(cudaMemcpyAsync(A.cbounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    ok(cudaMemsetAsync(A.arrivals, 0, std::max<size_t>(n_int, 1) * 4, st));
+    ok(cudaMemsetAsync(A.n_interior, 0, std::max<size_t>(n_int, 1) * 4, st));
+    prim_bounds_kernel<<<grid, 256, 0, st>>>(d_prim_vertex, d_pos, n, A);
+    morton_kernel<<<grid, 256, 0, st>>>(n, A);
+    size_t tmp_bytes = 0;
+    ok(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, A.keys, keys_sorted, A.perm, perm_sorted, (int)n, 0, 63, st));
+    ok(cudaMallocAsync(&sort_tmp, std::max<size_t>(tmp_bytes, 16), st));
+    if (e == cudaSuccess) ok(cub::DeviceRadixSort::SortPairs(sort_tmp, tmp_bytes, A.keys, keys_sorted, A.perm, perm_sorted, (int)n, 0, 63, st));
+    std::swap(A.perm, perm_sorted);
+    std::swap(A.keys, keys_sorted);
+    if (n > 1) {
+      radix_tree_kernel<<<grid, 256, 0, st>>>(A.keys, (int)n, A);
+      refit_kernel<<<grid, 256, 0, st>>>(n, A);
+      ok(cudaMemcpyAsync(&n_interior_root, A.n_interior, 4, cudaMemcpyDeviceToHost, st));
+    }
+    ok(cudaStreamSynchronize(st));
+    ok(cudaGetLastError());
+  }
+  if (e == cudaSuccess) {
+    const uint32_t n_nodes = 2u + 2u * n_interior_root;
+    ok(dev_alloc(&nodes, 2 * (size_t)n_nodes, st));
+    if (e == cudaSuccess) {
+      if (n_interior_root == 0) single_leaf_kernel<<<1, 32, 0, st>>>(n, A, nodes);
+      else emit_kernel<<<grid, 256, 0, st>>>(n, A, nodes);
+      ok(cudaGetLastError());
+      *n_nodes_out = n_nodes;
+    }
+  }
+  void* scratch[] = {A.pb_min, A.pb_max, A.keys, keys_sorted, perm_sorted, A.parent, A.left, A.right, A.first, A.last, A.nb_min, A.nb_max,
+                     A.arrivals, A.n_interior, A.cbounds, sort_tmp};
+  for (void* p : scratch)
+    if (p) cudaFreeAsync(p, st);
+  if (e != cudaSuccess) {
+    if (nodes) cudaFreeAsync(nodes, st);
+    if (A.perm) cudaFreeAsync(A.perm, st);
+    return (int)e;
+  }
+  *nodes_out = nodes;
+  *perm_out = A.perm;
+  return (int)cudaSuccess;
+}
+
+void launch_assemble_tris(cudaStream_t st, uint32_t n, const uint32_t* perm, const uint32_t* prim_vertex, const float* pos, const int32_t* prim_mesh,
+                          const int32_t* prim_material, const int32_t* prim_area_light, const PtrsMesh* meshes, float4* tri_verts, uint4* tri_index,
+                          uint32_t* inv_perm) {
+  if (n == 0) return;
+  assemble_tris_kernel<<<148 * 8, 256, 0, st>>>(n, perm, prim_vertex, pos, prim_mesh, prim_material, prim_area_light, meshes, tri_verts, tri_index, inv_perm);
+}
+void launch_remap_light_prims(cudaStream_t st, PtrsLight* lights, uint32_t n_lights, const uint32_t* inv_perm) {
+  if (n_lights == 0) return;
+  remap_light_prims_kernel<<<(n_lights + 127) / 128, 128, 0, st>>>(lights, n_lights, inv_perm);
+}
+
+}  // namespace ptrs

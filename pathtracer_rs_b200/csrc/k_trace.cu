@@ -119,6 +119,7 @@ struct IntersectWork {
   PtrsHit* __restrict__ hits;
   uint8_t* __restrict__ occluded;
   bool any_hit;
+  const uint32_t* __restrict__ prim_map;  // BVH position -> caller's primitive index (device-built BVH), or null
   __device__ bool begin(uint32_t i, LaneRay* r) {
     const float* q = (const float*)(rays + i);
     r->o = mk3(__ldg(q), __ldg(q + 1), __ldg(q + 2));
@@ -132,7 +133,7 @@ struct IntersectWork {
       occluded[i] = found ? 1 : 0;
     } else {
       PtrsHit out;
-      out.prim = found ? h.prim : -1;
+      out.prim = found ? (prim_map ? (int)__ldg(prim_map + h.prim) : h.prim) : -1;
       out.t = found ? h.t : 0.f;
       out.b0 = h.b0;
       out.b1 = h.b1;
@@ -145,9 +146,9 @@ struct IntersectWork {
 
 template <bool ANY_HIT, bool COUNT>
 __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) intersect_kernel(const __grid_constant__ DevScene sc, const PtrsRay* __restrict__ rays, uint32_t n, PtrsHit* __restrict__ hits,
-                                                         uint8_t* __restrict__ occluded, uint32_t* ticket, GlobalCounters* g) {
+                                                         uint8_t* __restrict__ occluded, uint32_t* ticket, GlobalCounters* g, const uint32_t* __restrict__ prim_map) {
   uint32_t c_nodes = 0, c_tris = 0;
-  IntersectWork w{rays, hits, occluded, ANY_HIT};
+  IntersectWork w{rays, hits, occluded, ANY_HIT, prim_map};
   trace_stream<COUNT>(sc, n, ticket, w, &c_nodes, &c_tris);
   if (COUNT) {
     warp_sum_add(c_nodes, &g->nodes_tested);
@@ -176,7 +177,7 @@ void launch_connect(cudaStream_t st, int sm, bool count, const DevScene& sc, con
   else connect_kernel<false><<<grid[0], 128, 0, st>>>(sc, P, ctr, g);
 }
 void launch_intersect(cudaStream_t st, int sm, bool any_hit, bool count, const DevScene& sc, const PtrsRay* rays, uint32_t n, PtrsHit* hits,
-                      uint8_t* occluded, uint32_t* ticket, GlobalCounters* g) {
+                      uint8_t* occluded, uint32_t* ticket, GlobalCounters* g, const uint32_t* prim_map) {
   static int grid[4] = {0, 0, 0, 0};
   if (!grid[0]) {
     grid[0] = persistent_grid(intersect_kernel<false, false>, 128, sm);
@@ -184,10 +185,10 @@ void launch_intersect(cudaStream_t st, int sm, bool any_hit, bool count, const D
     grid[2] = persistent_grid(intersect_kernel<true, false>, 128, sm);
     grid[3] = persistent_grid(intersect_kernel<true, true>, 128, sm);
   }
-  if (!any_hit && !count) intersect_kernel<false, false><<<grid[0], 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g);
-  else if (!any_hit) intersect_kernel<false, true><<<grid[1], 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g);
-  else if (!count) intersect_kernel<true, false><<<grid[2], 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g);
-  else intersect_kernel<true, true><<<grid[3], 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g);
+  if (!any_hit && !count) intersect_kernel<false, false><<<grid[0], 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map);
+  else if (!any_hit) intersect_kernel<false, true><<<grid[1], 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map);
+  else if (!count) intersect_kernel<true, false><<<grid[2], 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map);
+  else intersect_kernel<true, true><<<grid[3], 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map);
 }
 
 }  // namespace ptrs

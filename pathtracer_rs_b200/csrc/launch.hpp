@@ -32,7 +32,15 @@ void launch_extend(cudaStream_t st, int sm, bool count, const DevScene& sc, cons
                    RoundCounters* ctr, GlobalCounters* g);
 void launch_connect(cudaStream_t st, int sm, bool count, const DevScene& sc, const PathArrays& P, RoundCounters* ctr, GlobalCounters* g);
 void launch_intersect(cudaStream_t st, int sm, bool any_hit, bool count, const DevScene& sc, const PtrsRay* rays, uint32_t n, PtrsHit* hits,
-                      uint8_t* occluded, uint32_t* ticket, GlobalCounters* g);
+                      uint8_t* occluded, uint32_t* ticket, GlobalCounters* g, const uint32_t* prim_map);
+
+// k_bvh.cu
+int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vertex, const float* d_pos, float4** nodes_out, uint32_t* n_nodes_out,
+                        uint32_t** perm_out);
+void launch_assemble_tris(cudaStream_t st, uint32_t n, const uint32_t* perm, const uint32_t* prim_vertex, const float* pos, const int32_t* prim_mesh,
+                          const int32_t* prim_material, const int32_t* prim_area_light, const PtrsMesh* meshes, float4* tri_verts, uint4* tri_index,
+                          uint32_t* inv_perm);
+void launch_remap_light_prims(cudaStream_t st, PtrsLight* lights, uint32_t n_lights, const uint32_t* inv_perm);
 
 // k_shade.cu, built once per PtrsMaterialType
 #define PT_DECL_SHADE(M)                                                                                                              \

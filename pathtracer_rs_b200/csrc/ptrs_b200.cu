@@ -143,6 +143,9 @@ struct PtrsScene {
   DevScene dev{};
   DevBuf<float4> nodes, tri_verts;
   DevBuf<uint4> tri_index;
+  DevBuf<uint32_t> prim_map;  // device-built BVH: BVH position -> caller's primitive index
+  float bvh_build_ms = 0.f;
+  uint32_t n_dev_nodes = 0;
   DevBuf<float> normal, tangent, uv, texels;
   DevBuf<PtrsMesh> meshes;
   DevBuf<PtrsMaterial> materials;
@@ -450,10 +453,10 @@ int32_t ptrs_set_device(int32_t device) {
   return PTRS_OK;
 }
 
-int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) {
+static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsScene** out) {
   if (!d || !out) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
   if (d->abi_version != PTRS_ABI_VERSION) return fail(PTRS_ERR_INVALID_ARGUMENT, "PtrsSceneDesc.abi_version mismatch");
-  if (d->n_prims > 0 && (!d->nodes || !d->prim_vertex || !d->prim_mesh || !d->prim_material || !d->prim_area_light || !d->pos || !d->meshes))
+  if (d->n_prims > 0 && ((!device_bvh && !d->nodes) || !d->prim_vertex || !d->prim_mesh || !d->prim_material || !d->prim_area_light || !d->pos || !d->meshes))
     return fail(PTRS_ERR_INVALID_ARGUMENT, "missing geometry arrays");
   const SobolHost& sh = sobol_host();
   if (!sh.ok) return fail(PTRS_ERR_INVALID_ARGUMENT, "embedded Sobol tables are corrupt");
@@ -470,7 +473,7 @@ int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) {
     for (int k = 0; k < 3; ++k)
       if (d->prim_vertex[3 * (size_t)i + k] >= d->n_verts) return fail(PTRS_ERR_INVALID_ARGUMENT, "vertex index out of range");
   }
-  for (uint32_t i = 0; i < d->n_nodes; ++i) {
+  for (uint32_t i = 0; !device_bvh && i < d->n_nodes; ++i) {
     const PtrsBvhNode& n = d->nodes[i];
     if (n.n_prims > 0 ? (uint64_t)n.offset + n.n_prims > d->n_prims : (n.offset >= d->n_nodes || i + 1 >= d->n_nodes || n.axis > 2))
       return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH node");
@@ -495,10 +498,63 @@ int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) {
     if (l.type == PTRS_LIGHT_INFINITE && (l.env < 0 || (uint32_t)l.env >= d->n_envs)) return fail(PTRS_ERR_INVALID_ARGUMENT, "env id out of range");
   }
 
+  for (uint32_t i = 0; i < d->n_meshes; ++i) {
+    const uint32_t f = d->meshes[i].flags;
+    if (((f & PTRS_MESH_HAS_NORMAL) && !d->normal) || ((f & PTRS_MESH_HAS_TANGENT) && !d->tangent) || ((f & PTRS_MESH_HAS_UV) && !d->uv))
+      return fail(PTRS_ERR_INVALID_ARGUMENT, "mesh flags name an attribute pool that is NULL");
+  }
+  CUDA_TRY(s->meshes.upload(d->meshes, d->n_meshes));
+  CUDA_TRY(s->lights.upload(d->lights, d->n_lights));
+  uint32_t n_dev_nodes = d->n_nodes;
+  if (device_bvh) {
+    // unordered primitives in, BVH built and triangles laid out on the device (k_bvh.cu)
+    DevBuf<uint32_t> pv, inv;
+    DevBuf<float> pos;
+    DevBuf<int32_t> pm, pmat, pal;
+    CUDA_TRY(pv.upload(d->prim_vertex, (size_t)d->n_prims * 3));
+    CUDA_TRY(pos.upload(d->pos, (size_t)d->n_verts * 3));
+    CUDA_TRY(pm.upload(d->prim_mesh, d->n_prims));
+    CUDA_TRY(pmat.upload(d->prim_material, d->n_prims));
+    CUDA_TRY(pal.upload(d->prim_area_light, d->n_prims));
+    CUDA_TRY(inv.alloc(d->n_prims));
+    CUDA_TRY(s->tri_verts.alloc((size_t)d->n_prims * 3));
+    CUDA_TRY(s->tri_index.alloc(d->n_prims));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0, 0));
+    float4* nodes = nullptr;
+    uint32_t* perm = nullptr;
+    const int be = build_bvh_on_device(0, d->n_prims, pv.p, pos.p, &nodes, &n_dev_nodes, &perm);
+    if (be != (int)cudaSuccess) return fail(PTRS_ERR_CUDA, std::string("device BVH build: ") + cudaGetErrorString((cudaError_t)be));
+    s->nodes.p = nodes;
+    s->nodes.n = (size_t)n_dev_nodes * 2;
+    s->prim_map.p = perm;
+    s->prim_map.n = d->n_prims;
+    launch_assemble_tris(0, d->n_prims, perm, pv.p, pos.p, pm.p, pmat.p, pal.p, s->meshes.p, s->tri_verts.p, s->tri_index.p, inv.p);
+    launch_remap_light_prims(0, s->lights.p, d->n_lights, inv.p);
+    CUDA_TRY(cudaEventRecord(e1, 0));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    CUDA_TRY(cudaGetLastError());
+    cudaEventElapsedTime(&s->bvh_build_ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    s->scene_bytes += (uint64_t)n_dev_nodes * 32 + (uint64_t)d->n_prims * 4;
+    if (n_dev_nodes > 0) {
+      float root[8];
+      CUDA_TRY(cudaMemcpy(root, s->nodes.p, 32, cudaMemcpyDeviceToHost));
+      s->world_bound[0] = root[0];
+      s->world_bound[1] = root[1];
+      s->world_bound[2] = root[2];
+      s->world_bound[3] = root[3];
+      s->world_bound[4] = root[4];
+      s->world_bound[5] = root[5];
+    }
+  }
   // re-layout: the 32 B node records are kept, but the two children of every interior node are placed side
   // by side (64 B pairs in depth-first order, root alone in slot 0) so that one traversal step reads one
   // contiguous 64 B block; triangles become 3 x float4 with metadata in .w
-  {
+  if (!device_bvh) {
     std::vector<PtrsBvhNode> dev_nodes;
     if (d->n_nodes > 0) {
       dev_nodes.reserve(2 * (size_t)d->n_nodes);
@@ -527,8 +583,9 @@ int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) {
     static_assert(sizeof(PtrsBvhNode) == 32, "LinearBVHNode is 32 bytes");
     CUDA_TRY(s->nodes.upload(reinterpret_cast<const float4*>(dev_nodes.data()), dev_nodes.size() * 2));
     s->scene_bytes += (uint64_t)dev_nodes.size() * 32;
+    n_dev_nodes = (uint32_t)dev_nodes.size();
   }
-  {
+  if (!device_bvh) {
     std::vector<float4> tv((size_t)d->n_prims * 3);
     std::vector<uint4> ti(d->n_prims);
     for (uint32_t i = 0; i < d->n_prims; ++i) {
@@ -554,17 +611,10 @@ int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) {
   if (d->normal) CUDA_TRY(s->normal.upload(d->normal, (size_t)d->n_verts * 3));
   if (d->tangent) CUDA_TRY(s->tangent.upload(d->tangent, (size_t)d->n_verts * 3));
   if (d->uv) CUDA_TRY(s->uv.upload(d->uv, (size_t)d->n_verts * 2));
-  for (uint32_t i = 0; i < d->n_meshes; ++i) {
-    const uint32_t f = d->meshes[i].flags;
-    if (((f & PTRS_MESH_HAS_NORMAL) && !d->normal) || ((f & PTRS_MESH_HAS_TANGENT) && !d->tangent) || ((f & PTRS_MESH_HAS_UV) && !d->uv))
-      return fail(PTRS_ERR_INVALID_ARGUMENT, "mesh flags name an attribute pool that is NULL");
-  }
-  CUDA_TRY(s->meshes.upload(d->meshes, d->n_meshes));
   CUDA_TRY(s->materials.upload(d->materials, d->n_materials));
   CUDA_TRY(s->textures.upload(d->textures, d->n_textures));
   CUDA_TRY(s->mipmaps.upload(d->mipmaps, d->n_mipmaps));
   CUDA_TRY(s->texels.upload(d->texels, d->n_texels));
-  CUDA_TRY(s->lights.upload(d->lights, d->n_lights));
   CUDA_TRY(s->infinite_lights.upload(d->infinite_lights, d->n_infinite_lights));
   {
     std::vector<DevEnv> envs(d->n_envs);
@@ -632,11 +682,12 @@ int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) {
   v.infinite_lights = s->infinite_lights.p;
   v.envs = s->envs.p;
   v.sobol = s->sobol.p;
-  v.n_nodes = d->n_nodes;
+  v.n_nodes = d->n_prims > 0 ? n_dev_nodes : 0u;
+  s->n_dev_nodes = v.n_nodes;
   v.n_prims = d->n_prims;
   v.n_lights = d->n_lights;
   v.n_infinite_lights = d->n_infinite_lights;
-  if (d->n_nodes > 0) {
+  if (!device_bvh && d->n_nodes > 0) {
     std::memcpy(s->world_bound, d->nodes[0].bounds_min, 12);
     std::memcpy(s->world_bound + 3, d->nodes[0].bounds_max, 12);
   }
@@ -646,6 +697,26 @@ int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) {
   CUDA_TRY(cudaEventCreate(&s->ev[1]));
   CUDA_TRY(cudaDeviceSynchronize());
   *out = s.release();
+  return PTRS_OK;
+}
+
+int32_t ptrs_scene_create(const PtrsSceneDesc* d, PtrsScene** out) { return scene_create_impl(d, false, out); }
+int32_t ptrs_scene_create_device_bvh(const PtrsSceneDesc* d, PtrsScene** out) { return scene_create_impl(d, true, out); }
+
+int32_t ptrs_scene_bvh_info(const PtrsScene* scene, uint32_t* n_nodes, float* device_build_ms) {
+  if (!scene) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  if (n_nodes) *n_nodes = scene->n_dev_nodes;
+  if (device_build_ms) *device_build_ms = scene->bvh_build_ms;
+  return PTRS_OK;
+}
+int32_t ptrs_scene_download_nodes(const PtrsScene* scene, PtrsBvhNode* nodes, uint32_t capacity, uint32_t* prim_order) {
+  if (!scene || !nodes) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  if (capacity < scene->n_dev_nodes) return fail(PTRS_ERR_INVALID_ARGUMENT, "node capacity too small");
+  CUDA_TRY(cudaMemcpy(nodes, scene->nodes.p, (size_t)scene->n_dev_nodes * 32, cudaMemcpyDeviceToHost));
+  if (prim_order) {
+    if (!scene->prim_map.p) return fail(PTRS_ERR_INVALID_ARGUMENT, "the scene keeps the caller's primitive order (host-built BVH)");
+    CUDA_TRY(cudaMemcpy(prim_order, scene->prim_map.p, scene->prim_map.n * 4, cudaMemcpyDeviceToHost));
+  }
   return PTRS_OK;
 }
 
@@ -680,7 +751,7 @@ static int32_t do_intersect(PtrsScene* s, const PtrsRay* d_rays, size_t n, PtrsH
   if (n > 0xfffffff0ull) return fail(PTRS_ERR_INVALID_ARGUMENT, "too many rays in one call");
   CUDA_TRY(cudaMemsetAsync(s->ticket.p, 0, 16, st));
   if (count) CUDA_TRY(cudaMemsetAsync(s->gcount.p, 0, sizeof(GlobalCounters), st));
-  launch_intersect(st, s->sm_count, any_hit, count, s->dev, d_rays, (uint32_t)n, d_hits, d_occ, s->ticket.p, s->gcount.p);
+  launch_intersect(st, s->sm_count, any_hit, count, s->dev, d_rays, (uint32_t)n, d_hits, d_occ, s->ticket.p, s->gcount.p, s->prim_map.p);
   CUDA_TRY(cudaGetLastError());
   return PTRS_OK;
 }

@@ -28,7 +28,8 @@ EXPORTS = [
     "ptrs_intersect_p_device", "ptrs_intersect_counted_device", "ptrs_film_create", "ptrs_film_wrap_device", "ptrs_film_destroy",
     "ptrs_film_clear", "ptrs_film_download", "ptrs_film_resolve", "ptrs_film_resolve_srgb8", "ptrs_film_device_ptr",
     "ptrs_film_sample_bounds", "ptrs_render_params_default", "ptrs_render", "ptrs_path_radiance", "ptrs_stats",
-    "ptrs_set_stats_mode", "ptrs_sobol_samples", "ptrs_generate_rays", "ptrs_trim_memory",
+    "ptrs_set_stats_mode", "ptrs_sobol_samples", "ptrs_generate_rays", "ptrs_trim_memory", "ptrs_scene_create_device_bvh",
+    "ptrs_scene_bvh_info", "ptrs_scene_download_nodes",
 ]
 
 
@@ -53,6 +54,9 @@ def lib():
         L.ptrs_device_count.argtypes = [i32p]
         L.ptrs_set_device.argtypes = [i32]
         L.ptrs_scene_create.argtypes = [descp, C.POINTER(vp)]
+        L.ptrs_scene_create_device_bvh.argtypes = [descp, C.POINTER(vp)]
+        L.ptrs_scene_bvh_info.argtypes = [vp, C.POINTER(C.c_uint32), fp]
+        L.ptrs_scene_download_nodes.argtypes = [vp, C.POINTER(PtrsBvhNode), C.c_uint32, C.POINTER(C.c_uint32)]
         L.ptrs_scene_destroy.argtypes = [vp]
         L.ptrs_scene_world_bound.argtypes = [vp, fp]
         L.ptrs_scene_device_bytes.restype = C.c_uint64
@@ -157,12 +161,31 @@ class Film:
 class RenderScene:
     """Device copy of a flattened scene (src/pathtracer/mod.rs:84-106)."""
 
-    def __init__(self, flat):
+    def __init__(self, flat, device_bvh=False):
+        """device_bvh=True ignores the description's nodes and builds a linear BVH on the GPU (ptrs_scene_create_device_bvh)."""
         desc = flat.desc if isinstance(flat, FlatScene) else flat
         h = C.c_void_p()
-        _check(lib().ptrs_scene_create(desc, C.byref(h)))
+        _check((lib().ptrs_scene_create_device_bvh if device_bvh else lib().ptrs_scene_create)(desc, C.byref(h)))
         self._h = h
         self.n_lights = desc.contents.n_lights
+        self.n_prims = desc.contents.n_prims
+        self.device_bvh = device_bvh
+
+    def bvh_info(self):
+        """(device node count, device build time in ms; 0 for a host-built tree)"""
+        n, ms = C.c_uint32(0), C.c_float(0)
+        _check(lib().ptrs_scene_bvh_info(self._h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def download_nodes(self):
+        """Device-side tree: (nodes structured array in the traversal layout, prim_order or None)."""
+        from .host import NODE_DTYPE
+
+        n, _ = self.bvh_info()
+        nodes = np.empty(n, dtype=NODE_DTYPE)
+        order = np.empty(self.n_prims, dtype=np.uint32) if self.device_bvh else None
+        _check(lib().ptrs_scene_download_nodes(self._h, _p(nodes, PtrsBvhNode), n, _p(order, C.c_uint32) if self.device_bvh else None))
+        return nodes, order
 
     def close(self):
         if getattr(self, "_h", None):

@@ -228,3 +228,109 @@ def test_headless_cli_renders_the_xml_scene(gpu, host, tmp_path):
     assert png.shape == (80, 96, 4)
     assert np.array_equal(png, film.to_rgba_image())
     scene.close()
+
+
+# ---- BVH built on the device (csrc/k_bvh.cu) ------------------------------------------------
+def _walk_device_tree(nodes):
+    """(leaf ranges, max leaf size); checks that every child box lies inside its parent's box."""
+    leaves, stack = [], [0]
+    while stack:
+        i = stack.pop()
+        n = nodes[i]
+        if n["n_prims"] > 0:
+            leaves.append((int(n["offset"]), int(n["n_prims"])))
+            continue
+        for c in (int(n["offset"]), int(n["offset"]) + 1):
+            assert np.all(nodes[c]["bmin"] >= n["bmin"]) and np.all(nodes[c]["bmax"] <= n["bmax"]), "child box outside its parent"
+            stack.append(c)
+    return leaves
+
+
+@pytest.mark.parametrize("scene_name", ["cornell", "field_small", "terrain_small"])
+def test_device_bvh_is_a_valid_tree(gpu, request, scene_name):
+    flat, _ = request.getfixturevalue(scene_name)
+    scene = gpu.RenderScene(flat, device_bvh=True)
+    nodes, order = scene.download_nodes()
+    n_nodes, ms = scene.bvh_info()
+    assert n_nodes == nodes.shape[0] and ms > 0
+    assert np.array_equal(np.sort(order), np.arange(flat.n_prims, dtype=np.uint32)), "primitive order is not a permutation"
+    leaves = _walk_device_tree(nodes)
+    covered = np.zeros(flat.n_prims, dtype=np.int32)
+    tri = flat.prim_vertices()[order]  # BVH order
+    for off, cnt in leaves:
+        assert 1 <= cnt <= 4
+        covered[off: off + cnt] += 1
+    assert np.all(covered == 1), "a primitive is missing from, or repeated in, the leaves"
+    # leaf boxes hold their triangles exactly (min / max are exact in f32)
+    leaf_nodes = nodes[nodes["n_prims"] > 0]
+    for n in leaf_nodes[:: max(1, leaf_nodes.shape[0] // 2000)]:
+        t = tri[int(n["offset"]): int(n["offset"]) + int(n["n_prims"])].reshape(-1, 3)
+        assert np.array_equal(t.min(axis=0), n["bmin"]) and np.array_equal(t.max(axis=0), n["bmax"])
+    bmin, bmax = scene.world_bound()
+    assert np.array_equal(bmin, tri.reshape(-1, 3).min(axis=0)) and np.array_equal(bmax, tri.reshape(-1, 3).max(axis=0))
+    scene.close()
+
+
+@pytest.mark.parametrize("scene_name", ["cornell", "field_small", "terrain_small", "atrium_small"])
+def test_device_bvh_hits_equal_the_reference_built_bvh(gpu, host, request, scene_name):
+    """Same triangle test on the same vertices, so the closest hit does not depend on the tree — except between
+    candidates within an ulp or two of each other: the later-visited one wins exact ties (shape.rs:150-154) and the
+    slab test's t_min is not conservative (bounds.rs:190-232 only widens t_max), so a leaf whose box starts at the
+    current t_max is culled or not depending on what was found first.  Measured: <= 1 ray in 50 000, 7e-8 relative."""
+    flat, cam = request.getfixturevalue(scene_name)
+    ref = gpu.RenderScene(flat)
+    dev = gpu.RenderScene(flat, device_bvh=True)
+    bmin, bmax = flat.world_bound()
+    for rays in (host.coherent_rays(cam, 192), host.incoherent_rays(bmin, bmax, 7, 60000)):
+        a, b = ref.intersect(rays), dev.intersect(rays)
+        assert np.array_equal(a["prim"] >= 0, b["prim"] >= 0)
+        hit = a["prim"] >= 0
+        dt = a["t"][hit] != b["t"][hit]
+        assert dt.mean() < 1e-4, f"{dt.sum()} closest-hit distances differ between the two trees"
+        assert np.allclose(a["t"][hit], b["t"][hit], rtol=1e-6, atol=0)
+        same = a["prim"] == b["prim"]
+        assert same.mean() > 0.999, f"{(~same).sum()} primitive ids differ"
+        for f in ("b0", "b1", "b2"):
+            assert np.array_equal(a[f][same & hit], b[f][same & hit])
+        seg = rays.copy()
+        seg["t_max"] = np.where(hit, a["t"] * np.float32(1.5), np.float32(1.0)).astype(np.float32)
+        seg["t_max"][::2] = (a["t"][::2] * np.float32(0.5)).astype(np.float32)
+        assert np.mean(ref.intersect_p(seg) != dev.intersect_p(seg)) < 1e-4
+    ref.close()
+    dev.close()
+
+
+@pytest.mark.parametrize("scene_name,spp,depth", [("cornell_env", 16, 15), ("field_small", 16, 8)])
+def test_device_bvh_render_matches(gpu, request, scene_name, spp, depth):
+    flat, cam = request.getfixturevalue(scene_name)
+    imgs = []
+    for dev_bvh in (False, True):
+        scene = gpu.RenderScene(flat, device_bvh=dev_bvh)
+        integ = gpu.PathIntegrator(gpu.SamplerBuilder(spp), max_depth=depth)
+        film = gpu.Film(cam.width, cam.height)
+        integ.render(cam, scene, film)
+        imgs.append(film.to_channel_updates())
+        scene.close()
+    assert _rel_mse(imgs[1], imgs[0]) < 1e-4
+
+
+def test_device_bvh_tiny_scenes(gpu, host):
+    """1, 2 and 4 triangles: the root is the only node (a leaf); 5 triangles: the first interior node."""
+    for n_tri in (1, 2, 4, 5):
+        b = host.SceneBuilder()
+        m = b.material(host.MAT_MATTE, [b.constant_texture([0.5, 0.5, 0.5])])
+        pos = np.array([[k, 0, 0] for k in range(n_tri)] * 1, dtype=np.float32)
+        verts = np.concatenate([pos + np.array(o, dtype=np.float32) for o in ([0, 0, 0], [0.8, 0, 0], [0, 0.8, 0])])
+        idx = np.array([[k, n_tri + k, 2 * n_tri + k] for k in range(n_tri)], dtype=np.uint32)
+        b.mesh(verts, idx, material=m)
+        flat = b.finalize()
+        ref, dev = gpu.RenderScene(flat), gpu.RenderScene(flat, device_bvh=True)
+        rays = np.zeros(n_tri + 1, dtype=host.RAY_DTYPE)
+        rays["o"] = [[k + 0.2, 0.2, 1.0] for k in range(n_tri + 1)]
+        rays["d"] = [0, 0, -1]
+        rays["t_max"] = np.inf
+        a, c = ref.intersect(rays), dev.intersect(rays)
+        assert np.array_equal(a, c)
+        assert dev.bvh_info()[0] == (2 if n_tri <= 4 else 4)
+        ref.close()
+        dev.close()

@@ -285,10 +285,15 @@ __global__ void remap_light_prims_kernel(PtrsLight* lights, uint32_t n_lights, c
   if (i < n_lights && lights[i].type == PTRS_LIGHT_AREA) lights[i].prim = (int32_t)inv_perm[lights[i].prim];
 }
 
-template <class T>
-cudaError_t dev_alloc(T** p, size_t count, cudaStream_t st) {
-  return cudaMallocAsync(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T), st);
-}
+struct Arena {  // one stream-ordered allocation carved into 256-byte aligned arrays
+  char* base = nullptr;
+  size_t used = 0;
+  template <class T>
+  void take(T** p, size_t count) {
+    if (base) *p = reinterpret_cast<T*>(base + used);
+    used += (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~(size_t)255;
+  }
+};
 
 }  // namespace
 
@@ -303,7 +308,7 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
   if (n == 0) return cudaSuccess;
   BuildArrays A{};
   uint64_t* keys_sorted = nullptr;
-  uint32_t* perm_sorted = nullptr;
+  uint32_t *perm_in = nullptr, *perm_sorted = nullptr;
   void* sort_tmp = nullptr;
   float4* nodes = nullptr;
   cudaError_t e = cudaSuccess;
@@ -312,26 +317,49 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
     return e == cudaSuccess;
   };
   const size_t n_int = n > 1 ? n - 1 : 0;
-  ok(dev_alloc(&A.pb_min, n, st)) && ok(dev_alloc(&A.pb_max, n, st)) && ok(dev_alloc(&A.keys, n, st)) && ok(dev_alloc(&A.perm, n, st)) &&
-      ok(dev_alloc(&keys_sorted, n, st)) && ok(dev_alloc(&perm_sorted, n, st)) && ok(dev_alloc(&A.parent, 2 * (size_t)n, st)) &&
-      ok(dev_alloc(&A.left, n_int, st)) && ok(dev_alloc(&A.right, n_int, st)) && ok(dev_alloc(&A.first, n_int, st)) && ok(dev_alloc(&A.last, n_int, st)) &&
-      ok(dev_alloc(&A.nb_min, 2 * (size_t)n, st)) && ok(dev_alloc(&A.nb_max, 2 * (size_t)n, st)) && ok(dev_alloc(&A.arrivals, n_int, st)) &&
-      ok(dev_alloc(&A.n_interior, n_int, st)) && ok(dev_alloc(&A.cbounds, 6, st));
+  size_t sort_bytes = 0;
+  ok(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, A.keys, keys_sorted, perm_in, perm_sorted, (int)n, 0, 63, st));
+  Arena arena;
+  auto carve = [&](Arena& ar) {
+    ar.take(&A.pb_min, n);
+    ar.take(&A.pb_max, n);
+    ar.take(&A.keys, n);
+    ar.take(&perm_in, n);
+    ar.take(&keys_sorted, n);
+    ar.take(&A.parent, 2 * (size_t)n);
+    ar.take(&A.left, n_int);
+    ar.take(&A.right, n_int);
+    ar.take(&A.first, n_int);
+    ar.take(&A.last, n_int);
+    ar.take(&A.nb_min, 2 * (size_t)n);
+    ar.take(&A.nb_max, 2 * (size_t)n);
+    ar.take(&A.arrivals, n_int);
+    ar.take(&A.n_interior, n_int);
+    ar.take(&A.cbounds, 6);
+    char* tmp = nullptr;
+    ar.take(&tmp, std::max<size_t>(sort_bytes, 16));
+    sort_tmp = tmp;
+  };
+  carve(arena);  // sizes only
+  const size_t arena_bytes = arena.used;
+  void* arena_mem = nullptr;
+  ok(cudaMallocAsync(&arena_mem, arena_bytes, st));
+  ok(cudaMallocAsync(reinterpret_cast<void**>(&perm_sorted), (size_t)n * 4, st));  // survives: the primitive order handed back
   const int grid = 148 * 8;
   uint32_t n_interior_root = 0;
   if (e == cudaSuccess) {
+    arena = Arena{static_cast<char*>(arena_mem), 0};
+    carve(arena);
+    A.perm = perm_in;
     const uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     ok(cudaMemcpyAsync(A.cbounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
     ok(cudaMemsetAsync(A.arrivals, 0, std::max<size_t>(n_int, 1) * 4, st));
     ok(cudaMemsetAsync(A.n_interior, 0, std::max<size_t>(n_int, 1) * 4, st));
     prim_bounds_kernel<<<grid, 256, 0, st>>>(d_prim_vertex, d_pos, n, A);
     morton_kernel<<<grid, 256, 0, st>>>(n, A);
-    size_t tmp_bytes = 0;
-    ok(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, A.keys, keys_sorted, A.perm, perm_sorted, (int)n, 0, 63, st));
-    ok(cudaMallocAsync(&sort_tmp, std::max<size_t>(tmp_bytes, 16), st));
-    if (e == cudaSuccess) ok(cub::DeviceRadixSort::SortPairs(sort_tmp, tmp_bytes, A.keys, keys_sorted, A.perm, perm_sorted, (int)n, 0, 63, st));
-    std::swap(A.perm, perm_sorted);
-    std::swap(A.keys, keys_sorted);
+    ok(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, A.keys, keys_sorted, perm_in, perm_sorted, (int)n, 0, 63, st));
+    A.perm = perm_sorted;
+    A.keys = keys_sorted;
     if (n > 1) {
       radix_tree_kernel<<<grid, 256, 0, st>>>(A.keys, (int)n, A);
       refit_kernel<<<grid, 256, 0, st>>>(n, A);
@@ -342,7 +370,7 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
   }
   if (e == cudaSuccess) {
     const uint32_t n_nodes = 2u + 2u * n_interior_root;
-    ok(dev_alloc(&nodes, 2 * (size_t)n_nodes, st));
+    ok(cudaMallocAsync(reinterpret_cast<void**>(&nodes), (size_t)n_nodes * 32, st));
     if (e == cudaSuccess) {
       if (n_interior_root == 0) single_leaf_kernel<<<1, 32, 0, st>>>(n, A, nodes);
       else emit_kernel<<<grid, 256, 0, st>>>(n, A, nodes);
@@ -350,17 +378,14 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
       *n_nodes_out = n_nodes;
     }
   }
-  void* scratch[] = {A.pb_min, A.pb_max, A.keys, keys_sorted, perm_sorted, A.parent, A.left, A.right, A.first, A.last, A.nb_min, A.nb_max,
-                     A.arrivals, A.n_interior, A.cbounds, sort_tmp};
-  for (void* p : scratch)
-    if (p) cudaFreeAsync(p, st);
+  if (arena_mem) cudaFreeAsync(arena_mem, st);
   if (e != cudaSuccess) {
     if (nodes) cudaFreeAsync(nodes, st);
-    if (A.perm) cudaFreeAsync(A.perm, st);
+    if (perm_sorted) cudaFreeAsync(perm_sorted, st);
     return (int)e;
   }
   *nodes_out = nodes;
-  *perm_out = A.perm;
+  *perm_out = perm_sorted;
   return (int)cudaSuccess;
 }
 

@@ -165,6 +165,35 @@ def bvh_microbench(gpu, host, torch, peak_gbs):
                         "achieved_gbs": alg_bytes / t / 1e9, "frac": alg_bytes / t / 1e9 / peak_gbs}
         del d_rays, d_hits, d_occ
     scene.close()
+    # the same mesh with the BVH built on the device (ptrs_scene_create_device_bvh, csrc/k_bvh.cu)
+    dev = {}
+    for tag in ("build_ms_cold", "build_ms_warm"):
+        scene = gpu.RenderScene(flat, device_bvh=True)
+        dev["n_nodes"], dev[tag] = scene.bvh_info()
+        if tag == "build_ms_cold":
+            scene.close()
+    dev["speedup_vs_host_sah"] = flat.bvh_seconds * 1e3 / dev["build_ms_warm"]
+    rays = host.incoherent_rays(bmin, bmax, 42, n_side * n_side)
+    n = rays.shape[0]
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).cuda()
+    d_hits = torch.empty(n * 20, dtype=torch.uint8, device="cuda")
+    nodes, tris = scene.intersect_counted_device(d_rays.data_ptr(), n, d_hits.data_ptr(), any_hit=False, stream=stream)
+    ms = []
+    for it in range(6):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        scene.intersect_device(d_rays.data_ptr(), n, d_hits.data_ptr(), stream)
+        e1.record()
+        e1.synchronize()
+        if it >= 3:
+            ms.append(e0.elapsed_time(e1))
+    t = float(np.mean(ms)) * 1e-3
+    alg_bytes = 32 * nodes + 36 * tris + n * 48
+    dev["incoherent_closest"] = {"mrays_per_s": n / t / 1e6, "ms": t * 1e3, "nodes_per_ray": nodes / n, "tris_per_ray": tris / n,
+                                 "achieved_gbs": alg_bytes / t / 1e9, "frac": alg_bytes / t / 1e9 / peak_gbs}
+    out["device_bvh"] = dev
+    scene.close()
     return out
 
 

@@ -301,7 +301,12 @@ int SceneBuilder::add_image_texture(int channels, const float* image, int width,
   t.dv = dv;
   t.mip = push_mip(mm);
   textures_.push_back(t);
+  tex_mips_.emplace((int)textures_.size() - 1, std::move(mm));
   return (int)textures_.size() - 1;
+}
+const HostMipMap* SceneBuilder::image_texture_mip(int texture) const {
+  auto it = tex_mips_.find(texture);
+  return it == tex_mips_.end() ? nullptr : &it->second;
 }
 int SceneBuilder::add_material(const PtrsMaterial& m) {
   materials_.push_back(m);
@@ -385,7 +390,8 @@ int SceneBuilder::add_mesh(const MeshInput& mesh) {
     tri_mesh_.push_back(mesh_id);
     tri_material_.push_back(mesh.material);
     int light = -1;
-    if (mesh.ke_tex >= 0) {  // importer/mitsuba.rs:309-323: one DiffuseAreaLight per triangle
+    if (!mesh.tri_emits.empty() && mesh.tri_emits.size() != nt) throw std::runtime_error("tri_emits size mismatch");
+    if (mesh.ke_tex >= 0 && (mesh.tri_emits.empty() || mesh.tri_emits[t])) {  // importer/mitsuba.rs:309-323: one DiffuseAreaLight per triangle
       PtrsLight l{};
       l.type = PTRS_LIGHT_AREA;
       l.prim = (int32_t)tri;

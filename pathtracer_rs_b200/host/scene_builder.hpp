@@ -5,6 +5,7 @@
 // PtrsSceneDesc the device library consumes.
 #pragma once
 #include <cstdint>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -45,7 +46,8 @@ struct MeshInput {
   M4 obj_to_world = M4::identity();
   int material = 0;
   int alpha_tex = -1;
-  int ke_tex = -1;             // >= 0: every triangle becomes a DiffuseAreaLight with this ke
+  int ke_tex = -1;             // >= 0: every triangle becomes a DiffuseAreaLight with this ke ...
+  std::vector<uint8_t> tri_emits;  // ... unless this per-triangle mask (glTF emissive textures) says otherwise
 };
 
 struct FlatScene {
@@ -94,6 +96,8 @@ class SceneBuilder {
   int add_infinite_light(const M4& light_to_world, const float* rgb, int width, int height);
 
   size_t triangle_count() const { return tri_vertex_.size() / 3; }
+  // host copy of an image texture's pyramid (importers evaluate emission maps with it), or null
+  const HostMipMap* image_texture_mip(int texture) const;
   FlatScene finalize(int max_prims_in_node = 4, int n_threads = 0);
 
  private:
@@ -112,6 +116,7 @@ class SceneBuilder {
   std::vector<PtrsEnvLight> envs_;
   std::vector<HostDistribution2D> env_dists_;
   std::vector<HostMipMap> env_mips_;
+  std::map<int, HostMipMap> tex_mips_;  // image texture id -> pyramid
 };
 
 // Camera::new (src/common/mod.rs:33-62) from an isometry + Perspective3::new(aspect, fovy, n, f).

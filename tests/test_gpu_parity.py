@@ -334,3 +334,22 @@ def test_device_bvh_tiny_scenes(gpu, host):
         assert dev.bvh_info()[0] == (2 if n_tri <= 4 else 4)
         ref.close()
         dev.close()
+
+
+def test_imported_gltf_scene_renders_like_the_oracle(gpu, host, oracle, tmp_path):
+    """A glTF document with textured Disney / glass / mirror materials, an alpha mask, a normal map, emissive
+    triangles and punctual lights, imported by host/importer_gltf.cpp, through both integrators."""
+    from test_gltf_import import write_gltf
+
+    path, _ = write_gltf(host, tmp_path, "glb")
+    flat, cam = host.import_scene(path, res=(96, 64), default_lights=True)
+    scene = gpu.RenderScene(flat)
+    integ = gpu.PathIntegrator(gpu.SamplerBuilder(32), max_depth=8)
+    film = gpu.Film(cam.width, cam.height)
+    integ.render(cam, scene, film)
+    img = film.to_channel_updates()
+    ref_film, _ = oracle.render(flat, cam, integ.params)
+    ref = oracle.resolve(ref_film)
+    assert np.isfinite(ref).all() and ref.max() > 0
+    assert _rel_mse(img, ref) < 1e-3
+    scene.close()

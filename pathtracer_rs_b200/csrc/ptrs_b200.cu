@@ -813,8 +813,12 @@ int32_t ptrs_film_create(int32_t width, int32_t height, PtrsFilm** out) {
   f->width = width;
   f->height = height;
   f->owned = true;
-  CUDA_TRY(cudaMalloc(&f->d, (size_t)width * height * sizeof(float4)));
-  CUDA_TRY(cudaMemset(f->d, 0, (size_t)width * height * sizeof(float4)));
+  // pooled, stream-ordered allocation like the scene buffers: creating / destroying a film per render does not
+  // pay cudaMalloc / cudaFree (device-wide synchronisation, page mapping)
+  keep_pool_reserved();
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&f->d), (size_t)width * height * sizeof(float4), (cudaStream_t)0));
+  CUDA_TRY(cudaMemsetAsync(f->d, 0, (size_t)width * height * sizeof(float4), (cudaStream_t)0));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));
   *out = f.release();
   return PTRS_OK;
 }
@@ -830,7 +834,7 @@ int32_t ptrs_film_wrap_device(int32_t width, int32_t height, float* d_rgbw, Ptrs
 }
 int32_t ptrs_film_destroy(PtrsFilm* film) {
   if (!film) return PTRS_OK;
-  if (film->owned && film->d) cudaFree(film->d);
+  if (film->owned && film->d) cudaFreeAsync(film->d, (cudaStream_t)0);
   delete film;
   return PTRS_OK;
 }

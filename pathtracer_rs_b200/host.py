@@ -107,7 +107,10 @@ class FlatScene:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().ptrs_host_scene_free(self._h)
+            try:
+                lib().ptrs_host_scene_free(self._h)
+            except TypeError:  # interpreter shutdown: module globals are already gone
+                pass
             self._h = None
 
     @property

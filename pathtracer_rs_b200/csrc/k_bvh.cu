@@ -29,24 +29,27 @@ __device__ __forceinline__ uint32_t f2o(float f) {
 }
 __device__ __forceinline__ float o2f(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
 
+// One 32-byte record (= one DRAM sector) per radix-tree node, so that a refit step touches three sectors (the
+// parent's record, the sibling's box, the parent's box) instead of a dozen scattered 4-byte fields.
+struct __align__(32) TreeNode {  // internal nodes [0, n-1); leaves are addressed as (n - 1 + sorted position)
+  uint32_t left, right, parent;
+  uint32_t first, last;   // sorted range covered
+  uint32_t arrivals;      // refit: children finished so far
+  uint32_t n_interior;    // emitted interior nodes in the subtree (0 when the subtree collapses into a leaf)
+  uint32_t pad;
+};
+struct __align__(32) NodeBox {
+  float4 mn, mx;  // xyz used
+};
 struct BuildArrays {
-  // per primitive, caller order
-  float4* pb_min;  // xyz = bounds min, w unused
+  float4* pb_min;  // per primitive, caller order: bounds min / max
   float4* pb_max;
-  // per primitive, sorted order
-  uint64_t* keys;
+  uint64_t* keys;  // per primitive, sorted order
   uint32_t* perm;  // sorted position -> caller's primitive index
-  // radix tree: internal nodes [0, n-1), leaves are addressed as (n - 1 + sorted position)
-  uint32_t* parent;     // 2n - 1
-  uint32_t* left;       // n - 1
-  uint32_t* right;      // n - 1
-  uint32_t* first;      // n - 1: sorted range covered
-  uint32_t* last;       // n - 1
-  float4* nb_min;       // 2n - 1
-  float4* nb_max;       // 2n - 1
-  uint32_t* arrivals;   // n - 1
-  uint32_t* n_interior;  // n - 1: emitted interior nodes in the subtree (0 when the subtree collapses into a leaf)
-  uint32_t* cbounds;    // 6 ordered uints: centroid bounds
+  TreeNode* node;         // n - 1
+  uint32_t* leaf_parent;  // n
+  NodeBox* box;           // 2n - 1
+  uint32_t* cbounds;      // 6 ordered uints: centroid bounds
 };
 
 __global__ void __launch_bounds__(256) prim_bounds_kernel(const uint32_t* __restrict__ prim_vertex, const float* __restrict__ pos, uint32_t n, BuildArrays A) {
@@ -135,13 +138,18 @@ __global__ void __launch_bounds__(256) radix_tree_kernel(const uint64_t* __restr
     const int lo = min(i, j), hi = max(i, j);
     const uint32_t lc = lo == gamma ? (uint32_t)(n - 1 + gamma) : (uint32_t)gamma;
     const uint32_t rc = hi == gamma + 1 ? (uint32_t)(n - 1 + gamma + 1) : (uint32_t)(gamma + 1);
-    A.left[i] = lc;
-    A.right[i] = rc;
-    A.first[i] = (uint32_t)lo;
-    A.last[i] = (uint32_t)hi;
-    A.parent[lc] = (uint32_t)i;
-    A.parent[rc] = (uint32_t)i;
-    if (i == 0) A.parent[0] = 0xffffffffu;
+    TreeNode& nd = A.node[i];
+    nd.left = lc;
+    nd.right = rc;
+    nd.first = (uint32_t)lo;
+    nd.last = (uint32_t)hi;
+    nd.arrivals = 0u;
+    nd.n_interior = 0u;
+    if (lc >= (uint32_t)(n - 1)) A.leaf_parent[lc - (uint32_t)(n - 1)] = (uint32_t)i;
+    else A.node[lc].parent = (uint32_t)i;
+    if (rc >= (uint32_t)(n - 1)) A.leaf_parent[rc - (uint32_t)(n - 1)] = (uint32_t)i;
+    else A.node[rc].parent = (uint32_t)i;
+    if (i == 0) nd.parent = 0xffffffffu;
   }
 }
 
@@ -152,30 +160,32 @@ __global__ void __launch_bounds__(256) refit_kernel(uint32_t n, BuildArrays A) {
     const uint32_t prim = A.perm[j];
     uint32_t node = n - 1 + j;
     float4 mn = A.pb_min[prim], mx = A.pb_max[prim];
-    A.nb_min[node] = mn;
-    A.nb_max[node] = mx;
+    A.box[node] = NodeBox{mn, mx};
     if (n == 1) return;
+    uint32_t p = A.leaf_parent[j];
+    uint32_t ni_self = 0;  // emitted interior nodes below (and including) `node`
     for (;;) {
-      const uint32_t p = A.parent[node];
-      if (p == 0xffffffffu) break;
       __threadfence();
-      if (atomicAdd(&A.arrivals[p], 1u) == 0u) break;  // the sibling subtree is not finished: its thread continues
+      TreeNode* pn = A.node + p;
+      if (atomicAdd(&pn->arrivals, 1u) == 0u) break;  // the sibling subtree is not finished: its thread continues
       __threadfence();
-      const uint32_t l = A.left[p], r = A.right[p];
-      const uint32_t other = l == node ? r : l;
-      const float4 omn = __ldcg(A.nb_min + other), omx = __ldcg(A.nb_max + other);
+      const uint4 w0 = __ldcg(reinterpret_cast<const uint4*>(pn));      // left, right, parent, first
+      const uint4 w1 = __ldcg(reinterpret_cast<const uint4*>(pn) + 1);  // last, arrivals, n_interior, pad
+      const uint32_t other = w0.x == node ? w0.y : w0.x;
+      const float4 omn = __ldcg(&A.box[other].mn), omx = __ldcg(&A.box[other].mx);
       mn = make_float4(fminf(mn.x, omn.x), fminf(mn.y, omn.y), fminf(mn.z, omn.z), 0.f);
       mx = make_float4(fmaxf(mx.x, omx.x), fmaxf(mx.y, omx.y), fmaxf(mx.z, omx.z), 0.f);
-      A.nb_min[p] = mn;
-      A.nb_max[p] = mx;
+      A.box[p] = NodeBox{mn, mx};
       uint32_t ni = 0;
-      if (A.last[p] - A.first[p] + 1u > PT_BVH_MAX_LEAF) {
-        ni = 1u;
-        if (l < n - 1) ni += __ldcg(A.n_interior + l);
-        if (r < n - 1) ni += __ldcg(A.n_interior + r);
+      if (w1.x - w0.w + 1u > PT_BVH_MAX_LEAF) {
+        ni = 1u + ni_self;
+        if (other < n - 1) ni += __ldcg(&A.node[other].n_interior);
       }
-      A.n_interior[p] = ni;
+      pn->n_interior = ni;
+      ni_self = ni;
       node = p;
+      p = w0.z;
+      if (p == 0xffffffffu) break;
     }
   }
 }
@@ -193,20 +203,19 @@ __device__ __forceinline__ NodeRec make_node(float4 mn, float4 mx, uint32_t offs
 // one thread per emitted interior node: depth-first pair number from the path to the root, then the two child records
 __global__ void __launch_bounds__(256) emit_kernel(uint32_t n, BuildArrays A, float4* __restrict__ nodes) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n - 1; i += gridDim.x * blockDim.x) {
-    if (A.n_interior[i] == 0) continue;
+    const TreeNode self = A.node[i];
+    if (self.n_interior == 0) continue;
     uint32_t pair = 1;
-    for (uint32_t c = i; c != 0;) {
-      const uint32_t p = A.parent[c];
+    for (uint32_t c = i, p = self.parent; c != 0;) {
+      const TreeNode pn = A.node[p];
       pair += 1;
-      if (A.right[p] == c) {
-        const uint32_t l = A.left[p];
-        if (l < n - 1) pair += A.n_interior[l];
-      }
+      if (pn.right == c && pn.left < n - 1) pair += A.node[pn.left].n_interior;
       c = p;
+      p = pn.parent;
     }
-    const uint32_t l = A.left[i], r = A.right[i];
-    const uint32_t l_int = l < n - 1 ? A.n_interior[l] : 0u, r_int = r < n - 1 ? A.n_interior[r] : 0u;
-    const float4 lmn = A.nb_min[l], lmx = A.nb_max[l], rmn = A.nb_min[r], rmx = A.nb_max[r];
+    const uint32_t l = self.left, r = self.right;
+    const uint32_t l_int = l < n - 1 ? A.node[l].n_interior : 0u, r_int = r < n - 1 ? A.node[r].n_interior : 0u;
+    const float4 lmn = A.box[l].mn, lmx = A.box[l].mx, rmn = A.box[r].mn, rmx = A.box[r].mx;
     // split axis: where the children's box centres differ most; the lower child goes first
     const float dc[3] = {(rmn.x + rmx.x) - (lmn.x + lmx.x), (rmn.y + rmx.y) - (lmn.y + lmx.y), (rmn.z + rmx.z) - (lmn.z + lmx.z)};
     uint32_t axis = 0;
@@ -215,15 +224,16 @@ __global__ void __launch_bounds__(256) emit_kernel(uint32_t n, BuildArrays A, fl
     const bool swap = dc[axis] < 0.f;
     auto child = [&](uint32_t c, uint32_t c_int, uint32_t c_pair, float4 mn, float4 mx) {
       if (c_int) {
-        const float4 gmn_l = A.nb_min[A.left[c]], gmx_l = A.nb_max[A.left[c]], gmn_r = A.nb_min[A.right[c]], gmx_r = A.nb_max[A.right[c]];
+        const uint32_t gl = A.node[c].left, gr = A.node[c].right;
+        const float4 gmn_l = A.box[gl].mn, gmx_l = A.box[gl].mx, gmn_r = A.box[gr].mn, gmx_r = A.box[gr].mx;
         const float g[3] = {(gmn_r.x + gmx_r.x) - (gmn_l.x + gmx_l.x), (gmn_r.y + gmx_r.y) - (gmn_l.y + gmx_l.y), (gmn_r.z + gmx_r.z) - (gmn_l.z + gmx_l.z)};
         uint32_t ax = 0;
         if (fabsf(g[1]) > fabsf(g[ax])) ax = 1;
         if (fabsf(g[2]) > fabsf(g[ax])) ax = 2;
         return make_node(mn, mx, 2u * c_pair, 0u, ax);
       }
-      const uint32_t f = c < n - 1 ? A.first[c] : c - (n - 1);
-      const uint32_t cnt = c < n - 1 ? A.last[c] - A.first[c] + 1u : 1u;
+      const uint32_t f = c < n - 1 ? A.node[c].first : c - (n - 1);
+      const uint32_t cnt = c < n - 1 ? A.node[c].last - A.node[c].first + 1u : 1u;
       return make_node(mn, mx, f, cnt, 0u);
     };
     const NodeRec ln = child(l, l_int, pair + 1, lmn, lmx), rn = child(r, r_int, pair + 1 + l_int, rmn, rmx);
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(256) emit_kernel(uint32_t n, BuildArrays A, fl
     nodes[4 * (size_t)pair + 2] = second.a;
     nodes[4 * (size_t)pair + 3] = second.b;
     if (i == 0) {
-      const NodeRec root = make_node(A.nb_min[0], A.nb_max[0], 2u, 0u, axis);
+      const NodeRec root = make_node(A.box[0].mn, A.box[0].mx, 2u, 0u, axis);
       nodes[0] = root.a;
       nodes[1] = root.b;
       nodes[2] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -326,15 +336,9 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
     ar.take(&A.keys, n);
     ar.take(&perm_in, n);
     ar.take(&keys_sorted, n);
-    ar.take(&A.parent, 2 * (size_t)n);
-    ar.take(&A.left, n_int);
-    ar.take(&A.right, n_int);
-    ar.take(&A.first, n_int);
-    ar.take(&A.last, n_int);
-    ar.take(&A.nb_min, 2 * (size_t)n);
-    ar.take(&A.nb_max, 2 * (size_t)n);
-    ar.take(&A.arrivals, n_int);
-    ar.take(&A.n_interior, n_int);
+    ar.take(&A.node, n_int);
+    ar.take(&A.leaf_parent, n);
+    ar.take(&A.box, 2 * (size_t)n);
     ar.take(&A.cbounds, 6);
     char* tmp = nullptr;
     ar.take(&tmp, std::max<size_t>(sort_bytes, 16));
@@ -353,8 +357,6 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
     A.perm = perm_in;
     const uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     ok(cudaMemcpyAsync(A.cbounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    ok(cudaMemsetAsync(A.arrivals, 0, std::max<size_t>(n_int, 1) * 4, st));
-    ok(cudaMemsetAsync(A.n_interior, 0, std::max<size_t>(n_int, 1) * 4, st));
     prim_bounds_kernel<<<grid, 256, 0, st>>>(d_prim_vertex, d_pos, n, A);
     morton_kernel<<<grid, 256, 0, st>>>(n, A);
     ok(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, A.keys, keys_sorted, perm_in, perm_sorted, (int)n, 0, 63, st));
@@ -363,7 +365,7 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
     if (n > 1) {
       radix_tree_kernel<<<grid, 256, 0, st>>>(A.keys, (int)n, A);
       refit_kernel<<<grid, 256, 0, st>>>(n, A);
-      ok(cudaMemcpyAsync(&n_interior_root, A.n_interior, 4, cudaMemcpyDeviceToHost, st));
+      ok(cudaMemcpyAsync(&n_interior_root, &A.node[0].n_interior, 4, cudaMemcpyDeviceToHost, st));
     }
     ok(cudaStreamSynchronize(st));
     ok(cudaGetLastError());

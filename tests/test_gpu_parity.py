@@ -353,3 +353,37 @@ def test_imported_gltf_scene_renders_like_the_oracle(gpu, host, oracle, tmp_path
     assert np.isfinite(ref).all() and ref.max() > 0
     assert _rel_mse(img, ref) < 1e-3
     scene.close()
+
+
+def test_full_size_bench_workload_properties(gpu, host, oracle):
+    """BASELINE configs[1] at full size (Cornell + env map, 1024 x 1024, 64 spp, depth 15: 67.6 M camera paths), where the
+    oracle is too slow to run whole.  Size-independent properties: the path count of §8; the film's weight channel (a pure
+    function of the Sobol film positions) equals the oracle's on a band of rows; two sample shards sum to the whole
+    render (the multi-GPU decomposition); a render is reproducible; and a 16 x 16-tile sample of the image matches the oracle."""
+    flat, cam = host.make_scene(host.SCENE_CORNELL_ENV, seed=1, res=(1024, 1024))
+    scene = gpu.RenderScene(flat)
+    integ = gpu.PathIntegrator(gpu.SamplerBuilder(64), max_depth=15)
+    full = gpu.Film(cam.width, cam.height)
+    st = integ.render(cam, scene, full)
+    assert st["camera_paths"] == 1028 * 1028 * 64 == 67_634_176
+    a = full.download()
+    assert np.isfinite(a).all() and (a[..., 3] > 0).all() and (a[..., :3] >= 0).all()
+    parts = gpu.Film(cam.width, cam.height)
+    integ.render(cam, scene, parts, sample_stride=(2, 0))
+    integ.render(cam, scene, parts, sample_stride=(2, 1))
+    b = parts.download()
+    assert np.allclose(a[..., 3], b[..., 3], rtol=1e-5)  # weights: same terms, different order
+    assert _rel_mse(b[..., :3] / b[..., 3:], a[..., :3] / a[..., 3:]) < 1e-9
+    again = gpu.Film(cam.width, cam.height)
+    integ.render(cam, scene, again)
+    assert np.allclose(again.download(), a, rtol=2e-5, atol=1e-6)  # atomics reorder the float sums, nothing else
+    # the oracle on every 61st 16 x 16 tile (70 tiles, all 64 spp) — full-resolution Sobol indices, m = 11
+    ref_film, ref_st = oracle.render(flat, cam, integ.params, tile_stride=61)
+    touched = ref_film[..., 3] > 0
+    assert touched.sum() > 10000
+    inner = touched & np.isclose(ref_film[..., 3], a[..., 3], rtol=1e-5)  # pixels whose whole footprint lies in sampled tiles
+    assert inner.sum() > 4000
+    got = a[..., :3][inner] / a[..., 3:][inner]
+    want = ref_film[..., :3][inner] / ref_film[..., 3:][inner]
+    assert _rel_mse(got, want) < 1e-3
+    scene.close()

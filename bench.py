@@ -32,7 +32,20 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-WORKLOAD = {"name": "cornell+envmap 1024x1024 64spp depth15 (BASELINE configs[1])", "res": (1024, 1024), "spp": 64, "max_depth": 15}
+WORKLOAD = {"name": "cornell+envmap 1024x1024 64spp depth15 (BASELINE configs[1])", "res": (1024, 1024), "spp": 64, "max_depth": 15,
+            "scene": "SCENE_CORNELL_ENV", "n_tris": 0}
+# The other BASELINE configs, selectable with --workload for the tables in DESIGN.md §6 (the default and
+# the driver's line stay configs[1]).  --spp overrides the per-GPU sample count (C5's 1024 spp is run in
+# full only when sharded; a reduced-spp run says so in config.workload).
+WORKLOADS = {
+    "c1": {"name": "cornell 512x512 16spp depth15 (BASELINE configs[0])", "res": (512, 512), "spp": 16, "max_depth": 15,
+           "scene": "SCENE_CORNELL", "n_tris": 0},
+    "c2": WORKLOAD,
+    "c3": {"name": "1M-triangle material field (glass/substrate/metal/Disney/matte + env + area lights) 1920x1080 256spp depth15 (BASELINE configs[2])",
+           "res": (1920, 1080), "spp": 256, "max_depth": 15, "scene": "SCENE_MATERIAL_FIELD", "n_tris": 1000000},
+    "c5": {"name": "262k-triangle atrium 3840x2160 1024spp depth15 (BASELINE configs[4])", "res": (3840, 2160), "spp": 1024, "max_depth": 15,
+           "scene": "SCENE_ATRIUM", "n_tris": 262144},
+}
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -98,8 +111,11 @@ def run_reference(args):
     import pathtracer_rs_b200.host as host
     from oracle import oracle
 
-    w = WORKLOAD
-    flat, cam = host.make_scene(host.SCENE_CORNELL_ENV, seed=1, res=w["res"])
+    w = dict(WORKLOADS[args.workload])
+    if args.spp:
+        w["name"] += f" [run at {args.spp} spp per GPU]"
+        w["spp"] = args.spp
+    flat, cam = host.make_scene(getattr(host, w["scene"]), seed=1, n_tris=w["n_tris"], res=w["res"])
     params = host.default_render_params(spp=w["spp"], max_depth=w["max_depth"])
     n_tiles, stride = cpu_sample_plan(oracle, flat, cam, params, target_s=8.0)
     cores = os.cpu_count() or 1
@@ -218,9 +234,12 @@ def run_gpu(args):
     n_gpus = world
     peak_gbs, peak_src = measured_peaks()
 
-    w = WORKLOAD
+    w = dict(WORKLOADS[args.workload])
+    if args.spp:
+        w["name"] += f" [run at {args.spp} spp per GPU]"
+        w["spp"] = args.spp
     W, H = w["res"]
-    flat, cam = host.make_scene(host.SCENE_CORNELL_ENV, seed=1, res=w["res"])
+    flat, cam = host.make_scene(getattr(host, w["scene"]), seed=1, n_tris=w["n_tris"], res=w["res"])
     scene = gpu.RenderScene(flat)
     # weak scaling: the image is rendered at spp * N with rank g taking sample numbers s = g (mod N)
     integ = gpu.PathIntegrator(gpu.SamplerBuilder(w["spp"] * n_gpus), max_depth=w["max_depth"])
@@ -325,7 +344,7 @@ def run_gpu(args):
                 "avg_launch_ms": float(np.mean(ext_ms)) / max(1, stats["extend_launches"]),
                 "bytes_per_ray": alg_bytes / ext_rays, "nodes_per_ray": st_count["nodes_tested"] / ext_rays,
                 "tris_per_ray": st_count["tris_tested"] / ext_rays, "share_of_step": float(np.mean(ext_ms)) / (sum(step_ms) / len(step_ms)),
-                "note": "scene (36 triangles, 59 nodes) is L1/L2 resident: the HBM-bound case is bvh_microbench"}
+                "note": f"scene ({flat.n_prims} triangles, {flat.n_nodes} nodes) is cache resident (L1/L2): the HBM-bound case is bvh_microbench"}
 
     # ---- CPU baseline: the oracle on a bounded sample of the same workload ----------------------------
     cpu = None
@@ -400,6 +419,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bvh-microbench", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

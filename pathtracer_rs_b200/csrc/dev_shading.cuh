@@ -380,15 +380,11 @@ PT_DEVN float triangle_pdf_at_point(const DevScene& sc, int prim, const Inter& r
   float t, b0, b1, b2;
   if (!tri_core(p0, p1, p2, o, rp, CUDART_INF_F, &t, &b0, &b1, &b2)) return 0.0f;
   if (tri_post_reject(sc, prim, p0, p1, p2, __float_as_uint(v2.w), b0, b1, b2, true)) return 0.0f;
-  // isect_light.general.{p, n} of the hit
+  // isect_light.general.{p, n} of the hit.  On a mesh with normals or tangents the reference's n is the geometric
+  // normal flipped towards the shading normal (set_shading_geometry, interaction.rs:194-214) — +-n; only
+  // |dot(n, -wi)| is used and negation is exact, so the shading frame of the light's triangle is not rebuilt.
   V3 p_hit = b0 * p0 + b1 * p1 + b2 * p2;
   V3 n = normalize(cross(p0 - p2, p1 - p2));
-  const uint32_t flags = __float_as_uint(v2.w) & 0xffu;
-  if (flags & (PTRS_MESH_HAS_NORMAL | PTRS_MESH_HAS_TANGENT)) {
-    SurfInter si;
-    reconstruct_hit(sc, prim, b0, b1, b2, wi, &si);
-    n = si.g.n;
-  }
   return norm_squared(ref.p - p_hit) / (fabsf(dot(n, -wi)) * area);
 }
 

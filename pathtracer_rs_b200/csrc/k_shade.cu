@@ -185,6 +185,10 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const _
         const PtrsMaterial& m = sc.materials[mat_id];
         Bsdf bsdf;
         PathRay out = pr;
+        bool do_nee = false;
+        V2 u_light = V2{0.f, 0.f}, u_scattering = V2{0.f, 0.f};
+        float u_idx = 0.f;
+        const Spec beta0 = beta;  // throughput before this bounce: what the direct-lighting estimate is weighted by
         if (!compute_scattering_functions<MAT>(sc, m, &si, &bsdf)) {
           // null BSDF: continue straight through; `bounces -= 1; continue` nets -1 (integrator.rs:434-439)
           V3 o;
@@ -198,20 +202,14 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const _
           PathSampler ps;
           const int2 pix = unpack_pixel(pa.pixel);
           sampler_start(rc.sobol, rc.split, ps, pix.x, pix.y, pa.sample, flags & 0xffffu);
-          // direct lighting (integrator.rs:443-447, 192-217)
+          // direct lighting (integrator.rs:443-447, 192-217): its five sample values are drawn here, in the
+          // reference's order; the estimate itself runs after the path's continuation has been stored, when the
+          // path state is dead and before the 96-byte record becomes live
           if (bsdf_num_components(bsdf, BSDF_ALL & ~BSDF_SPECULAR) > 0 && sc.n_lights > 0) {
-            V2 u_light = get_2d(rc.sobol, rc.split, sobol, ps);
-            V2 u_scattering = get_2d(rc.sobol, rc.split, sobol, ps);
-            float u_idx = get_1d(rc.sobol, rc.split, sobol, ps);
-            unsigned long long li64 = (unsigned long long)floorf(u_idx * (float)sc.n_lights);
-            int light_idx = (int)(li64 < (unsigned long long)(sc.n_lights - 1) ? li64 : (unsigned long long)(sc.n_lights - 1));
-            float scat_pdf;
-            uint32_t nf;
-            nee_prepare(sc, si, bsdf, u_scattering, light_idx, u_light, &nee.n0, &nee.n1, &nee.n2, &nee.n3, &nee.n4, &scat_pdf, &nf);
-            if (nf & (PT_NEE_SHADOW | PT_NEE_MIS)) {
-              nee.n5 = make_float4(beta.r, beta.g, beta.b, scat_pdf);
-              push_nee = true;
-            }
+            do_nee = true;
+            u_light = get_2d(rc.sobol, rc.split, sobol, ps);
+            u_scattering = get_2d(rc.sobol, rc.split, sobol, ps);
+            u_idx = get_1d(rc.sobol, rc.split, sobol, ps);
           }
           // continuation (integrator.rs:449-499)
           V3 wi = mk3(0, 0, 0);
@@ -260,6 +258,17 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const _
           oa.bb = beta.b;
           st256(&P.slot[p].r, out);
           st256(&P.slot[p].a, oa);
+        }
+        if (do_nee) {
+          unsigned long long li64 = (unsigned long long)floorf(u_idx * (float)sc.n_lights);
+          int light_idx = (int)(li64 < (unsigned long long)(sc.n_lights - 1) ? li64 : (unsigned long long)(sc.n_lights - 1));
+          float scat_pdf;
+          uint32_t nf;
+          nee_prepare(sc, si, bsdf, u_scattering, light_idx, u_light, &nee.n0, &nee.n1, &nee.n2, &nee.n3, &nee.n4, &scat_pdf, &nf);
+          if (nf & (PT_NEE_SHADOW | PT_NEE_MIS)) {
+            nee.n5 = make_float4(beta0.r, beta0.g, beta0.b, scat_pdf);
+            push_nee = true;
+          }
         }
       }
     }

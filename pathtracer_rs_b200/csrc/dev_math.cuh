@@ -86,14 +86,25 @@ PT_DEV float next_float_down(float v) {
   ui += vv > 0.0f ? 1u : 0xffffffffu;
   return v == -CUDART_INF_F ? v : __uint_as_float(ui);
 }
+// `off > 0 ? next_float_up(v) : (off < 0 ? next_float_down(v) : v)` (math.rs:123-129) as one select chain: for a
+// finite non-zero v both functions add the same +-1 to the bit pattern (the quirk above), they differ only at
+// +-0 and at the infinity each one keeps.  Bit-identical to the nested calls for every (v, off), NaNs included;
+// no branch, so the six origin offsets of a bounce do not split the warp eighteen ways.
+PT_DEV float nudge_along(float v, float off) {
+  const bool is_up = off > 0.0f, is_dn = off < 0.0f, zero = v == 0.0f;
+  const uint32_t base = zero ? (is_up ? 0u : 0x80000000u) : __float_as_uint(v);
+  const uint32_t delta = (zero ? is_up : (v > 0.0f)) ? 1u : 0xffffffffu;
+  const bool keep = (is_up && v == CUDART_INF_F) || (is_dn && v == -CUDART_INF_F) || !(is_up || is_dn);
+  return keep ? v : __uint_as_float(base + delta);
+}
 PT_DEV V3 offset_ray_origin(V3 p, V3 p_error, V3 n, V3 w) {  // math.rs:107-131
   float d = dot(vabs(n), p_error);
   V3 offset = d * n;
   if (dot(w, n) < 0.0f) offset = -offset;
   V3 po = p + offset;
-  po.x = offset.x > 0.0f ? next_float_up(po.x) : (offset.x < 0.0f ? next_float_down(po.x) : po.x);
-  po.y = offset.y > 0.0f ? next_float_up(po.y) : (offset.y < 0.0f ? next_float_down(po.y) : po.y);
-  po.z = offset.z > 0.0f ? next_float_up(po.z) : (offset.z < 0.0f ? next_float_down(po.z) : po.z);
+  po.x = nudge_along(po.x, offset.x);
+  po.y = nudge_along(po.y, offset.y);
+  po.z = nudge_along(po.z, offset.z);
   return po;
 }
 PT_DEV bool solve_linear_system_2x2(float a00, float a01, float a10, float a11, float b0, float b1, float* x0, float* x1) {  // math.rs:149-165

@@ -272,16 +272,25 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const _
         }
       }
     }
-    // both appends of the warp (connect queue with its 96-byte record, next extend queue), atomics in flight together
+    // the appends of the warp (connect queue with its 96-byte record, the rays of those records, next extend
+    // queue): one atomic each, in flight together
     {
+      const uint32_t nfl = push_nee ? __float_as_uint(nee.n3.w) : 0u;
       const uint32_t ma = __ballot_sync(0xffffffffu, push_nee), mb = __ballot_sync(0xffffffffu, push_ext);
-      uint32_t ba = 0, bb = 0;
+      const uint32_t ms = __ballot_sync(0xffffffffu, (nfl & PT_NEE_SHADOW) != 0), mm = __ballot_sync(0xffffffffu, (nfl & PT_NEE_MIS) != 0);
+      uint32_t ba = 0, bb = 0, br = 0;
       if (lane == 0) {
-        if (ma) ba = atomicAdd(&ctr->n_nee, (uint32_t)__popc(ma));
+        if (ma) {
+          const unsigned long long both = atomicAdd(reinterpret_cast<unsigned long long*>(&ctr->n_nee),
+                                                    (unsigned long long)__popc(ma) | ((unsigned long long)(__popc(ms) + __popc(mm)) << 32));
+          ba = (uint32_t)both;
+          br = (uint32_t)(both >> 32);
+        }
         if (mb) bb = atomicAdd(&ctr_next->n_ext, (uint32_t)__popc(mb));
       }
       ba = __shfl_sync(0xffffffffu, ba, 0);
       bb = __shfl_sync(0xffffffffu, bb, 0);
+      br = __shfl_sync(0xffffffffu, br, 0);
       const uint32_t lt = (1u << lane) - 1u;
       if (push_nee) {
         const uint32_t k = ba + __popc(ma & lt);
@@ -290,6 +299,8 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const _
         st256(dst, F8{nee.n0, nee.n1});
         st256(dst + 1, F8{nee.n2, nee.n3});
         st256(dst + 2, F8{nee.n4, nee.n5});
+        if (nfl & PT_NEE_SHADOW) P.q_ray[br + __popc(ms & lt)] = 2u * k;
+        if (nfl & PT_NEE_MIS) P.q_ray[br + __popc(ms) + __popc(mm & lt)] = 2u * k + 1u;
       }
       if (push_ext) q_ext_next[bb + __popc(mb & lt)] = p;
     }

@@ -63,18 +63,18 @@ __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) extend_kernel(const 
 }
 
 // ---- connect ---------------------------------------------------------------------------------------
-// Rays of estimate_direct for every pending record: work item 2i is the shadow segment of record i
-// (integrator.rs:66-78, light.rs:39-41, any-hit), item 2i+1 its BSDF-sampled MIS ray (integrator.rs:113-135,
-// closest hit).  The kernel only traces: what was found goes to nee_res[i], and connect_resolve_kernel
+// Rays of estimate_direct for the pending records: shade lists in q_ray the rays that exist, 2 * record for a
+// shadow segment (integrator.rs:66-78, light.rs:39-41, any-hit), 2 * record + 1 for a BSDF-sampled MIS ray
+// (integrator.rs:113-135, closest hit), so every work item is a ray and no lane idles on an absent one.  The kernel only traces: what was found goes to nee_res[i], and connect_resolve_kernel
 // (k_misc.cu) evaluates emitted radiance and adds the bounce's direct lighting at full warp width.
 struct ConnectWork {
   const PathArrays& P;
   uint32_t n_shadow, n_mis;
+  uint32_t cur;  // 2 * record + kind of the ray in hand
   __device__ bool begin(uint32_t i, LaneRay* r) {
-    const uint32_t rec = i >> 1;
-    const uint32_t nf = __float_as_uint(P.nee[rec].n3.w);
-    if (i & 1u) {
-      if (!(nf & PT_NEE_MIS)) return false;
+    cur = P.q_ray[i];
+    const uint32_t rec = cur >> 1;
+    if (cur & 1u) {
       const F8 n23 = ld256(reinterpret_cast<const F8*>(&P.nee[rec].n2));
       r->o = mk3(n23.a);
       r->d = mk3(n23.b);
@@ -82,7 +82,6 @@ struct ConnectWork {
       r->any_hit = false;
       ++n_mis;
     } else {
-      if (!(nf & PT_NEE_SHADOW)) return false;
       const F8 n01 = ld256(reinterpret_cast<const F8*>(&P.nee[rec].n0));
       r->o = mk3(n01.a);
       r->d = mk3(n01.b);
@@ -92,9 +91,9 @@ struct ConnectWork {
     }
     return true;
   }
-  __device__ bool end(uint32_t i, const DevHit& h, bool found, LaneRay*) {
-    NeeRes* res = P.nee_res + (i >> 1);
-    if (i & 1u) *reinterpret_cast<float4*>(res) = make_float4(__int_as_float(found ? h.prim : -1), h.b0, h.b1, h.b2);
+  __device__ bool end(uint32_t, const DevHit& h, bool found, LaneRay*) {
+    NeeRes* res = P.nee_res + (cur >> 1);
+    if (cur & 1u) *reinterpret_cast<float4*>(res) = make_float4(__int_as_float(found ? h.prim : -1), h.b0, h.b1, h.b2);
     else res->occluded = found ? 1u : 0u;
     return false;
   }
@@ -103,8 +102,8 @@ struct ConnectWork {
 template <bool COUNT>
 __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) connect_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ PathArrays P, RoundCounters* ctr, GlobalCounters* g) {
   uint32_t c_nodes = 0, c_tris = 0;
-  ConnectWork w{P, 0u, 0u};
-  trace_stream<COUNT>(sc, 2u * ctr->n_nee, &ctr->t_nee, w, &c_nodes, &c_tris);
+  ConnectWork w{P, 0u, 0u, 0u};
+  trace_stream<COUNT>(sc, ctr->n_ray, &ctr->t_ray, w, &c_nodes, &c_tris);
   warp_sum_add(w.n_shadow, &g->shadow_rays);
   warp_sum_add(w.n_mis, &g->mis_rays);
   if (COUNT) {

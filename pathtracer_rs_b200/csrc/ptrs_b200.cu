@@ -120,6 +120,7 @@ struct Workspace {
   DevBuf<NeeRec> nee;
   DevBuf<NeeRes> nee_res;
   DevBuf<int> q_ext[2], q_nee, q_class;
+  DevBuf<uint32_t> q_ray;
   DevBuf<RoundCounters> counters;
   DevBuf<GlobalCounters> gcount;
   PathArrays arrays() {
@@ -129,10 +130,11 @@ struct Workspace {
     a.q_hit = q_hit.p;
     a.nee = nee.p;
     a.nee_res = nee_res.p;
+    a.q_ray = q_ray.p;
     return a;
   }
   uint64_t bytes() const {
-    return (uint64_t)cap * (sizeof(PathSlot) + 16 + sizeof(NeeRec) + sizeof(NeeRes) + 4 * 3 + (4 + 16) * PT_N_CLASSES) + (uint64_t)rounds * sizeof(RoundCounters);
+    return (uint64_t)cap * (sizeof(PathSlot) + 16 + sizeof(NeeRec) + sizeof(NeeRes) + 4 * 5 + (4 + 16) * PT_N_CLASSES) + (uint64_t)rounds * sizeof(RoundCounters);
   }
 };
 
@@ -279,6 +281,7 @@ int32_t ensure_workspace(PtrsScene* s, uint32_t cap, uint32_t rounds) {
   WS_ALLOC(w.q_ext[0], cap);
   WS_ALLOC(w.q_ext[1], cap);
   WS_ALLOC(w.q_nee, cap);
+  WS_ALLOC(w.q_ray, (size_t)cap * 2);
   WS_ALLOC(w.q_class, (size_t)cap * PT_N_CLASSES);
   WS_ALLOC(w.counters, rounds + 1);
   WS_ALLOC(w.gcount, 1);

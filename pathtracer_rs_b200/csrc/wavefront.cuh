@@ -17,6 +17,7 @@
 //
 // Path state: 64-byte slot records + queue-ordered payloads, see PathArrays below.
 #pragma once
+#include <cstddef>
 #include "dev_shading.cuh"
 #include "dev_sobol.cuh"
 
@@ -72,6 +73,7 @@ struct PathArrays {
   float4* q_hit;    // PT_N_CLASSES x cap, aligned with the class queues
   NeeRec* nee;      // cap, aligned with the connect queue
   NeeRes* nee_res;  // cap, aligned with the connect queue
+  uint32_t* q_ray;  // 2 x cap: the rays the connect stage has to trace, 2 * record + {0 shadow segment, 1 MIS ray}
 };
 #define PT_F_SPECULAR (1u << 16)
 #define PT_F_HAS_DIFF (1u << 17)
@@ -118,10 +120,13 @@ PT_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];"
 struct RoundCounters {
   uint32_t n_ext;                  // length of the extend queue of this round
   uint32_t n_class[PT_N_CLASSES];  // lengths of the per-material shade queues
-  uint32_t n_nee;                  // length of the connect queue
-  uint32_t t_ext, t_class[PT_N_CLASSES], t_nee;  // work tickets
-  uint32_t pad[32 - 4 - 2 * PT_N_CLASSES];  // 128 B per round
+  // connect stage: direct-lighting records and the rays of those records (q_ray).  The pair is one 8-byte
+  // aligned word so that shade reserves both with a single 64-bit atomicAdd (records in the low half).
+  uint32_t n_nee, n_ray;
+  uint32_t t_ext, t_class[PT_N_CLASSES], t_nee, t_ray;  // work tickets
+  uint32_t pad[32 - 6 - 2 * PT_N_CLASSES];  // 128 B per round
 };
+static_assert(offsetof(RoundCounters, n_nee) % 8 == 0 && sizeof(RoundCounters) == 128, "RoundCounters layout");
 
 struct GlobalCounters {
   unsigned long long shadow_rays, mis_rays, nodes_tested, tris_tested, nee_nodes_tested, nee_tris_tested;

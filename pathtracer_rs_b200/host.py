@@ -65,6 +65,7 @@ def lib():
         L.ptrs_host_save_hdr.argtypes = [C.c_char_p, fp, i32, i32]
         L.ptrs_host_load_png.argtypes = [C.c_char_p, ip, ip, ip, C.POINTER(C.c_uint8)]
         L.ptrs_host_save_png.argtypes = [C.c_char_p, C.POINTER(C.c_uint8), i32, i32, i32]
+        L.ptrs_host_decode_image.argtypes = [C.POINTER(C.c_uint8), C.c_size_t, ip, ip, ip, C.POINTER(C.c_uint8)]
         L.ptrs_host_snake_case.argtypes = [C.c_char_p, C.c_char_p, i32]
         u8p = C.POINTER(C.c_uint8)
         L.ptrs_host_tev_create_image.restype = C.c_int64
@@ -192,6 +193,16 @@ def load_png(path):
     _img_check(lib().ptrs_host_load_png(os.fsencode(path), C.byref(w), C.byref(h), C.byref(c), None))
     out = np.empty((h.value, w.value, c.value), dtype=np.uint8)
     _img_check(lib().ptrs_host_load_png(os.fsencode(path), C.byref(w), C.byref(h), C.byref(c), out.ctypes.data_as(C.POINTER(C.c_uint8))))
+    return out
+
+
+def decode_image(data):
+    """PNG or JPEG bytes -> (h, w, c) uint8, what image::open gives the importers."""
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    w, h, c = C.c_int(0), C.c_int(0), C.c_int(0)
+    _img_check(lib().ptrs_host_decode_image(buf, len(data), C.byref(w), C.byref(h), C.byref(c), None))
+    out = np.empty((h.value, w.value, c.value), dtype=np.uint8)
+    _img_check(lib().ptrs_host_decode_image(buf, len(data), C.byref(w), C.byref(h), C.byref(c), out.ctypes.data_as(C.POINTER(C.c_uint8))))
     return out
 
 

@@ -204,6 +204,16 @@ int ptrs_host_load_png(const char* path, int* w, int* h, int* channels, uint8_t*
     if (out) std::memcpy(out, img.data.data(), img.data.size());
   });
 }
+// PNG or JPEG bytes -> 8-bit pixels; call with out == NULL first for the size
+int ptrs_host_decode_image(const uint8_t* bytes, size_t n, int* w, int* h, int* channels, uint8_t* out) {
+  return guard([&] {
+    const ImageU8 img = decode_image(bytes, n);
+    *w = img.width;
+    *h = img.height;
+    *channels = img.channels;
+    if (out) std::memcpy(out, img.data.data(), img.data.size());
+  });
+}
 int ptrs_host_save_png(const char* path, const uint8_t* pixels, int w, int h, int channels) {
   return guard([&] { save_png(path, pixels, w, h, channels); });
 }

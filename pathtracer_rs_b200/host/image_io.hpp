@@ -1,7 +1,7 @@
 // Image files on either side of the rendering path:
 //   Radiance .hdr (RGBE) in   what InfiniteAreaLight::new reads through image::hdr::HdrDecoder
 //                              (src/pathtracer/light.rs:331-346; image 0.23.14, not in the checkout)
-//   8-bit PNG in               Mitsuba <texture type="bitmap"> / glTF images (image::open(..) -> ImageRgb8)
+//   8-bit PNG / JPEG in        Mitsuba <texture type="bitmap"> / glTF images (image::open(..) -> ImageRgb8)
 //   8-bit PNG out              camera.film.to_rgba_image().save("render.png") (src/headless.rs:222, 231)
 // zlib does the DEFLATE part; everything else (chunks, filters, CRC, RGBE run-length coding) is here.
 #pragma once
@@ -33,6 +33,12 @@ ImageU8 load_png(const std::string& path);
 ImageU8 decode_png(const uint8_t* bytes, size_t n);
 std::vector<uint8_t> encode_png(const uint8_t* pixels, int width, int height, int channels);
 void save_png(const std::string& path, const uint8_t* pixels, int width, int height, int channels);
+
+// JPEG (jpeg_decode.cpp): baseline / extended-sequential / progressive Huffman, 8-bit, grey or YCbCr / RGB.
+ImageU8 decode_jpeg(const uint8_t* bytes, size_t n);
+// what image::open does for the importers: the format is sniffed from the first bytes (PNG or JPEG)
+ImageU8 decode_image(const uint8_t* bytes, size_t n);
+ImageU8 load_image(const std::string& path);
 
 std::vector<uint8_t> read_file(const std::string& path);
 

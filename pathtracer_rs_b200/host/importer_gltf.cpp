@@ -2,7 +2,7 @@
 // (camera) and src/pathtracer/importer/gltf.rs (materials :171-289, meshes :291-383, node walk and lights :385-503,
 // scene assembly :505-584).  The reference reads the file through the `gltf` crate (1.0, not in the checkout:
 // accessor decoding, TRS / matrix node transforms, KHR_lights_punctual, KHR_materials_transmission / _ior) and
-// decodes images with `image`; here PNG images are supported, JPEG ones raise an error when a material uses them.
+// decodes images with `image`; here PNG and JPEG images are decoded (image_io.cpp, jpeg_decode.cpp).
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -283,8 +283,7 @@ struct Importer {
       if (off + len > buffers[(size_t)buf].size()) bad("image bufferView runs past the end of its buffer");
       bytes.assign(buffers[(size_t)buf].begin() + off, buffers[(size_t)buf].begin() + off + len);
     }
-    if (bytes.size() >= 3 && bytes[0] == 0xFF && bytes[1] == 0xD8) bad("JPEG images are not supported (image " + std::to_string(idx) + "): convert to PNG");
-    return image_cache.emplace(idx, decode_png(bytes.data(), bytes.size())).first->second;
+    return image_cache.emplace(idx, decode_image(bytes.data(), bytes.size())).first->second;
   }
   struct TexRef {
     long image;

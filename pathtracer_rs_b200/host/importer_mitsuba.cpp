@@ -143,7 +143,7 @@ struct Importer {
                                    need(p.f, "uoffset", "checkerboard"), need(p.f, "voffset", "checkerboard"));
     }
     if (type == "bitmap") {
-      const ImageU8 img = load_png(sibling_path(path, need(p.s, "filename", "bitmap")));
+      const ImageU8 img = load_image(sibling_path(path, need(p.s, "filename", "bitmap")));
       if (img.channels != 3) bad("unsupported image format for texture");  // only DynamicImage::ImageRgb8
       std::vector<float> f(img.data.size());
       for (size_t k = 0; k < f.size(); ++k) f[k] = 1.0f * inverse_gamma_correct((float)img.data[k] / 255.0f);

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const _
       }
       bool alive = bounces < rc.max_depth;  // integrator.rs:429
       if (alive) {
-        if (flags & PT_F_HAS_DIFF) {  // compute_scattering_functions -> compute_differentials
+        if ((flags & PT_F_HAS_DIFF) && sc.uses_differentials) {  // compute_scattering_functions -> compute_differentials
           RayDiff rd;
           V3 o, d;
           camera_ray(rc.cam, pa.fx, pa.fy, rc.diff_scale, &o, &d, &rd.rx_d, &rd.ry_d);

@@ -690,6 +690,15 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
   v.n_prims = d->n_prims;
   v.n_lights = d->n_lights;
   v.n_infinite_lights = d->n_infinite_lights;
+  v.uses_differentials = 0;
+  for (uint32_t i = 0; i < d->n_materials; ++i) {
+    static const int n_tex[PTRS_MAT_COUNT] = {1, 0, 3, 5, 4, 4};
+    const PtrsMaterial& m = d->materials[i];
+    for (int k = 0; k < n_tex[m.type]; ++k) v.uses_differentials |= d->textures[m.tex[k]].type == PTRS_TEX_IMAGE;
+    if (m.normal_map >= 0) v.uses_differentials |= d->textures[m.normal_map].type == PTRS_TEX_IMAGE;
+  }
+  for (uint32_t i = 0; i < d->n_lights; ++i)  // emitted radiance at a camera-ray hit is looked up with the hit's differentials
+    if (d->lights[i].type == PTRS_LIGHT_AREA) v.uses_differentials |= d->textures[d->lights[i].ke_tex].type == PTRS_TEX_IMAGE;
   if (!device_bvh && d->n_nodes > 0) {
     std::memcpy(s->world_bound, d->nodes[0].bounds_min, 12);
     std::memcpy(s->world_bound + 3, d->nodes[0].bounds_max, 12);

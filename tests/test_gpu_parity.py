@@ -209,7 +209,7 @@ def test_error_behaviour(gpu, host, cornell):
 
 def test_headless_cli_renders_the_xml_scene(gpu, host, tmp_path):
     """examples/headless (the stand-in for `pathtracer-rs SCENE -o out --headless -r WxH -s N -d D`, src/main.rs) on the
-    Cornell XML fixture == the same render through the Python mirror of the interface, byte for byte."""
+    Cornell XML fixture == the same render through the Python mirror of the interface (same PNG up to float-atomic order)."""
     import subprocess
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -226,7 +226,10 @@ def test_headless_cli_renders_the_xml_scene(gpu, host, tmp_path):
     film = gpu.Film(cam.width, cam.height)
     integ.render(cam, scene, film)
     assert png.shape == (80, 96, 4)
-    assert np.array_equal(png, film.to_rgba_image())
+    # two renders differ in the last bits of the film sums (float atomics commute, they do not associate), which can
+    # move a value across an 8-bit rounding boundary: at most one level, on a handful of the 30 720 bytes
+    diff = np.abs(png.astype(np.int32) - film.to_rgba_image().astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).sum() <= 8
     scene.close()
 
 
@@ -355,17 +358,27 @@ def test_imported_gltf_scene_renders_like_the_oracle(gpu, host, oracle, tmp_path
     scene.close()
 
 
-def test_full_size_bench_workload_properties(gpu, host, oracle):
-    """BASELINE configs[1] at full size (Cornell + env map, 1024 x 1024, 64 spp, depth 15: 67.6 M camera paths), where the
-    oracle is too slow to run whole.  Size-independent properties: the path count of §8; the film's weight channel (a pure
-    function of the Sobol film positions) equals the oracle's on a band of rows; two sample shards sum to the whole
-    render (the multi-GPU decomposition); a render is reproducible; and a 16 x 16-tile sample of the image matches the oracle."""
-    flat, cam = host.make_scene(host.SCENE_CORNELL_ENV, seed=1, res=(1024, 1024))
+FULL_SIZE = {
+    # name: (scene, triangles, resolution, spp, oracle tile stride, camera paths)
+    "c2_cornell_env": ("SCENE_CORNELL_ENV", 0, (1024, 1024), 64, 61, 1028 * 1028 * 64),
+    "c3_material_field_1m": ("SCENE_MATERIAL_FIELD", 1_000_000, (1920, 1080), 256, 83, 1924 * 1084 * 256),
+    "c5_atrium_4k_64spp": ("SCENE_ATRIUM", 262_144, (3840, 2160), 64, 331, 3844 * 2164 * 64),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FULL_SIZE))
+def test_full_size_workload_properties(gpu, host, oracle, name):
+    """BASELINE configs[1], [2] and [4] at full resolution (C2 and C3 at their full sample counts: 67.6 M and 533.9 M
+    camera paths; C5's 4K frame at 64 of its 1024 spp), where the oracle is too slow to run whole.  Size-independent
+    properties: the path count of SURVEY.md §8; two sample shards sum to the whole render (the multi-GPU decomposition);
+    a render is reproducible; and a strided sample of 16 x 16 tiles of the image, all spp, matches the oracle."""
+    kind, n_tris, res, spp, tile_stride, n_paths = FULL_SIZE[name]
+    flat, cam = host.make_scene(getattr(host, kind), seed=1, n_tris=n_tris, res=res)
     scene = gpu.RenderScene(flat)
-    integ = gpu.PathIntegrator(gpu.SamplerBuilder(64), max_depth=15)
+    integ = gpu.PathIntegrator(gpu.SamplerBuilder(spp), max_depth=15)
     full = gpu.Film(cam.width, cam.height)
     st = integ.render(cam, scene, full)
-    assert st["camera_paths"] == 1028 * 1028 * 64 == 67_634_176
+    assert st["camera_paths"] == n_paths
     a = full.download()
     assert np.isfinite(a).all() and (a[..., 3] > 0).all() and (a[..., :3] >= 0).all()
     parts = gpu.Film(cam.width, cam.height)
@@ -374,11 +387,13 @@ def test_full_size_bench_workload_properties(gpu, host, oracle):
     b = parts.download()
     assert np.allclose(a[..., 3], b[..., 3], rtol=1e-5)  # weights: same terms, different order
     assert _rel_mse(b[..., :3] / b[..., 3:], a[..., :3] / a[..., 3:]) < 1e-9
+    del parts, b
     again = gpu.Film(cam.width, cam.height)
     integ.render(cam, scene, again)
-    assert np.allclose(again.download(), a, rtol=2e-5, atol=1e-6)  # atomics reorder the float sums, nothing else
-    # the oracle on every 61st 16 x 16 tile (70 tiles, all 64 spp) — full-resolution Sobol indices, m = 11
-    ref_film, ref_st = oracle.render(flat, cam, integ.params, tile_stride=61)
+    assert np.allclose(again.download(), a, rtol=2e-5, atol=1e-5 * float(a[..., :3].max()))  # atomics reorder the float sums, nothing else
+    del again
+    # the oracle on every tile_stride-th 16 x 16 tile (about 100 tiles, all spp) — full-resolution Sobol indices
+    ref_film, ref_st = oracle.render(flat, cam, integ.params, tile_stride=tile_stride)
     touched = ref_film[..., 3] > 0
     assert touched.sum() > 10000
     inner = touched & np.isclose(ref_film[..., 3], a[..., 3], rtol=1e-5)  # pixels whose whole footprint lies in sampled tiles

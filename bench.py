@@ -9,9 +9,10 @@ A step = one full render of the workload (67.6 M camera paths) accumulated into 
   value     paths/s with scene and film resident in HBM (CUDA events on the launching stream)
   e2e       the same through the C ABI with HOST buffers: ptrs_scene_create from host arrays, render,
             ptrs_film_download — host<->device copies inside the timed region
-  roofline  extend kernel (closest-hit BVH traversal): algorithmic bytes (32 B x nodes tested + 36 B x
-            triangles tested + 28 B ray + 20 B hit) / its summed launch time, against the
-            measured HBM copy bandwidth in MEASURED_PEAKS.json
+  roofline  extend kernel (closest-hit BVH traversal, the kernel BASELINE.json's "% of L2/HBM roofline" is about):
+            algorithmic bytes (32 B x nodes tested + 36 B x triangles tested + 28 B ray + 20 B hit)
+            / its summed launch time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json;
+            roofline.stages adds the connect and shade stages the same way (shade is the largest share on C2)
   cpu_baseline  the C++ oracle (a restatement of the reference's rayon integrator; the Rust crate cannot
             be built in this image) on a bounded, strided sample of the same workload's 16x16 tiles
 Multi-GPU (weak scaling): rank g renders Sobol sample numbers {s : s mod N == g} of a 64*N-spp render of
@@ -345,6 +346,24 @@ def run_gpu(args):
                 "bytes_per_ray": alg_bytes / ext_rays, "nodes_per_ray": st_count["nodes_tested"] / ext_rays,
                 "tris_per_ray": st_count["tris_tested"] / ext_rays, "share_of_step": float(np.mean(ext_ms)) / (sum(step_ms) / len(step_ms)),
                 "note": f"scene ({flat.n_prims} triangles, {flat.n_nodes} nodes) is cache resident (L1/L2): the HBM-bound case is bvh_microbench"}
+
+    # the other two stages next to it, so the line shows where the rest of the step goes: the connect stage by the
+    # same traversal byte count (ms_shadow also contains connect_resolve), the shade stage by its record traffic
+    # (84 B in: queue entry, hit, 64 B path slot; up to 176 B out: slot, 96 B direct-lighting record, queue entries)
+    step_mean = sum(step_ms) / len(step_ms)
+    nee_rays = st_count["shadow_rays"] + st_count["mis_rays"]
+    nee_bytes = 32 * st_count["nee_nodes_tested"] + 36 * st_count["nee_tris_tested"] + 32 * nee_rays + 1 * st_count["shadow_rays"] + 16 * st_count["mis_rays"]
+    shade_bytes = (84 + 176) * ext_rays
+    stages = {
+        "extend": {"ms": float(np.mean(ext_ms)), "share_of_step": float(np.mean(ext_ms)) / step_mean, "achieved_gbs": achieved, "frac": achieved / peak_gbs},
+        "connect+resolve": {"ms": stats["ms_shadow"], "share_of_step": stats["ms_shadow"] / step_mean,
+                            "achieved_gbs": nee_bytes / (stats["ms_shadow"] * 1e-3) / 1e9, "frac": nee_bytes / (stats["ms_shadow"] * 1e-3) / 1e9 / peak_gbs,
+                            "nodes_per_ray": st_count["nee_nodes_tested"] / max(1, nee_rays)},
+        "shade (all materials + miss)": {"ms": stats["ms_shade"], "share_of_step": stats["ms_shade"] / step_mean,
+                                         "achieved_gbs": shade_bytes / (stats["ms_shade"] * 1e-3) / 1e9, "frac": shade_bytes / (stats["ms_shade"] * 1e-3) / 1e9 / peak_gbs,
+                                         "note": "latency bound (dependent scene / table loads at 16 warps per SM), not a bandwidth kernel; upper-bound bytes"},
+    }
+    roofline["stages"] = stages
 
     # ---- CPU baseline: the oracle on a bounded sample of the same workload ----------------------------
     cpu = None

@@ -90,13 +90,22 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def host_threads():
+    """Threads the CPU arm uses: every core this process may run on.  Passed explicitly because torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would silently make the reference arm single-threaded."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_sample_plan(oracle, flat, cam, params, target_s=12.0):
     """Pick a tile stride so that the oracle renders a uniform subset of the workload's 16x16 tiles in
     roughly target_s seconds on this host."""
     n_tiles = oracle.tile_count(cam, params)
     probe_stride = max(1, n_tiles // 64)
     t0 = time.perf_counter()
-    _, st = oracle.render(flat, cam, params, tile_stride=probe_stride)
+    _, st = oracle.render(flat, cam, params, n_threads=host_threads(), tile_stride=probe_stride)
     dt = time.perf_counter() - t0
     per_tile = dt / max(1, (n_tiles + probe_stride - 1) // probe_stride)
     want = max(16, int(target_s / max(per_tile, 1e-9)))
@@ -119,13 +128,13 @@ def run_reference(args):
     flat, cam = host.make_scene(getattr(host, w["scene"]), seed=1, n_tris=w["n_tris"], res=w["res"])
     params = host.default_render_params(spp=w["spp"], max_depth=w["max_depth"])
     n_tiles, stride = cpu_sample_plan(oracle, flat, cam, params, target_s=8.0)
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     for _ in range(args.warmup):
-        oracle.render(flat, cam, params, tile_stride=stride * 8)
+        oracle.render(flat, cam, params, n_threads=cores, tile_stride=stride * 8)
     times, paths, rays = [], 0, 0
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        _, st = oracle.render(flat, cam, params, tile_stride=stride)
+        _, st = oracle.render(flat, cam, params, n_threads=cores, tile_stride=stride)
         times.append(time.perf_counter() - t0)
         paths = st["camera_paths"]
         rays = st["extension_rays"] + st["shadow_rays"] + st["mis_rays"]
@@ -373,9 +382,9 @@ def run_gpu(args):
         p1 = host.default_render_params(spp=w["spp"], max_depth=w["max_depth"])
         n_tiles, stride = cpu_sample_plan(oracle, flat, cam, p1, target_s=12.0)
         t0 = time.perf_counter()
-        _, ost = oracle.render(flat, cam, p1, tile_stride=stride)
+        _, ost = oracle.render(flat, cam, p1, n_threads=host_threads(), tile_stride=stride)
         dt = time.perf_counter() - t0
-        cpu = {"value": ost["camera_paths"] / dt, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
+        cpu = {"value": ost["camera_paths"] / dt, "unit": "samples/s", "cores": host_threads(), "kind": "port",
                "sample": f"every {stride}th of the {n_tiles} 16x16 tiles, all {w['spp']} spp ({ost['camera_paths']} camera paths, {dt:.1f} s)",
                "mrays_per_s": (ost["extension_rays"] + ost["shadow_rays"] + ost["mis_rays"]) / dt / 1e6}
 

@@ -14,6 +14,7 @@
 // tree, so visit counts differ, but closest hits do not: the triangle test is the same code on the same vertices.
 #include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "launch.hpp"
 #include "wavefront.cuh"
@@ -274,8 +275,8 @@ __global__ void __launch_bounds__(256) assemble_tris_kernel(uint32_t n, const ui
                                                             const PtrsMesh* __restrict__ meshes, float4* __restrict__ tri_verts, uint4* __restrict__ tri_index,
                                                             uint32_t* __restrict__ inv_perm) {
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const uint32_t i = perm[k];
-    inv_perm[i] = k;
+    const uint32_t i = perm ? perm[k] : k;  // null perm: the caller's order is the BVH order (reference-built tree)
+    if (inv_perm) inv_perm[i] = k;
     const int32_t mesh = prim_mesh[i];
     const PtrsMesh m = meshes[mesh];
     uint32_t meta2 = m.flags & 0xffu;
@@ -287,6 +288,53 @@ __global__ void __launch_bounds__(256) assemble_tris_kernel(uint32_t n, const ui
       tri_verts[3 * (size_t)k + c] = make_float4(__ldg(pos + 3 * (size_t)v[c]), __ldg(pos + 3 * (size_t)v[c] + 1), __ldg(pos + 3 * (size_t)v[c] + 2), __int_as_float(w[c]));
     }
     tri_index[k] = make_uint4(v[0], v[1], v[2], (uint32_t)mesh);
+  }
+}
+
+// index validation of the caller's primitive arrays, so that every later kernel can trust them
+__global__ void __launch_bounds__(256) validate_prims_kernel(uint32_t n, const uint32_t* __restrict__ prim_vertex, const int32_t* __restrict__ prim_mesh,
+                                                             const int32_t* __restrict__ prim_material, const int32_t* __restrict__ prim_area_light,
+                                                             uint32_t n_verts, uint32_t n_meshes, uint32_t n_materials, uint32_t n_lights,
+                                                             uint32_t* __restrict__ err) {
+  uint32_t e = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (prim_mesh[i] < 0 || (uint32_t)prim_mesh[i] >= n_meshes || prim_material[i] < 0 || (uint32_t)prim_material[i] >= n_materials ||
+        prim_area_light[i] >= (int32_t)n_lights)
+      e |= 1u;
+    for (int k = 0; k < 3; ++k)
+      if (prim_vertex[3 * (size_t)i + k] >= n_verts) e |= 2u;
+  }
+  if (e) atomicOr(err, e);
+}
+
+// ---- pair layout of a reference-built tree -------------------------------------------------------------------------
+// The reference's flattened tree (accelerator.rs:348-357) is in depth-first preorder: first child at i + 1, second at
+// `offset`.  The traversal layout places the children of the r-th interior node (in that same order) side by side in
+// slots 2 (r + 1), 2 (r + 1) + 1, so the position of every record follows from an exclusive prefix count of interior
+// nodes: one scan and one scatter pass instead of a serial walk on the host.
+__global__ void __launch_bounds__(256) interior_flag_kernel(const float4* __restrict__ raw, uint32_t n, uint32_t* __restrict__ flag) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    flag[i] = (__float_as_uint(raw[2 * (size_t)i + 1].w) & 0xffffu) == 0 ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) pair_layout_kernel(const float4* __restrict__ raw, uint32_t n, const uint32_t* __restrict__ rank, float4* __restrict__ out) {
+  auto place = [&](uint32_t j, uint32_t slot) {
+    const float4 a = raw[2 * (size_t)j];
+    float4 b = raw[2 * (size_t)j + 1];
+    if ((__float_as_uint(b.w) & 0xffffu) == 0) b.z = __uint_as_float(2u * (rank[j] + 1u));  // interior: where ITS children sit
+    out[2 * (size_t)slot] = a;
+    out[2 * (size_t)slot + 1] = b;
+  };
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (i == 0) {
+      place(0, 0);
+      out[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+      out[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float4 b = raw[2 * (size_t)i + 1];
+    if ((__float_as_uint(b.w) & 0xffffu) != 0) continue;
+    const uint32_t k = 2u * (rank[i] + 1u);
+    place(i + 1, k);
+    place(__float_as_uint(b.z), k + 1);
   }
 }
 
@@ -397,6 +445,55 @@ void launch_assemble_tris(cudaStream_t st, uint32_t n, const uint32_t* perm, con
   if (n == 0) return;
   assemble_tris_kernel<<<148 * 8, 256, 0, st>>>(n, perm, prim_vertex, pos, prim_mesh, prim_material, prim_area_light, meshes, tri_verts, tri_index, inv_perm);
 }
+// returns the error bits of validate_prims_kernel (0 = fine), or a negative cudaError_t
+int validate_prims_on_device(cudaStream_t st, uint32_t n, const uint32_t* prim_vertex, const int32_t* prim_mesh, const int32_t* prim_material,
+                             const int32_t* prim_area_light, uint32_t n_verts, uint32_t n_meshes, uint32_t n_materials, uint32_t n_lights) {
+  if (n == 0) return 0;
+  uint32_t* d_err = nullptr;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&d_err), 4, st);
+  if (e != cudaSuccess) return -(int)e;
+  cudaMemsetAsync(d_err, 0, 4, st);
+  validate_prims_kernel<<<148 * 8, 256, 0, st>>>(n, prim_vertex, prim_mesh, prim_material, prim_area_light, n_verts, n_meshes, n_materials, n_lights, d_err);
+  uint32_t h = 0;
+  e = cudaMemcpyAsync(&h, d_err, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFreeAsync(d_err, st);
+  return e == cudaSuccess ? (int)h : -(int)e;
+}
+
+// d_raw: the n reference-order records on the device; *out receives 2 (n_interior + 1) records in the traversal layout
+int pair_layout_on_device(cudaStream_t st, const float4* d_raw, uint32_t n, uint32_t n_interior, float4** out, uint32_t* n_out) {
+  *out = nullptr;
+  *n_out = 0;
+  if (n == 0) return (int)cudaSuccess;
+  const uint32_t n_dev = 2u * (n_interior + 1u);
+  uint32_t *flag = nullptr, *rank = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flag, rank, (int)n, st);
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&flag), (size_t)n * 4, st);
+  if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&rank), (size_t)n * 4, st);
+  if (e == cudaSuccess) e = cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, st);
+  if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(out), (size_t)n_dev * 32, st);
+  if (e == cudaSuccess) {
+    interior_flag_kernel<<<148 * 8, 256, 0, st>>>(d_raw, n, flag);
+    e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, rank, (int)n, st);
+  }
+  if (e == cudaSuccess) {
+    pair_layout_kernel<<<148 * 8, 256, 0, st>>>(d_raw, n, rank, *out);
+    e = cudaGetLastError();
+  }
+  if (flag) cudaFreeAsync(flag, st);
+  if (rank) cudaFreeAsync(rank, st);
+  if (tmp) cudaFreeAsync(tmp, st);
+  if (e != cudaSuccess && *out) {
+    cudaFreeAsync(*out, st);
+    *out = nullptr;
+  }
+  if (e == cudaSuccess) *n_out = n_dev;
+  return (int)e;
+}
+
 void launch_remap_light_prims(cudaStream_t st, PtrsLight* lights, uint32_t n_lights, const uint32_t* inv_perm) {
   if (n_lights == 0) return;
   remap_light_prims_kernel<<<(n_lights + 127) / 128, 128, 0, st>>>(lights, n_lights, inv_perm);

@@ -468,18 +468,35 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
   std::unique_ptr<PtrsScene> s(new PtrsScene());
   s->device = dev;
   CUDA_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev));
-  // validate indices once on the host so that the kernels can trust them
-  for (uint32_t i = 0; i < d->n_prims; ++i) {
-    if (d->prim_mesh[i] < 0 || (uint32_t)d->prim_mesh[i] >= d->n_meshes || d->prim_material[i] < 0 ||
-        (uint32_t)d->prim_material[i] >= d->n_materials || d->prim_area_light[i] >= (int32_t)d->n_lights)
-      return fail(PTRS_ERR_INVALID_ARGUMENT, "primitive references an out-of-range mesh / material / light");
-    for (int k = 0; k < 3; ++k)
-      if (d->prim_vertex[3 * (size_t)i + k] >= d->n_verts) return fail(PTRS_ERR_INVALID_ARGUMENT, "vertex index out of range");
-  }
-  for (uint32_t i = 0; !device_bvh && i < d->n_nodes; ++i) {
-    const PtrsBvhNode& n = d->nodes[i];
-    if (n.n_prims > 0 ? (uint64_t)n.offset + n.n_prims > d->n_prims : (n.offset >= d->n_nodes || i + 1 >= d->n_nodes || n.axis > 2))
-      return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH node");
+  // The primitive arrays are validated on the device once they are uploaded (validate_prims_on_device below).  The
+  // tree is validated here in one pass: the reference's flattened tree is in depth-first preorder (first child at
+  // i + 1, second at `offset`, accelerator.rs:348-357), so walking the records in index order with a stack of the
+  // second children still owed must consume every record exactly once — which also rules out shared subtrees and
+  // cycles, the only inputs that could keep a traversal kernel from terminating.
+  uint32_t n_interior = 0;
+  if (!device_bvh && d->n_prims > 0) {
+    if (d->n_nodes == 0) return fail(PTRS_ERR_INVALID_ARGUMENT, "missing geometry arrays");
+    std::vector<uint32_t> owed;
+    bool prev_interior = false;
+    for (uint32_t i = 0; i < d->n_nodes; ++i) {
+      const PtrsBvhNode& n = d->nodes[i];
+      if (i > 0 && !prev_interior) {
+        if (owed.empty()) return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH (records after the end of the tree)");
+        if (owed.back() != i) return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH node (second child must follow the first child's subtree)");
+        owed.pop_back();
+      }
+      if (n.n_prims > 0) {
+        if ((uint64_t)n.offset + n.n_prims > d->n_prims) return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH node");
+        prev_interior = false;
+      } else {
+        if (n.offset >= d->n_nodes || i + 1 >= d->n_nodes || n.axis > 2) return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH node");
+        if (n.offset <= i + 1) return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH node (second child must follow the first child's subtree)");
+        owed.push_back(n.offset);
+        prev_interior = true;
+        ++n_interior;
+      }
+    }
+    if (prev_interior || !owed.empty()) return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH (nodes are shared between subtrees)");
   }
   for (uint32_t i = 0; i < d->n_materials; ++i) {
     const PtrsMaterial& m = d->materials[i];
@@ -508,9 +525,10 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
   }
   CUDA_TRY(s->meshes.upload(d->meshes, d->n_meshes));
   CUDA_TRY(s->lights.upload(d->lights, d->n_lights));
-  uint32_t n_dev_nodes = d->n_nodes;
-  if (device_bvh) {
-    // unordered primitives in, BVH built and triangles laid out on the device (k_bvh.cu)
+  uint32_t n_dev_nodes = 0;
+  if (d->n_prims > 0) {
+    // the caller's arrays go up as they are; re-layout (triangles as 3 x float4 with metadata in .w, nodes as 64-byte
+    // sibling pairs) happens on the device
     DevBuf<uint32_t> pv, inv;
     DevBuf<float> pos;
     DevBuf<int32_t> pm, pmat, pal;
@@ -519,97 +537,63 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
     CUDA_TRY(pm.upload(d->prim_mesh, d->n_prims));
     CUDA_TRY(pmat.upload(d->prim_material, d->n_prims));
     CUDA_TRY(pal.upload(d->prim_area_light, d->n_prims));
-    CUDA_TRY(inv.alloc(d->n_prims));
+    const int bad = validate_prims_on_device(0, d->n_prims, pv.p, pm.p, pmat.p, pal.p, d->n_verts, d->n_meshes, d->n_materials, d->n_lights);
+    if (bad < 0) return fail(PTRS_ERR_CUDA, std::string("primitive validation: ") + cudaGetErrorString((cudaError_t)(-bad)));
+    if (bad & 1) return fail(PTRS_ERR_INVALID_ARGUMENT, "primitive references an out-of-range mesh / material / light");
+    if (bad & 2) return fail(PTRS_ERR_INVALID_ARGUMENT, "vertex index out of range");
     CUDA_TRY(s->tri_verts.alloc((size_t)d->n_prims * 3));
     CUDA_TRY(s->tri_index.alloc(d->n_prims));
-    cudaEvent_t e0, e1;
-    CUDA_TRY(cudaEventCreate(&e0));
-    CUDA_TRY(cudaEventCreate(&e1));
-    CUDA_TRY(cudaEventRecord(e0, 0));
-    float4* nodes = nullptr;
-    uint32_t* perm = nullptr;
-    const int be = build_bvh_on_device(0, d->n_prims, pv.p, pos.p, &nodes, &n_dev_nodes, &perm);
-    if (be != (int)cudaSuccess) return fail(PTRS_ERR_CUDA, std::string("device BVH build: ") + cudaGetErrorString((cudaError_t)be));
-    s->nodes.p = nodes;
-    s->nodes.n = (size_t)n_dev_nodes * 2;
-    s->prim_map.p = perm;
-    s->prim_map.n = d->n_prims;
-    launch_assemble_tris(0, d->n_prims, perm, pv.p, pos.p, pm.p, pmat.p, pal.p, s->meshes.p, s->tri_verts.p, s->tri_index.p, inv.p);
-    launch_remap_light_prims(0, s->lights.p, d->n_lights, inv.p);
-    CUDA_TRY(cudaEventRecord(e1, 0));
-    CUDA_TRY(cudaEventSynchronize(e1));
-    CUDA_TRY(cudaGetLastError());
-    cudaEventElapsedTime(&s->bvh_build_ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    s->scene_bytes += (uint64_t)n_dev_nodes * 32 + (uint64_t)d->n_prims * 4;
-    if (n_dev_nodes > 0) {
-      float root[8];
-      CUDA_TRY(cudaMemcpy(root, s->nodes.p, 32, cudaMemcpyDeviceToHost));
-      s->world_bound[0] = root[0];
-      s->world_bound[1] = root[1];
-      s->world_bound[2] = root[2];
-      s->world_bound[3] = root[3];
-      s->world_bound[4] = root[4];
-      s->world_bound[5] = root[5];
-    }
-  }
-  // re-layout: the 32 B node records are kept, but the two children of every interior node are placed side
-  // by side (64 B pairs in depth-first order, root alone in slot 0) so that one traversal step reads one
-  // contiguous 64 B block; triangles become 3 x float4 with metadata in .w
-  if (!device_bvh) {
-    std::vector<PtrsBvhNode> dev_nodes;
-    if (d->n_nodes > 0) {
-      dev_nodes.reserve(2 * (size_t)d->n_nodes);
-      dev_nodes.resize(2);
-      std::memset(dev_nodes.data(), 0, 2 * sizeof(PtrsBvhNode));
-      dev_nodes[0] = d->nodes[0];
-      std::vector<std::pair<uint32_t, uint32_t>> todo;  // (reference index, device index) of interior nodes
-      if (d->nodes[0].n_prims == 0) todo.emplace_back(0u, 0u);
-      uint64_t placed = 1;
-      while (!todo.empty()) {
-        const auto [ri, di] = todo.back();
-        todo.pop_back();
-        const uint32_t left = ri + 1, right = d->nodes[ri].offset;
-        if (right <= left) return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH node (second child must follow the first child's subtree)");
-        placed += 2;
-        if (placed > d->n_nodes) return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH (nodes are shared between subtrees)");
-        const uint32_t k = (uint32_t)dev_nodes.size();
-        dev_nodes.push_back(d->nodes[left]);
-        dev_nodes.push_back(d->nodes[right]);
-        dev_nodes[di].offset = k;
-        // depth-first: the left subtree's pairs follow immediately, so push right first
-        if (d->nodes[right].n_prims == 0) todo.emplace_back(right, k + 1);
-        if (d->nodes[left].n_prims == 0) todo.emplace_back(left, k);
+    if (device_bvh) {
+      // unordered primitives in, BVH built and triangles laid out on the device (k_bvh.cu)
+      CUDA_TRY(inv.alloc(d->n_prims));
+      cudaEvent_t e0, e1;
+      CUDA_TRY(cudaEventCreate(&e0));
+      CUDA_TRY(cudaEventCreate(&e1));
+      CUDA_TRY(cudaEventRecord(e0, 0));
+      float4* nodes = nullptr;
+      uint32_t* perm = nullptr;
+      const int be = build_bvh_on_device(0, d->n_prims, pv.p, pos.p, &nodes, &n_dev_nodes, &perm);
+      if (be != (int)cudaSuccess) return fail(PTRS_ERR_CUDA, std::string("device BVH build: ") + cudaGetErrorString((cudaError_t)be));
+      s->nodes.p = nodes;
+      s->nodes.n = (size_t)n_dev_nodes * 2;
+      s->prim_map.p = perm;
+      s->prim_map.n = d->n_prims;
+      launch_assemble_tris(0, d->n_prims, perm, pv.p, pos.p, pm.p, pmat.p, pal.p, s->meshes.p, s->tri_verts.p, s->tri_index.p, inv.p);
+      launch_remap_light_prims(0, s->lights.p, d->n_lights, inv.p);
+      CUDA_TRY(cudaEventRecord(e1, 0));
+      CUDA_TRY(cudaEventSynchronize(e1));
+      CUDA_TRY(cudaGetLastError());
+      cudaEventElapsedTime(&s->bvh_build_ms, e0, e1);
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      s->scene_bytes += (uint64_t)n_dev_nodes * 32 + (uint64_t)d->n_prims * 4;
+      if (n_dev_nodes > 0) {
+        float root[8];
+        CUDA_TRY(cudaMemcpy(root, s->nodes.p, 32, cudaMemcpyDeviceToHost));
+        s->world_bound[0] = root[0];
+        s->world_bound[1] = root[1];
+        s->world_bound[2] = root[2];
+        s->world_bound[3] = root[3];
+        s->world_bound[4] = root[4];
+        s->world_bound[5] = root[5];
       }
+    } else {
+      // reference-built tree: the 32 B records are kept, but the two children of every interior node are placed side
+      // by side (64 B pairs in depth-first order, root alone in slot 0) so that one traversal step reads one
+      // contiguous 64 B block; boxes, split axes, leaf ranges and the visit order stay those of the reference
+      static_assert(sizeof(PtrsBvhNode) == 32, "LinearBVHNode is 32 bytes");
+      DevBuf<float4> raw;
+      CUDA_TRY(raw.upload(reinterpret_cast<const float4*>(d->nodes), (size_t)d->n_nodes * 2));
+      float4* nodes = nullptr;
+      const int pe = pair_layout_on_device(0, raw.p, d->n_nodes, n_interior, &nodes, &n_dev_nodes);
+      if (pe != (int)cudaSuccess) return fail(PTRS_ERR_CUDA, std::string("BVH re-layout: ") + cudaGetErrorString((cudaError_t)pe));
+      s->nodes.p = nodes;
+      s->nodes.n = (size_t)n_dev_nodes * 2;
+      s->scene_bytes += (uint64_t)n_dev_nodes * 32;
+      launch_assemble_tris(0, d->n_prims, nullptr, pv.p, pos.p, pm.p, pmat.p, pal.p, s->meshes.p, s->tri_verts.p, s->tri_index.p, nullptr);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaStreamSynchronize(0));  // the staging buffers above are released when this scope ends
     }
-    static_assert(sizeof(PtrsBvhNode) == 32, "LinearBVHNode is 32 bytes");
-    CUDA_TRY(s->nodes.upload(reinterpret_cast<const float4*>(dev_nodes.data()), dev_nodes.size() * 2));
-    s->scene_bytes += (uint64_t)dev_nodes.size() * 32;
-    n_dev_nodes = (uint32_t)dev_nodes.size();
-  }
-  if (!device_bvh) {
-    std::vector<float4> tv((size_t)d->n_prims * 3);
-    std::vector<uint4> ti(d->n_prims);
-    for (uint32_t i = 0; i < d->n_prims; ++i) {
-      const PtrsMesh& m = d->meshes[d->prim_mesh[i]];
-      uint32_t meta2 = m.flags & 0xffu;
-      if (m.alpha_tex >= 0) meta2 |= PT_TRI_ALPHA_BIT | ((uint32_t)m.alpha_tex << 9);
-      const int32_t w[3] = {d->prim_material[i], d->prim_area_light[i], (int32_t)meta2};
-      for (int k = 0; k < 3; ++k) {
-        const uint32_t v = d->prim_vertex[3 * (size_t)i + k];
-        float4 f;
-        f.x = d->pos[3 * (size_t)v];
-        f.y = d->pos[3 * (size_t)v + 1];
-        f.z = d->pos[3 * (size_t)v + 2];
-        std::memcpy(&f.w, &w[k], 4);
-        tv[3 * (size_t)i + k] = f;
-      }
-      ti[i] = make_uint4(d->prim_vertex[3 * (size_t)i], d->prim_vertex[3 * (size_t)i + 1], d->prim_vertex[3 * (size_t)i + 2],
-                         (uint32_t)d->prim_mesh[i]);
-    }
-    CUDA_TRY(s->tri_verts.upload(tv.data(), tv.size()));
-    CUDA_TRY(s->tri_index.upload(ti.data(), ti.size()));
   }
   if (d->normal) CUDA_TRY(s->normal.upload(d->normal, (size_t)d->n_verts * 3));
   if (d->tangent) CUDA_TRY(s->tangent.upload(d->tangent, (size_t)d->n_verts * 3));

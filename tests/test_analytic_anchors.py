@@ -1,6 +1,8 @@
 """Analytic anchors for the whole integrator, independent of any reading of the reference: a convex body inside a
 uniform white environment ("white furnace").  Every path that hits the body leaves it after one bounce and sees
-radiance 1, so a Lambertian cube of albedo rho must render as rho, a perfect mirror as 1 and the background as 1 —
+radiance 1, so a Lambertian cube of albedo rho must render as rho, a perfect mirror as 1, a pane of glass as 1
+(Fresnel reflection + transmission lose nothing, the radiance scaling of entering and leaving cancels) and the
+background as 1 —
 whatever the split between light sampling, BSDF sampling, MIS weights and Russian roulette
 (src/pathtracer/integrator.rs:23-139, 401-499), and whatever the env-map importance sampling does
 (light.rs:402-461, sampling.rs:128-230).  Run on the CPU oracle here and on the CUDA path under -m gpu."""
@@ -12,16 +14,21 @@ XML = """<scene version="0.5.0">
     <transform name="toWorld"><matrix value="-1 0 0 0 0 1 0 0.4 0 0 -1 4 0 0 0 1"/></transform>
     <film type="ldrfilm"><integer name="width" value="48"/><integer name="height" value="48"/></film></sensor>
   {bsdf}
-  <shape type="cube"><transform name="toWorld"><matrix value="0.6 0 0.35 0 0 0.7 0 0 -0.35 0 0.6 0 0 0 0 1"/></transform><ref id="m"/></shape>
+  <shape type="cube"><transform name="toWorld"><matrix value="{matrix}"/></transform><ref id="m"/></shape>
   <emitter type="envmap"><string name="filename" value="white.hdr"/><transform name="toWorld"><matrix value="1 0 0 0 0 1 0 0 0 0 1 0 0 0 0 1"/></transform></emitter>
 </scene>"""
 MATTE = '<bsdf type="diffuse" id="m"><rgb name="reflectance" value="0.25, 0.5, 0.75"/></bsdf>'
 MIRROR = '<bsdf type="conductor" id="m"><string name="material" value="none"/></bsdf>'
+GLASS = '<bsdf type="dielectric" id="m"><float name="intIOR" value="1.5"/><float name="extIOR" value="1"/></bsdf>'
+CUBE = "0.6 0 0.35 0 0 0.7 0 0 -0.35 0 0.6 0 0 0 0 1"  # rotated about y, convex: one bounce and out
+SLAB = "0.9 0 0 0 0 0.9 0 0.3 0 0 0.04 0 0 0 0 1"  # a thin pane facing the camera: in through one face, out through the other
+CASES = [(MATTE, CUBE, (0.25, 0.5, 0.75), 8), (MIRROR, CUBE, (1.0, 1.0, 1.0), 8), (GLASS, SLAB, (1.0, 1.0, 1.0), 30)]
+IDS = ["matte", "mirror", "glass_pane"]
 
 
-def _scene(host, tmp_path, bsdf):
+def _scene(host, tmp_path, bsdf, matrix):
     host.save_hdr(str(tmp_path / "white.hdr"), np.ones((8, 16, 3), dtype=np.float32))
-    (tmp_path / "f.xml").write_text(XML.format(bsdf=bsdf))
+    (tmp_path / "f.xml").write_text(XML.format(bsdf=bsdf, matrix=matrix))
     return host.import_scene(str(tmp_path / "f.xml"), res=(48, 48))
 
 
@@ -44,21 +51,21 @@ def _check(host, cam, flat, rgb, intersect, expect_on_body):
     assert np.allclose(on, np.broadcast_to(expect_on_body, on.shape), rtol=0.12)
 
 
-@pytest.mark.parametrize("bsdf,expect", [(MATTE, (0.25, 0.5, 0.75)), (MIRROR, (1.0, 1.0, 1.0))], ids=["matte", "mirror"])
-def test_white_furnace_oracle(host, oracle, tmp_path, bsdf, expect):
-    flat, cam = _scene(host, tmp_path, bsdf)
-    params = host.default_render_params(spp=64, max_depth=8)
+@pytest.mark.parametrize("bsdf,matrix,expect,depth", CASES, ids=IDS)
+def test_white_furnace_oracle(host, oracle, tmp_path, bsdf, matrix, expect, depth):
+    flat, cam = _scene(host, tmp_path, bsdf, matrix)
+    params = host.default_render_params(spp=64, max_depth=depth)
     film, _ = oracle.render(flat, cam, params)
     rgb = film[..., :3] / film[..., 3:]
     _check(host, cam, flat, rgb, lambda r: oracle.intersect(flat, r)[0], np.array(expect, dtype=np.float32))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("bsdf,expect", [(MATTE, (0.25, 0.5, 0.75)), (MIRROR, (1.0, 1.0, 1.0))], ids=["matte", "mirror"])
-def test_white_furnace_gpu(gpu, host, tmp_path, bsdf, expect):
-    flat, cam = _scene(host, tmp_path, bsdf)
+@pytest.mark.parametrize("bsdf,matrix,expect,depth", CASES, ids=IDS)
+def test_white_furnace_gpu(gpu, host, tmp_path, bsdf, matrix, expect, depth):
+    flat, cam = _scene(host, tmp_path, bsdf, matrix)
     scene = gpu.RenderScene(flat)
-    integ = gpu.PathIntegrator(gpu.SamplerBuilder(64), max_depth=8)
+    integ = gpu.PathIntegrator(gpu.SamplerBuilder(64), max_depth=depth)
     film = gpu.Film(cam.width, cam.height)
     integ.render(cam, scene, film)
     a = film.download()

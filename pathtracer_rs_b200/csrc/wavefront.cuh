@@ -9,10 +9,12 @@
 //     queue per material class with ballot-aggregated atomics (one atomic per class per warp), so
 //     every shade<MAT> launch runs warps that are uniform in material code (material sorting)
 //   * shade emits at most three rays per path and bounce — the extension ray into the next round's
-//     extend queue, the NEE shadow segment and the MIS ray into the connect queue
-//   * connect traces the shadow (any-hit) and MIS (closest-hit) rays of a path in ONE thread and adds
-//     beta * n_lights * (Ld_light + Ld_bsdf) to the path's radiance: a single writer per path per
-//     launch keeps the float summation order of integrator.rs:443-447 (deterministic images)
+//     extend queue, the NEE shadow segment and the MIS ray as one direct-lighting record in the connect
+//     queue plus one q_ray entry per ray that exists
+//   * connect traces the listed shadow (any-hit) and MIS (closest-hit) rays, one ray per work item;
+//     connect_resolve then adds beta * n_lights * (Ld_light + Ld_bsdf) to the path's radiance, one thread
+//     per record: a single writer per path per launch keeps the float summation order of
+//     integrator.rs:443-447
 //   * per-round counters (queue lengths, tickets) live in one zero-initialised block per batch
 //
 // Path state: 64-byte slot records + queue-ordered payloads, see PathArrays below.

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-1 (session 3) profiling pass, run under gpurun.  usage: tools/ncu_r1_s3.sh <tag>
+# Profiling pass of a round, run under gpurun.  usage: tools/ncu_round.sh <tag>
 #  0. the plain bench line (no profiler)
 #  1. launch list (gpu__time_duration) of the bench command itself, CPU baseline and microbench legs switched off
 #  2. DRAM bytes of every extend launch of a 64-spp render (metrics-only pass) -> roofline.traffic

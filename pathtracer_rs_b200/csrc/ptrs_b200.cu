@@ -930,8 +930,12 @@ static int32_t render_impl(PtrsScene* s, const PtrsCamera* cam, const PtrsRender
   float ms[5] = {0, 0, 0, 0, 0};
   uint64_t ext_rays = 0, paths = 0;
   CUDA_TRY(cudaEventRecord(s->ev[0], st));
-  for (uint64_t base = 0; base < total; base += s->ws.cap) {
-    const uint32_t n_work = (uint32_t)std::min<uint64_t>(s->ws.cap, total - base);
+  // equal batches (whole 8x4 blocks) rather than full ones and a remainder: a nearly empty last batch would
+  // still pay for every round's launches
+  const uint64_t n_batches = (total + s->ws.cap - 1) / s->ws.cap;
+  const uint64_t per_batch = n_batches ? std::min<uint64_t>(s->ws.cap, (((total + n_batches - 1) / n_batches) + 31) & ~(uint64_t)31) : 0;
+  for (uint64_t base = 0; base < total; base += per_batch) {
+    const uint32_t n_work = (uint32_t)std::min<uint64_t>(per_batch, total - base);
     r = run_batch(s, rc, base, n_work, list_xy ? d_xy.p + 2 * base : nullptr, list_xy ? d_s.p + base : nullptr, st, tm, &ext_rays);
     if (r != PTRS_OK) return r;
     if (film) {

@@ -69,6 +69,8 @@ class ClockSampler(threading.Thread):
         self.gpu_index, self.samples, self.stop_flag = gpu_index, [], threading.Event()
 
     def run(self):
+        if self._run_nvml():
+            return
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -78,6 +80,32 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
+
+    def _run_nvml(self):
+        """The same readings through NVML every 20 ms (an nvidia-smi process takes ~100 ms per sample, too coarse for a
+        timed region of half a second).  False if NVML is not usable: the caller falls back to nvidia-smi."""
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.02)
+        return True
 
     def summary(self):
         self.stop_flag.set()

@@ -248,6 +248,11 @@ def bvh_microbench(gpu, host, torch, peak_gbs):
                                  "achieved_gbs": alg_bytes / t / 1e9, "frac": alg_bytes / t / 1e9 / peak_gbs}
     out["device_bvh"] = dev
     scene.close()
+    try:  # the memory system's answer to this tree's access pattern: random 64-byte gathers over a buffer of the tree's size
+        tree_bytes = int(out["n_nodes"]) * 32 + int(out["n_tris"]) * 48
+        out["hbm_gather64_gbs_tree_sized"] = gpu.gather_bandwidth(tree_bytes, 256)
+    except Exception:
+        pass
     return out
 
 
@@ -401,6 +406,16 @@ def run_gpu(args):
                                          "note": "latency bound (dependent scene / table loads at 16 warps per SM), not a bandwidth kernel; upper-bound bytes"},
     }
     roofline["stages"] = stages
+    # What the memory system gives THIS access pattern, measured here and now (MEASURED_PEAKS.json has a copy
+    # bandwidth only): streaming 256-bit reads and independent random 64-byte gathers (one sibling pair of nodes),
+    # from an L2-resident buffer and from one far larger than L2 (ptrs_read_bandwidth / ptrs_gather_bandwidth).
+    try:
+        probes = {"l2_stream_read_gbs_64MiB": gpu.read_bandwidth(64 << 20, 30), "l2_gather64_gbs_64MiB": gpu.gather_bandwidth(64 << 20, 512),
+                  "hbm_stream_read_gbs_4GiB": gpu.read_bandwidth(4 << 30, 2), "hbm_gather64_gbs_1GiB": gpu.gather_bandwidth(1 << 30, 256)}
+        roofline["probes"] = probes
+        roofline["frac_of_l2_gather"] = achieved / probes["l2_gather64_gbs_64MiB"]
+    except Exception as e:  # diagnostic only
+        roofline["probes"] = {"error": str(e)}
 
     # ---- CPU baseline: the oracle on a bounded sample of the same workload ----------------------------
     cpu = None

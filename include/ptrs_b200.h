@@ -319,6 +319,14 @@ uint64_t ptrs_scene_device_bytes(const PtrsScene* scene);
 /* Device memory of destroyed scenes / films / path workspaces stays reserved in the device's default memory pool
  * for re-use by the next ptrs_scene_create / ptrs_render; this returns it to the driver. */
 int32_t ptrs_trim_memory(void);
+/* Diagnostic: read bandwidth of `reps` streaming passes (256-bit non-coherent loads, persistent grid) over a
+ * zeroed device buffer of `bytes`.  A buffer that fits in L2 gives the L2 read bandwidth the traversal
+ * kernels' roofline fraction is quoted against when the tree is cache resident; a much larger one the HBM
+ * read bandwidth. */
+int32_t ptrs_read_bandwidth(size_t bytes, int32_t reps, float* gb_per_s);
+/* Same for the traversal's access pattern: independent 64-byte gathers at pseudo-random aligned positions of the
+ * buffer, `gathers_per_thread` per thread of a persistent grid. */
+int32_t ptrs_gather_bandwidth(size_t bytes, int32_t gathers_per_thread, float* gb_per_s);
 
 /* RenderScene::intersect / intersect_p over a batch (mod.rs:92-98; accelerator.rs:359-475).
  * Host-buffer forms copy in and out; *_device forms take device pointers and only enqueue. */

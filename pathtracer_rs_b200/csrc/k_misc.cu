@@ -176,6 +176,57 @@ __global__ void __launch_bounds__(256) accumulate_kernel(const __grid_constant__
   }
 }
 
+// ---- read-bandwidth probe -------------------------------------------------------------------------------
+// The denominator for "fraction of the L2 roofline" (MEASURED_PEAKS.json holds no L2 figure): every
+// thread streams 256-bit non-coherent loads over a buffer `reps` times.  With a buffer that fits in L2 the passes after
+// the first are served by L2; with one far larger than L2 the figure is the HBM read bandwidth.
+__global__ void __launch_bounds__(256) read_probe_kernel(const float4* __restrict__ buf, size_t n_pairs, int reps, uint32_t* sink) {
+  float acc = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (int r = 0; r < reps; ++r)  // blocks rotate over the buffer from pass to pass, so no SM re-reads what its own L1 holds
+    for (size_t i = ((blockIdx.x + (size_t)r * 61u) % gridDim.x) * (size_t)blockDim.x + threadIdx.x; i < n_pairs; i += stride) {
+      float a, b, c, d, e, f, g, h;
+      asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(a), "=f"(b), "=f"(c), "=f"(d), "=f"(e), "=f"(f), "=f"(g), "=f"(h)
+                   : "l"(buf + 2 * i));
+      acc += a + b + c + d + e + f + g + h;
+    }
+  if (acc == 123.456f) *sink = 1u;  // keeps the loads alive
+}
+// The traversal's own access pattern: independent 64-byte gathers (one sibling pair = two 32-byte records) at
+// pseudo-random 64-byte-aligned positions, as many in flight as the hardware takes.  What a node fetch stream can
+// reach at best from L2 (buffer <= L2) or from HBM (buffer >> L2).
+__global__ void __launch_bounds__(256) gather_probe_kernel(const float4* __restrict__ buf, size_t n_blocks64, int per_thread, uint32_t* sink) {
+  float acc = 0.f;
+  uint64_t x = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+  for (int k = 0; k < per_thread; ++k) {
+    x ^= x >> 30;  // splitmix64 step: independent of the loaded data, so gathers overlap
+    x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27;
+    x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    const float4* p = buf + 4 * (size_t)(x % n_blocks64);
+    float a, b, c, d, e, f, g, h, a2, b2, c2, d2, e2, f2, g2, h2;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d), "=f"(e), "=f"(f), "=f"(g), "=f"(h) : "l"(p));
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a2), "=f"(b2), "=f"(c2), "=f"(d2), "=f"(e2), "=f"(f2), "=f"(g2), "=f"(h2)
+                 : "l"(p + 2));
+    acc += a + b + c + d + e + f + g + h + a2 + b2 + c2 + d2 + e2 + f2 + g2 + h2;
+  }
+  if (acc == 123.456f) *sink = 1u;
+}
+void launch_gather_probe(cudaStream_t st, int sm, const float4* buf, size_t n_blocks64, int per_thread, uint32_t* sink, uint64_t* n_gathers) {
+  static int grid = 0;
+  if (!grid) grid = persistent_grid(gather_probe_kernel, 256, sm);
+  *n_gathers = (uint64_t)grid * 256u * (uint64_t)per_thread;
+  gather_probe_kernel<<<grid, 256, 0, st>>>(buf, n_blocks64, per_thread, sink);
+}
+void launch_read_probe(cudaStream_t st, int sm, const float4* buf, size_t n_pairs, int reps, uint32_t* sink) {
+  static int grid = 0;
+  if (!grid) grid = persistent_grid(read_probe_kernel, 256, sm);
+  read_probe_kernel<<<grid, 256, 0, st>>>(buf, n_pairs, reps, sink);
+}
+
 // ---- Distribution1D guide tables ----------------------------------------------------------------------
 // guide[row][k] = #{ i < size : cdf[row][i] <= k / K }, k = 0..K (see DevEnv)
 __global__ void build_guide_kernel(const float* __restrict__ cdf, uint32_t size, uint32_t rows, uint32_t K, uint32_t* __restrict__ guide) {

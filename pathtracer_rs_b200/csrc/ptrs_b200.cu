@@ -734,6 +734,40 @@ int32_t ptrs_trim_memory(void) {
   return PTRS_OK;
 }
 
+static int32_t read_bandwidth_impl(size_t bytes, int32_t reps, bool gather, float* gb_per_s) {
+  if (!gb_per_s || bytes < 64 || reps < 1) return fail(PTRS_ERR_INVALID_ARGUMENT, "bad argument");
+  int dev = 0, sm = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+  DevBuf<float4> buf;
+  DevBuf<uint32_t> sink;
+  const size_t n_pairs = bytes / 32;
+  CUDA_TRY(buf.alloc(n_pairs * 2));
+  CUDA_TRY(sink.alloc(1));
+  CUDA_TRY(cudaMemsetAsync(buf.p, 0, n_pairs * 32, 0));
+  uint64_t n_gathers = 0;
+  if (gather) launch_gather_probe(0, sm, buf.p, n_pairs / 2, reps, sink.p, &n_gathers);
+  launch_read_probe(0, sm, buf.p, n_pairs, 2, sink.p);  // warm-up: code, TLB, and (for a small buffer) the L2 fill
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  CUDA_TRY(cudaEventRecord(e0, 0));
+  if (gather) launch_gather_probe(0, sm, buf.p, n_pairs / 2, reps, sink.p, &n_gathers);
+  else launch_read_probe(0, sm, buf.p, n_pairs, reps, sink.p);
+  CUDA_TRY(cudaEventRecord(e1, 0));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  CUDA_TRY(cudaGetLastError());
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *gb_per_s = gather ? (float)((double)n_gathers * 64.0 / (ms * 1e-3) / 1e9) : (float)((double)n_pairs * 32.0 * reps / (ms * 1e-3) / 1e9);
+  return PTRS_OK;
+}
+
+int32_t ptrs_read_bandwidth(size_t bytes, int32_t reps, float* gb_per_s) { return read_bandwidth_impl(bytes, reps, false, gb_per_s); }
+int32_t ptrs_gather_bandwidth(size_t bytes, int32_t gathers_per_thread, float* gb_per_s) { return read_bandwidth_impl(bytes, gathers_per_thread, true, gb_per_s); }
+
 int32_t ptrs_scene_world_bound(const PtrsScene* scene, float out[6]) {
   if (!scene || !out) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
   std::memcpy(out, scene->world_bound, 24);

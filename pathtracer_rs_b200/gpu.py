@@ -29,7 +29,7 @@ EXPORTS = [
     "ptrs_film_clear", "ptrs_film_download", "ptrs_film_resolve", "ptrs_film_resolve_srgb8", "ptrs_film_device_ptr",
     "ptrs_film_sample_bounds", "ptrs_render_params_default", "ptrs_render", "ptrs_path_radiance", "ptrs_stats",
     "ptrs_set_stats_mode", "ptrs_sobol_samples", "ptrs_generate_rays", "ptrs_trim_memory", "ptrs_scene_create_device_bvh",
-    "ptrs_scene_bvh_info", "ptrs_scene_download_nodes",
+    "ptrs_scene_bvh_info", "ptrs_scene_download_nodes", "ptrs_read_bandwidth", "ptrs_gather_bandwidth",
 ]
 
 
@@ -81,6 +81,8 @@ def lib():
         L.ptrs_path_radiance.argtypes = [vp, camp, rpp, i32p, i32p, sz, fp]
         L.ptrs_stats.argtypes = [vp, C.POINTER(PtrsStats)]
         L.ptrs_set_stats_mode.argtypes = [vp, i32]
+        L.ptrs_read_bandwidth.argtypes = [sz, i32, fp]
+        L.ptrs_gather_bandwidth.argtypes = [sz, i32, fp]
         L.ptrs_sobol_samples.argtypes = [camp, rpp, i32p, i32p, sz, i32p, sz, fp, u64p]
         L.ptrs_generate_rays.argtypes = [camp, rpp, i32p, i32p, sz, rayp, fp, fp]
         _LIB = L
@@ -104,6 +106,21 @@ def device_count():
 
 def set_device(i):
     _check(lib().ptrs_set_device(i))
+
+
+def read_bandwidth(n_bytes, reps=20):
+    """GB/s of `reps` streaming read passes over a device buffer of n_bytes (ptrs_read_bandwidth): L2 read bandwidth for
+    a buffer that fits in L2, HBM read bandwidth for a much larger one."""
+    out = C.c_float(0)
+    _check(lib().ptrs_read_bandwidth(n_bytes, reps, C.byref(out)))
+    return out.value
+
+
+def gather_bandwidth(n_bytes, gathers_per_thread=256):
+    """GB/s of independent random 64-byte gathers over a device buffer of n_bytes (ptrs_gather_bandwidth)."""
+    out = C.c_float(0)
+    _check(lib().ptrs_gather_bandwidth(n_bytes, gathers_per_thread, C.byref(out)))
+    return out.value
 
 
 def trim_memory():

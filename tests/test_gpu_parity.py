@@ -402,3 +402,14 @@ def test_full_size_workload_properties(gpu, host, oracle, name):
     want = ref_film[..., :3][inner] / ref_film[..., 3:][inner]
     assert _rel_mse(got, want) < 1e-3
     scene.close()
+
+
+def test_bandwidth_probes_are_ordered(gpu):
+    """ptrs_read_bandwidth / ptrs_gather_bandwidth (the roofline denominators bench.py reports): an L2-resident buffer
+    streams faster than one far larger than L2, and random 64-byte gathers are slower than streaming on both."""
+    l2_stream, hbm_stream = gpu.read_bandwidth(32 << 20, 20), gpu.read_bandwidth(2 << 30, 2)
+    l2_gather, hbm_gather = gpu.gather_bandwidth(32 << 20, 256), gpu.gather_bandwidth(1 << 30, 128)
+    assert l2_stream > hbm_stream > hbm_gather > 100.0
+    assert l2_stream > l2_gather > hbm_gather
+    with pytest.raises(gpu.PtrsError):
+        gpu.read_bandwidth(8, 1)

@@ -413,3 +413,66 @@ def test_bandwidth_probes_are_ordered(gpu):
     assert l2_stream > l2_gather > hbm_gather
     with pytest.raises(gpu.PtrsError):
         gpu.read_bandwidth(8, 1)
+
+
+def test_scene_validation_rejects_malformed_input(gpu, host, cornell):
+    """ptrs_scene_create must refuse descriptions the kernels could not trust: out-of-range indices (checked on the
+    device after upload) and anything that is not a depth-first preorder tree (checked on the host in one pass) — a
+    shared subtree or a cycle would keep a traversal kernel from terminating.  The reference would panic on an
+    out-of-bounds index; here every case is PTRS_ERR_INVALID_ARGUMENT and the process stays usable."""
+    import ctypes as C
+
+    from pathtracer_rs_b200._abi import PtrsBvhNode, PtrsSceneDesc
+
+    flat, cam = cornell
+    base = flat.desc.contents
+    n_nodes, n_prims = base.n_nodes, base.n_prims
+
+    def attempt(mutate):
+        d = PtrsSceneDesc()
+        C.memmove(C.byref(d), C.byref(base), C.sizeof(PtrsSceneDesc))
+        nodes = (PtrsBvhNode * (n_nodes + 2))()
+        C.memmove(nodes, base.nodes, n_nodes * C.sizeof(PtrsBvhNode))
+        pv = (C.c_uint32 * (3 * n_prims))(*[base.prim_vertex[i] for i in range(3 * n_prims)])
+        pm = (C.c_int32 * n_prims)(*[base.prim_material[i] for i in range(n_prims)])
+        d.nodes, d.prim_vertex, d.prim_material = nodes, pv, pm
+        mutate(d, nodes, pv, pm)
+        with pytest.raises(gpu.PtrsError) as e:
+            gpu.RenderScene(C.pointer(d))
+        assert e.value.code == -1, e.value
+
+    interior = [i for i in range(n_nodes) if base.nodes[i].n_prims == 0]
+    leaves = [i for i in range(n_nodes) if base.nodes[i].n_prims > 0]
+    assert len(interior) > 3
+
+    def material_out_of_range(d, nodes, pv, pm):
+        pm[n_prims // 2] = d.n_materials
+
+    def vertex_out_of_range(d, nodes, pv, pm):
+        pv[5] = d.n_verts
+
+    def leaf_range_past_the_end(d, nodes, pv, pm):
+        nodes[leaves[-1]].offset = n_prims
+
+    def second_child_points_backwards(d, nodes, pv, pm):  # a cycle
+        nodes[interior[2]].offset = interior[1]
+
+    def shared_subtree(d, nodes, pv, pm):  # two interior nodes name the same second child
+        nodes[interior[1]].offset = nodes[interior[0]].offset
+
+    def trailing_records(d, nodes, pv, pm):
+        nodes[n_nodes] = nodes[leaves[0]]
+        d.n_nodes = n_nodes + 1
+
+    def truncated(d, nodes, pv, pm):
+        d.n_nodes = n_nodes - 1
+
+    def bad_axis(d, nodes, pv, pm):
+        nodes[interior[0]].axis = 3
+
+    for m in (material_out_of_range, vertex_out_of_range, leaf_range_past_the_end, second_child_points_backwards, shared_subtree,
+              trailing_records, truncated, bad_axis):
+        attempt(m)
+    scene = gpu.RenderScene(flat)  # the library is still usable and the untouched description still loads
+    assert scene.intersect(host.coherent_rays(cam, 8)).shape == (64,)
+    scene.close()

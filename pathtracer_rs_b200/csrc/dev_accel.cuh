@@ -209,7 +209,7 @@ PT_DEV bool box_geom(const NodeLoad& n, V3 o, V3 inv_dir, bool nx, bool ny, bool
 //              on the stack, and `t_entry < t_max` is applied again when it is popped — the very test the
 //              reference performs at that moment, since only that comparison depends on t_max
 //   postpone   (fast variant) a lane that reaches a leaf parks it and keeps descending until it holds a
-//              second leaf; the warp switches to the triangle phase when fewer than PT_BOX_MIN lanes can
+//              second leaf; the warp switches to the triangle phase when fewer than box_min (DevScene, 12 or 20) lanes can
 //              still take a box step.  Exactness: with nested boxes the slab entry distance can only grow
 //              from a node to its descendants (float subtraction and multiplication are monotonic), so a
 //              node accepted under a stale (larger) t_max that the reference would have culled can only
@@ -234,9 +234,6 @@ struct LaneRay {
 #endif
 #ifndef PT_SEARCH_MIN
 #define PT_SEARCH_MIN 6
-#endif
-#ifndef PT_BOX_MIN
-#define PT_BOX_MIN 16
 #endif
 
 // empty accelerator: every ray misses (accelerator.rs:360-362)
@@ -276,6 +273,9 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
     return;
   }
   const uint32_t FULL = 0xffffffffu;
+  // fewer lanes than this able to take a box step -> the warp turns to its parked leaves.  Scheduling only (results do
+  // not depend on it); measured: 12 is best on trees of a few dozen nodes, 20 on trees of 10^5 .. 10^7 nodes.
+  const int box_min = (int)sc.box_min;
   uint4 stack[PT_STACK_SIZE];
   int sp_ = 0;
   // node in hand (its box test passed under the t_max current at that time): offset, meta, entry distance
@@ -350,7 +350,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
       const bool can_box = live && ((cur_meta != PT_NO_NODE && !cur_leaf) || (cur_meta == PT_NO_NODE && sp_ > 0) || (cur_leaf && pl_cnt == 0));
       const uint32_t bmask = __ballot_sync(FULL, can_box);
       if (bmask == 0) break;
-      if (__popc(bmask) < PT_BOX_MIN && __ballot_sync(FULL, live && !can_box) != 0) break;
+      if (__popc(bmask) < box_min && __ballot_sync(FULL, live && !can_box) != 0) break;
       if (can_box) {
         if (cur_meta == PT_NO_NODE) {  // pop one entry; the reference's box test at pop time
           --sp_;

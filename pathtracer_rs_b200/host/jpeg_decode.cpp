@@ -34,6 +34,7 @@ struct Huffman {
     for (int len = 1; len <= 16; ++len) {
       valptr[len] = k;
       mincode[len] = code;
+      if (code + counts[len - 1] > (1 << len)) bad("over-subscribed Huffman table");
       for (int i = 0; i < counts[len - 1]; ++i, ++k, ++code) {
         if (len <= 9) {
           const int first = code << (9 - len);
@@ -41,7 +42,6 @@ struct Huffman {
         }
       }
       maxcode[len] = counts[len - 1] ? code - 1 : -1;
-      if (code > (1 << len)) bad("over-subscribed Huffman table");
       code <<= 1;
     }
     maxcode[17] = 0x7fffffff;
@@ -179,6 +179,7 @@ struct Decoder {
     width = u16();
     const int nc = u8();
     if (width <= 0 || height <= 0) bad("empty image");
+    if ((uint64_t)width * (uint64_t)height > (1ull << 28)) bad("image larger than 2^28 pixels");  // a corrupt header must not become a 100 GB allocation
     if (nc != 1 && nc != 3) bad("only 1- and 3-component files are supported");
     comps.resize((size_t)nc);
     for (auto& c : comps) {

@@ -80,6 +80,27 @@ def test_unsupported_and_broken_files_raise(host):
         host.decode_image(b.getvalue())
 
 
+def test_corrupted_files_never_crash(host):
+    """Every byte of a file is attacker-controlled (textures come from scene files): flipped bytes either still decode
+    to an image of the declared size or raise — tables, markers and entropy data are all hit by the mutations."""
+    g = np.load(GOLDEN)
+    rng = np.random.default_rng(11)
+    outcomes = {"ok": 0, "error": 0}
+    for name in ("baseline_420", "progressive_420", "baseline_422_restart", "grey"):
+        data = bytearray(g[name + "_file"].tobytes())
+        for _ in range(150):
+            m = bytearray(data)
+            for _ in range(int(rng.integers(1, 4))):
+                m[int(rng.integers(2, len(m)))] = int(rng.integers(0, 256))
+            try:
+                img = host.decode_image(bytes(m))
+                assert img.ndim == 3 and img.size > 0
+                outcomes["ok"] += 1
+            except RuntimeError:
+                outcomes["error"] += 1
+    assert outcomes["ok"] > 50 and outcomes["error"] > 50, outcomes
+
+
 XML = """<scene version="0.5.0">
   <sensor type="perspective"><float name="fov" value="40"/><transform name="toWorld"><matrix value="-1 0 0 0 0 1 0 0 0 0 -1 4 0 0 0 1"/></transform>
     <film type="ldrfilm"><integer name="width" value="64"/><integer name="height" value="48"/></film></sensor>

@@ -91,7 +91,7 @@ def lib():
 
 def _check(rc):
     if rc != 0:
-        raise PtrsError(rc, lib().ptrs_last_error().decode())
+        raise PtrsError(rc, lib().ptrs_last_error().decode(errors="replace"))
 
 
 def _p(a, t):

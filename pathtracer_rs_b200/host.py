@@ -102,7 +102,7 @@ class FlatScene:
 
     def __init__(self, handle):
         if not handle:
-            raise RuntimeError("host scene build failed: " + lib().ptrs_host_last_error().decode())
+            raise RuntimeError("host scene build failed: " + lib().ptrs_host_last_error().decode(errors="replace"))
         self._h = handle
         self.desc = lib().ptrs_host_scene_desc(handle)
 
@@ -171,7 +171,7 @@ def import_scene(path, res=(640, 480), default_lights=False, sunsky_hdr=None, n_
 
 def _img_check(rc):
     if rc != 0:
-        raise RuntimeError(lib().ptrs_host_last_error().decode())
+        raise RuntimeError(lib().ptrs_host_last_error().decode(errors="replace"))
 
 
 def load_hdr(path):
@@ -291,7 +291,7 @@ def build_bvh(bounds, max_prims=4, n_threads=1):
     rc = lib().ptrs_host_build_bvh(_fp(b), n, max_prims, n_threads, nodes.ctypes.data_as(C.POINTER(PtrsBvhNode)),
                                    nodes.shape[0], C.byref(cnt), order.ctypes.data_as(C.POINTER(C.c_uint32)))
     if rc != 0:
-        raise RuntimeError(lib().ptrs_host_last_error().decode())
+        raise RuntimeError(lib().ptrs_host_last_error().decode(errors="replace"))
     return nodes[: cnt.value].copy(), order
 
 
@@ -323,7 +323,7 @@ class SceneBuilder:
         h, w, c = img.shape
         r = lib().ptrs_host_add_image_texture(self._b, c, _fp(img), w, h, wrap, su, sv, du, dv)
         if r < 0:
-            raise RuntimeError(lib().ptrs_host_last_error().decode())
+            raise RuntimeError(lib().ptrs_host_last_error().decode(errors="replace"))
         return r
 
     def material(self, mtype, tex=(), remap_roughness=False, normal_map=-1):
@@ -343,7 +343,7 @@ class SceneBuilder:
         r = lib().ptrs_host_add_mesh(self._b, _fp(p), p.shape[0], _fp(n), _fp(t), _fp(u),
                                      idx.ctypes.data_as(C.POINTER(C.c_uint32)), idx.shape[0], _fp(x), material, alpha_tex, ke_tex)
         if r < 0:
-            raise RuntimeError(lib().ptrs_host_last_error().decode())
+            raise RuntimeError(lib().ptrs_host_last_error().decode(errors="replace"))
         return r
 
     def shape(self, kind, transform, material, ke_tex=-1):
@@ -364,7 +364,7 @@ class SceneBuilder:
         h, w, _ = img.shape
         r = lib().ptrs_host_add_infinite_light(self._b, _fp(x), _fp(img), w, h)
         if r < 0:
-            raise RuntimeError(lib().ptrs_host_last_error().decode())
+            raise RuntimeError(lib().ptrs_host_last_error().decode(errors="replace"))
         return r
 
     def finalize(self, max_prims_in_node=4, n_threads=0):

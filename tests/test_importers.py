@@ -275,3 +275,51 @@ def test_tev_update_image_tiles(host):
     assert seen[:6] == [("r", 0, 0, 100, 100), ("r", 0, 100, 100, 30), ("r", 100, 0, 100, 100), ("r", 100, 100, 100, 30),
                         ("r", 200, 0, 50, 100), ("r", 200, 100, 50, 30)]
     assert [s[0] for s in seen] == ["r"] * 6 + ["g"] * 6 + ["b"] * 6
+
+
+def test_corrupted_scene_files_raise_or_load(host, tmp_path):
+    """Scene files are untrusted input: random edits of the Cornell XML and of a small glTF document must either import
+    or raise (the reference panics); the XML / JSON readers and both importers never read out of bounds."""
+    import base64
+    import json
+
+    rng = np.random.default_rng(5)
+
+    def mutate(data, digits_only=False):
+        m = bytearray(data)
+        for _ in range(int(rng.integers(1, 6))):
+            k = int(rng.integers(0, len(m)))
+            op = int(rng.integers(0, 3))
+            if op == 0:
+                m[k] = int(rng.integers(32, 127))
+            elif op == 1:
+                del m[k:k + int(rng.integers(1, 20))]
+            else:
+                m[k:k] = bytes(rng.integers(48 if digits_only else 32, 58 if digits_only else 127, int(rng.integers(1, 8)), dtype=np.uint8))
+        return bytes(m)
+
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float32)
+    blob = pos.tobytes() + np.array([0, 1, 2, 0], dtype=np.uint16).tobytes()
+    doc = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0, "translation": [0, 0, -3]}],
+           "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1, "material": 0}]}],
+           "materials": [{"pbrMetallicRoughness": {"baseColorFactor": [0.8, 0.5, 0.2, 1], "metallicFactor": 0.1}, "emissiveFactor": [1, 1, 1]}],
+           "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}],
+           "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 6}],
+           "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3", "min": [0, 0, 0], "max": [1, 1, 0]},
+                         {"bufferView": 1, "componentType": 5123, "count": 3, "type": "SCALAR"}]}
+    sources = {"m.xml": (open(os.path.join(GOLDEN, "cornell-box.xml"), "rb").read(), False), "m.gltf": (json.dumps(doc).encode(), True)}
+    for name, (data, digits) in sources.items():
+        host.import_scene(_write(tmp_path / name, data), res=(32, 32))  # the unmodified file loads
+        outcomes = {"ok": 0, "error": 0}
+        for _ in range(120):
+            try:
+                host.import_scene(_write(tmp_path / name, mutate(data, digits)), res=(32, 32))
+                outcomes["ok"] += 1
+            except RuntimeError:
+                outcomes["error"] += 1
+        assert outcomes["error"] > 30, (name, outcomes)
+
+
+def _write(path, data):
+    path.write_bytes(data)
+    return str(path)

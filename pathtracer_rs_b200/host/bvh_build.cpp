@@ -62,9 +62,9 @@ constexpr int N_BUCKETS = 12;
 inline int bucket_of(const Bounds3& cb, const PrimInfo& pi, int dim) {
   // `as usize` saturates negatives/NaN to 0 in Rust; offsets are >= 0 here.
   float f = (float)N_BUCKETS * offset_dim(cb, pi.centroid, dim);
-  int b = f > 0.0f ? (int)f : 0;
-  if (b >= N_BUCKETS) b = N_BUCKETS - 1;
-  return b;
+  if (!(f > 0.0f)) return 0;                               // negatives and NaN
+  if (f >= (float)N_BUCKETS) return N_BUCKETS - 1;           // also +inf: (int)inf would be undefined here
+  return (int)f;
 }
 
 struct Builder {
@@ -100,12 +100,14 @@ struct Builder {
     Bounds3 cb = empty_bounds();
     for (size_t i = start; i < end; ++i) cb = bunion_p(cb, info[i].centroid);
     const int dim = maximum_extent(cb);
-    if (cb.mx[dim] == cb.mn[dim]) {
-      make_leaf();
-      return;
-    }
     size_t mid;
-    if (n <= 2) {
+    if (cb.mx[dim] == cb.mn[dim]) {
+      if (n <= 65535) {  // n_prims is 16 bits wide (LinearBVHNode, accelerator.rs:89-95)
+        make_leaf();
+        return;
+      }
+      mid = start + n / 2;  // more coincident primitives than a leaf can count: halve the range
+    } else if (n <= 2) {
       // select_nth_unstable_by(mid - start) on two elements with distinct keys == ascending order
       mid = (start + end) / 2;
       if (info[start + 1].centroid[dim] < info[start].centroid[dim])
@@ -162,6 +164,10 @@ struct Builder {
       }
     }
 
+    // With finite bounds both sides are non-empty.  With non-finite ones (where the reference indexes its buckets out of
+    // range and panics, or recurses without end) the range is halved instead, so the build always terminates with a
+    // valid tree.
+    if (mid == start || mid == end) mid = start + n / 2;
     int d0 = depth, d1 = depth;
     if (n >= task_cutoff) {
       std::vector<PtrsBvhNode> left, right;

@@ -202,6 +202,26 @@ def test_bvh_parallel_build_is_identical(host):
     assert np.array_equal(n1.view(np.uint8), n8.view(np.uint8)) and np.array_equal(o1, o8)
 
 
+def test_bvh_build_survives_hostile_bounds(host):
+    """Non-finite or coincident primitive bounds (a corrupt mesh): the reference indexes its SAH buckets out of range or
+    recurses without end; the restated builder must still return a valid tree over every primitive."""
+    rng = np.random.default_rng(1)
+    n = 3000
+    c = rng.random((n, 3)).astype(np.float32)
+    base = np.concatenate([c - 0.01, c + 0.01], 1).astype(np.float32)
+    for bad in (np.nan, np.inf, -np.inf, 3e38):
+        b = base.copy()
+        b[rng.integers(0, n, 40), rng.integers(0, 6, 40)] = bad
+        nodes, order = host.build_bvh(b)
+        assert np.array_equal(np.sort(order), np.arange(n))
+        leaves = nodes[nodes["n_prims"] > 0]
+        assert int(leaves["n_prims"].sum()) == n
+    same = np.tile(base[:1], (70000, 1))  # more coincident primitives than the 16-bit leaf count holds
+    nodes, order = host.build_bvh(same)
+    leaves = nodes[nodes["n_prims"] > 0]
+    assert int(leaves["n_prims"].astype(np.int64).sum()) == 70000 and len(nodes) == 3
+
+
 def test_cornell_scene_shape(cornell):
     flat, cam = cornell
     d = flat.desc.contents

@@ -114,9 +114,12 @@ PT_DEV void nee_prepare(const DevScene& sc, const SurfInter& si, const Bsdf& bsd
 #ifndef PT_SHADE_MIN_BLOCKS
 #define PT_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef PT_SHADE_BLOCK
+#define PT_SHADE_BLOCK 128
+#endif
 
 template <int MAT>
-__global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ RenderConst rc, PT_SHADE_PARAM DevScene sc, PT_SHADE_PARAM PathArrays P,
+__global__ void __launch_bounds__(PT_SHADE_BLOCK, PT_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ RenderConst rc, PT_SHADE_PARAM DevScene sc, PT_SHADE_PARAM PathArrays P,
                                                      const int* __restrict__ q, const float4* __restrict__ q_hit, int* __restrict__ q_ext_next,
                                                      int* __restrict__ q_nee, RoundCounters* ctr, RoundCounters* ctr_next) {
   const uint32_t n = ctr->n_class[MAT];
@@ -317,8 +320,8 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) shade_kernel(const _
 void PT_CAT(launch_shade_, PT_SHADE_MAT)(cudaStream_t st, int sm, const RenderConst& rc, const DevScene& sc, const PathArrays& P, const int* q,
                                          const float4* q_hit, int* q_next, int* q_nee, RoundCounters* ctr, RoundCounters* ctr_next) {
   static int grid = 0;
-  if (!grid) grid = persistent_grid(shade_kernel<PT_SHADE_MAT>, 128, sm);
-  shade_kernel<PT_SHADE_MAT><<<grid, 128, 0, st>>>(rc, sc, P, q, q_hit, q_next, q_nee, ctr, ctr_next);
+  if (!grid) grid = persistent_grid(shade_kernel<PT_SHADE_MAT>, PT_SHADE_BLOCK, sm);
+  shade_kernel<PT_SHADE_MAT><<<grid, PT_SHADE_BLOCK, 0, st>>>(rc, sc, P, q, q_hit, q_next, q_nee, ctr, ctr_next);
 }
 
 }  // namespace ptrs

@@ -2,7 +2,7 @@
 """bench.py — the reference's headline metric (camera samples/s and Mrays/s of the path integrator) on
 BASELINE.json's configs[1]: Cornell box + environment map, 1024x1024, 64 spp, max_depth 15.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c1|c2|c3|c5] [--spp S]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 A step = one full render of the workload (67.6 M camera paths) accumulated into a cleared film.
@@ -12,7 +12,10 @@ A step = one full render of the workload (67.6 M camera paths) accumulated into 
   roofline  extend kernel (closest-hit BVH traversal, the kernel BASELINE.json's "% of L2/HBM roofline" is about):
             algorithmic bytes (32 B x nodes tested + 36 B x triangles tested + 28 B ray + 20 B hit)
             / its summed launch time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json;
-            roofline.stages adds the connect and shade stages the same way (shade is the largest share on C2)
+            roofline.stages adds the connect and shade stages the same way (shade is the largest share on C2);
+            roofline.probes are the memory system's own figures measured in the same process — streaming reads and
+            random 64-byte gathers from an L2-resident and from an HBM-sized buffer — and roofline.frac_of_l2_gather
+            is the extend kernel against the one that matches its access pattern
   cpu_baseline  the C++ oracle (a restatement of the reference's rayon integrator; the Rust crate cannot
             be built in this image) on a bounded, strided sample of the same workload's 16x16 tiles
 Multi-GPU (weak scaling): rank g renders Sobol sample numbers {s : s mod N == g} of a 64*N-spp render of

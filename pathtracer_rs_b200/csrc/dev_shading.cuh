@@ -282,10 +282,16 @@ PT_DEV size_t find_interval_cdf(const float* __restrict__ cdf, size_t size, floa
 }
 // find_interval restricted to the guide bracket [lo, hi]: the predicate cdf[i] <= u is monotone in i, so the
 // partition point found inside the bracket is the one the full search finds
-PT_DEV size_t find_interval_guided(const float* __restrict__ cdf, size_t size, float u, const uint32_t* __restrict__ guide, uint32_t K) {
+PT_DEV void pt_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+PT_DEV size_t find_interval_guided(const float* __restrict__ cdf, size_t size, float u, const uint32_t* __restrict__ guide, uint32_t K,
+                                   const float* __restrict__ func_hint = nullptr) {
   uint32_t k = (uint32_t)(u * (float)K);
   if (k > K - 1u) k = K - 1u;
   size_t first = __ldg(guide + k), len = __ldg(guide + k + 1) - first;
+  // the bracket is known: start fetching the lines the search, the interval ends and the density will read, so the
+  // dependent loads below meet them in L1 instead of each paying an L2 round trip
+  pt_prefetch_l1(cdf + (first > 0 ? first - 1 : 0));
+  if (func_hint) pt_prefetch_l1(func_hint + (first > 0 ? first - 1 : 0));
   while (len > 0) {
     size_t half = len >> 1, middle = first + half;
     if (__ldg(cdf + middle) <= u) {
@@ -300,7 +306,7 @@ PT_DEV size_t find_interval_guided(const float* __restrict__ cdf, size_t size, f
 }
 PT_DEV float dist1d_sample(const float* func, const float* cdf, float func_int, int n, float u, float* pdf, size_t* off, const uint32_t* guide,
                            uint32_t K) {  // sampling.rs:164-182
-  size_t offset = guide ? find_interval_guided(cdf, (size_t)n + 1, u, guide, K) : find_interval_cdf(cdf, (size_t)n + 1, u);
+  size_t offset = guide ? find_interval_guided(cdf, (size_t)n + 1, u, guide, K, func) : find_interval_cdf(cdf, (size_t)n + 1, u);
   *off = offset;
   float c0 = __ldg(cdf + offset), c1 = __ldg(cdf + offset + 1);
   float du = u - c0;

@@ -202,18 +202,23 @@ __device__ __forceinline__ NodeRec make_node(float4 mn, float4 mx, uint32_t offs
 }
 
 // one thread per emitted interior node: depth-first pair number from the path to the root, then the two child records
-__global__ void __launch_bounds__(256) emit_kernel(uint32_t n, BuildArrays A, float4* __restrict__ nodes) {
+// *max_depth receives the largest (number of interior ancestors + 1) over the emitted interior nodes: the most pending
+// stack entries a traversal of this tree can hold
+__global__ void __launch_bounds__(256) emit_kernel(uint32_t n, BuildArrays A, float4* __restrict__ nodes, uint32_t* __restrict__ max_depth) {
+  uint32_t deepest = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n - 1; i += gridDim.x * blockDim.x) {
     const TreeNode self = A.node[i];
     if (self.n_interior == 0) continue;
-    uint32_t pair = 1;
+    uint32_t pair = 1, depth = 1;
     for (uint32_t c = i, p = self.parent; c != 0;) {
       const TreeNode pn = A.node[p];
       pair += 1;
+      depth += 1;
       if (pn.right == c && pn.left < n - 1) pair += A.node[pn.left].n_interior;
       c = p;
       p = pn.parent;
     }
+    deepest = max(deepest, depth);
     const uint32_t l = self.left, r = self.right;
     const uint32_t l_int = l < n - 1 ? A.node[l].n_interior : 0u, r_int = r < n - 1 ? A.node[r].n_interior : 0u;
     const float4 lmn = A.box[l].mn, lmx = A.box[l].mx, rmn = A.box[r].mn, rmx = A.box[r].mx;
@@ -251,6 +256,8 @@ __global__ void __launch_bounds__(256) emit_kernel(uint32_t n, BuildArrays A, fl
       nodes[3] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  for (int o = 16; o > 0; o >>= 1) deepest = max(deepest, __shfl_xor_sync(0xffffffffu, deepest, o));
+  if ((threadIdx.x & 31) == 0 && deepest) atomicMax(max_depth, deepest);
 }
 
 // scene of at most PT_BVH_MAX_LEAF primitives: the root is the only node, a leaf
@@ -295,12 +302,14 @@ __global__ void __launch_bounds__(256) assemble_tris_kernel(uint32_t n, const ui
 __global__ void __launch_bounds__(256) validate_prims_kernel(uint32_t n, const uint32_t* __restrict__ prim_vertex, const int32_t* __restrict__ prim_mesh,
                                                              const int32_t* __restrict__ prim_material, const int32_t* __restrict__ prim_area_light,
                                                              uint32_t n_verts, uint32_t n_meshes, uint32_t n_materials, uint32_t n_lights,
-                                                             uint32_t* __restrict__ err) {
+                                                             const PtrsLight* __restrict__ lights, uint32_t* __restrict__ err) {
   uint32_t e = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (prim_mesh[i] < 0 || (uint32_t)prim_mesh[i] >= n_meshes || prim_material[i] < 0 || (uint32_t)prim_material[i] >= n_materials ||
         prim_area_light[i] >= (int32_t)n_lights)
       e |= 1u;
+    else if (prim_area_light[i] >= 0 && lights[prim_area_light[i]].type != PTRS_LIGHT_AREA)  // area_le reads the light's ke texture
+      e |= 4u;
     for (int k = 0; k < 3; ++k)
       if (prim_vertex[3 * (size_t)i + k] >= n_verts) e |= 2u;
   }
@@ -359,10 +368,11 @@ struct Arena {  // one stream-ordered allocation carved into 256-byte aligned ar
 // *n_nodes_out 32-byte records (as float4 pairs) and *perm_out the primitive order (BVH position -> caller index);
 // both are stream-ordered allocations the caller frees with cudaFreeAsync.  Returns a cudaError_t.
 int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vertex, const float* d_pos, float4** nodes_out, uint32_t* n_nodes_out,
-                        uint32_t** perm_out) {
+                        uint32_t** perm_out, uint32_t* depth_out) {
   *nodes_out = nullptr;
   *perm_out = nullptr;
   *n_nodes_out = 0;
+  *depth_out = 0;
   if (n == 0) return cudaSuccess;
   BuildArrays A{};
   uint64_t* keys_sorted = nullptr;
@@ -395,8 +405,8 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
   carve(arena);  // sizes only
   const size_t arena_bytes = arena.used;
   void* arena_mem = nullptr;
-  ok(cudaMallocAsync(&arena_mem, arena_bytes, st));
-  ok(cudaMallocAsync(reinterpret_cast<void**>(&perm_sorted), (size_t)n * 4, st));  // survives: the primitive order handed back
+  ok(pool_alloc(&arena_mem, arena_bytes, st));
+  ok(pool_alloc(reinterpret_cast<void**>(&perm_sorted), (size_t)n * 4, st));  // survives: the primitive order handed back
   const int grid = 148 * 8;
   uint32_t n_interior_root = 0;
   if (e == cudaSuccess) {
@@ -420,10 +430,17 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
   }
   if (e == cudaSuccess) {
     const uint32_t n_nodes = 2u + 2u * n_interior_root;
-    ok(cudaMallocAsync(reinterpret_cast<void**>(&nodes), (size_t)n_nodes * 32, st));
+    ok(pool_alloc(reinterpret_cast<void**>(&nodes), (size_t)n_nodes * 32, st));
     if (e == cudaSuccess) {
-      if (n_interior_root == 0) single_leaf_kernel<<<1, 32, 0, st>>>(n, A, nodes);
-      else emit_kernel<<<grid, 256, 0, st>>>(n, A, nodes);
+      if (n_interior_root == 0) {
+        single_leaf_kernel<<<1, 32, 0, st>>>(n, A, nodes);
+      } else {
+        // cbounds is dead after morton_kernel: its first word becomes the depth cell
+        ok(cudaMemsetAsync(A.cbounds, 0, 4, st));
+        emit_kernel<<<grid, 256, 0, st>>>(n, A, nodes, A.cbounds);
+        ok(cudaMemcpyAsync(depth_out, A.cbounds, 4, cudaMemcpyDeviceToHost, st));
+        ok(cudaStreamSynchronize(st));
+      }
       ok(cudaGetLastError());
       *n_nodes_out = n_nodes;
     }
@@ -447,13 +464,14 @@ void launch_assemble_tris(cudaStream_t st, uint32_t n, const uint32_t* perm, con
 }
 // returns the error bits of validate_prims_kernel (0 = fine), or a negative cudaError_t
 int validate_prims_on_device(cudaStream_t st, uint32_t n, const uint32_t* prim_vertex, const int32_t* prim_mesh, const int32_t* prim_material,
-                             const int32_t* prim_area_light, uint32_t n_verts, uint32_t n_meshes, uint32_t n_materials, uint32_t n_lights) {
+                             const int32_t* prim_area_light, uint32_t n_verts, uint32_t n_meshes, uint32_t n_materials, uint32_t n_lights,
+                             const PtrsLight* lights) {
   if (n == 0) return 0;
   uint32_t* d_err = nullptr;
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&d_err), 4, st);
+  cudaError_t e = pool_alloc(reinterpret_cast<void**>(&d_err), 4, st);
   if (e != cudaSuccess) return -(int)e;
   cudaMemsetAsync(d_err, 0, 4, st);
-  validate_prims_kernel<<<148 * 8, 256, 0, st>>>(n, prim_vertex, prim_mesh, prim_material, prim_area_light, n_verts, n_meshes, n_materials, n_lights, d_err);
+  validate_prims_kernel<<<148 * 8, 256, 0, st>>>(n, prim_vertex, prim_mesh, prim_material, prim_area_light, n_verts, n_meshes, n_materials, n_lights, lights, d_err);
   uint32_t h = 0;
   e = cudaMemcpyAsync(&h, d_err, 4, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -471,10 +489,10 @@ int pair_layout_on_device(cudaStream_t st, const float4* d_raw, uint32_t n, uint
   void* tmp = nullptr;
   size_t tmp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flag, rank, (int)n, st);
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&flag), (size_t)n * 4, st);
-  if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&rank), (size_t)n * 4, st);
-  if (e == cudaSuccess) e = cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, st);
-  if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(out), (size_t)n_dev * 32, st);
+  cudaError_t e = pool_alloc(reinterpret_cast<void**>(&flag), (size_t)n * 4, st);
+  if (e == cudaSuccess) e = pool_alloc(reinterpret_cast<void**>(&rank), (size_t)n * 4, st);
+  if (e == cudaSuccess) e = pool_alloc(&tmp, tmp_bytes ? tmp_bytes : 1, st);
+  if (e == cudaSuccess) e = pool_alloc(reinterpret_cast<void**>(out), (size_t)n_dev * 32, st);
   if (e == cudaSuccess) {
     interior_flag_kernel<<<148 * 8, 256, 0, st>>>(d_raw, n, flag);
     e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, rank, (int)n, st);

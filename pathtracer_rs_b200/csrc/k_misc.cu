@@ -216,14 +216,12 @@ __global__ void __launch_bounds__(256) gather_probe_kernel(const float4* __restr
   if (acc == 123.456f) *sink = 1u;
 }
 void launch_gather_probe(cudaStream_t st, int sm, const float4* buf, size_t n_blocks64, int per_thread, uint32_t* sink, uint64_t* n_gathers) {
-  static int grid = 0;
-  if (!grid) grid = persistent_grid(gather_probe_kernel, 256, sm);
+  const int grid = PT_GRID(gather_probe_kernel, 256, sm);
   *n_gathers = (uint64_t)grid * 256u * (uint64_t)per_thread;
   gather_probe_kernel<<<grid, 256, 0, st>>>(buf, n_blocks64, per_thread, sink);
 }
 void launch_read_probe(cudaStream_t st, int sm, const float4* buf, size_t n_pairs, int reps, uint32_t* sink) {
-  static int grid = 0;
-  if (!grid) grid = persistent_grid(read_probe_kernel, 256, sm);
+  const int grid = PT_GRID(read_probe_kernel, 256, sm);
   read_probe_kernel<<<grid, 256, 0, st>>>(buf, n_pairs, reps, sink);
 }
 
@@ -338,23 +336,19 @@ __global__ void resolve_kernel(const float4* film, uint32_t n, float* rgb, uint8
 // ---- launchers -----------------------------------------------------------------------------------------
 void launch_generate(cudaStream_t st, int sm, const RenderConst& rc, const uint32_t* sobol, const PathArrays& P, uint64_t work_base,
                      uint32_t n_work, const int* list_xy, const int* list_s, int* q_ext, RoundCounters* ctr) {
-  static int grid = 0;
-  if (!grid) grid = persistent_grid(generate_kernel, 256, sm);
+  const int grid = PT_GRID(generate_kernel, 256, sm);
   generate_kernel<<<grid, 256, 0, st>>>(rc, sobol, P, work_base, n_work, list_xy, list_s, q_ext, ctr);
 }
 void launch_shade_miss(cudaStream_t st, int sm, const DevScene& sc, const PathArrays& P, const int* q, RoundCounters* ctr) {
-  static int grid = 0;
-  if (!grid) grid = persistent_grid(shade_miss_kernel, 128, sm);
+  const int grid = PT_GRID(shade_miss_kernel, 128, sm);
   shade_miss_kernel<<<grid, 128, 0, st>>>(sc, P, q, ctr);
 }
 void launch_connect_resolve(cudaStream_t st, int sm, const DevScene& sc, const PathArrays& P, const int* q_nee, RoundCounters* ctr) {
-  static int grid = 0;
-  if (!grid) grid = persistent_grid(connect_resolve_kernel, 256, sm);
+  const int grid = PT_GRID(connect_resolve_kernel, 256, sm);
   connect_resolve_kernel<<<grid, 256, 0, st>>>(sc, P, q_nee, ctr);
 }
 void launch_accumulate(cudaStream_t st, int sm, const RenderConst& rc, const PathArrays& P, uint32_t n, float4* film) {
-  static int grid = 0;
-  if (!grid) grid = persistent_grid(accumulate_kernel, 256, sm);
+  const int grid = PT_GRID(accumulate_kernel, 256, sm);
   accumulate_kernel<<<grid, 256, 0, st>>>(rc, P, n, film);
 }
 void launch_resolve(cudaStream_t st, const float4* film, uint32_t n, float* rgb, uint8_t* rgba8) {

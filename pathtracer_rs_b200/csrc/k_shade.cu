@@ -319,9 +319,7 @@ __global__ void __launch_bounds__(PT_SHADE_BLOCK, PT_SHADE_MIN_BLOCKS) shade_ker
 #define PT_CAT(a, b) PT_CAT2(a, b)
 void PT_CAT(launch_shade_, PT_SHADE_MAT)(cudaStream_t st, int sm, const RenderConst& rc, const DevScene& sc, const PathArrays& P, const int* q,
                                          const float4* q_hit, int* q_next, int* q_nee, RoundCounters* ctr, RoundCounters* ctr_next) {
-  static int grid = 0;
-  if (!grid) grid = persistent_grid(shade_kernel<PT_SHADE_MAT>, PT_SHADE_BLOCK, sm);
-  shade_kernel<PT_SHADE_MAT><<<grid, PT_SHADE_BLOCK, 0, st>>>(rc, sc, P, q, q_hit, q_next, q_nee, ctr, ctr_next);
+  shade_kernel<PT_SHADE_MAT><<<PT_GRID(shade_kernel<PT_SHADE_MAT>, PT_SHADE_BLOCK, sm), PT_SHADE_BLOCK, 0, st>>>(rc, sc, P, q, q_hit, q_next, q_nee, ctr, ctr_next);
 }
 
 }  // namespace ptrs

@@ -158,36 +158,19 @@ __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) intersect_kernel(con
 // ---- launchers -----------------------------------------------------------------------------------------
 void launch_extend(cudaStream_t st, int sm, bool count, const DevScene& sc, const PathArrays& P, const int* q_ext, int* q_class, uint32_t cap,
                    RoundCounters* ctr, GlobalCounters* g) {
-  static int grid[2] = {0, 0};
-  if (!grid[0]) {
-    grid[0] = persistent_grid(extend_kernel<false>, 128, sm);
-    grid[1] = persistent_grid(extend_kernel<true>, 128, sm);
-  }
-  if (count) extend_kernel<true><<<grid[1], 128, 0, st>>>(sc, P, q_ext, q_class, cap, ctr, g);
-  else extend_kernel<false><<<grid[0], 128, 0, st>>>(sc, P, q_ext, q_class, cap, ctr, g);
+  if (count) extend_kernel<true><<<PT_GRID(extend_kernel<true>, 128, sm), 128, 0, st>>>(sc, P, q_ext, q_class, cap, ctr, g);
+  else extend_kernel<false><<<PT_GRID(extend_kernel<false>, 128, sm), 128, 0, st>>>(sc, P, q_ext, q_class, cap, ctr, g);
 }
 void launch_connect(cudaStream_t st, int sm, bool count, const DevScene& sc, const PathArrays& P, RoundCounters* ctr, GlobalCounters* g) {
-  static int grid[2] = {0, 0};
-  if (!grid[0]) {
-    grid[0] = persistent_grid(connect_kernel<false>, 128, sm);
-    grid[1] = persistent_grid(connect_kernel<true>, 128, sm);
-  }
-  if (count) connect_kernel<true><<<grid[1], 128, 0, st>>>(sc, P, ctr, g);
-  else connect_kernel<false><<<grid[0], 128, 0, st>>>(sc, P, ctr, g);
+  if (count) connect_kernel<true><<<PT_GRID(connect_kernel<true>, 128, sm), 128, 0, st>>>(sc, P, ctr, g);
+  else connect_kernel<false><<<PT_GRID(connect_kernel<false>, 128, sm), 128, 0, st>>>(sc, P, ctr, g);
 }
 void launch_intersect(cudaStream_t st, int sm, bool any_hit, bool count, const DevScene& sc, const PtrsRay* rays, uint32_t n, PtrsHit* hits,
                       uint8_t* occluded, uint32_t* ticket, GlobalCounters* g, const uint32_t* prim_map) {
-  static int grid[4] = {0, 0, 0, 0};
-  if (!grid[0]) {
-    grid[0] = persistent_grid(intersect_kernel<false, false>, 128, sm);
-    grid[1] = persistent_grid(intersect_kernel<false, true>, 128, sm);
-    grid[2] = persistent_grid(intersect_kernel<true, false>, 128, sm);
-    grid[3] = persistent_grid(intersect_kernel<true, true>, 128, sm);
-  }
-  if (!any_hit && !count) intersect_kernel<false, false><<<grid[0], 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map);
-  else if (!any_hit) intersect_kernel<false, true><<<grid[1], 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map);
-  else if (!count) intersect_kernel<true, false><<<grid[2], 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map);
-  else intersect_kernel<true, true><<<grid[3], 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map);
+  if (!any_hit && !count) intersect_kernel<false, false><<<PT_GRID((intersect_kernel<false, false>), 128, sm), 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map);
+  else if (!any_hit) intersect_kernel<false, true><<<PT_GRID((intersect_kernel<false, true>), 128, sm), 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map);
+  else if (!count) intersect_kernel<true, false><<<PT_GRID((intersect_kernel<true, false>), 128, sm), 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map);
+  else intersect_kernel<true, true><<<PT_GRID((intersect_kernel<true, true>), 128, sm), 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map);
 }
 
 }  // namespace ptrs

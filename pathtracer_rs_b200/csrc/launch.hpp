@@ -1,8 +1,11 @@
 // Host-callable launchers of the kernels, one group per translation unit.  Every launcher sizes its
-// persistent grid as (resident CTAs per SM) x (SM count) from the occupancy API, cached per process.
+// persistent grid as (resident CTAs per SM) x (SM count) from the occupancy API, cached per DEVICE
+// (PT_GRID below): handles on different devices may be driven from different host threads.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <atomic>
 
 #include "../../include/ptrs_b200.h"
 
@@ -12,6 +15,9 @@ struct PathArrays;
 struct RoundCounters;
 struct GlobalCounters;
 struct RenderConst;
+
+// ptrs_b200.cu: stream-ordered allocation from the library's private memory pool of the current device
+cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t st);
 
 // k_misc.cu
 void launch_generate(cudaStream_t st, int sm, const RenderConst& rc, const uint32_t* sobol, const PathArrays& P, uint64_t work_base,
@@ -38,12 +44,13 @@ void launch_intersect(cudaStream_t st, int sm, bool any_hit, bool count, const D
 
 // k_bvh.cu
 int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vertex, const float* d_pos, float4** nodes_out, uint32_t* n_nodes_out,
-                        uint32_t** perm_out);
+                        uint32_t** perm_out, uint32_t* depth_out);
 void launch_assemble_tris(cudaStream_t st, uint32_t n, const uint32_t* perm, const uint32_t* prim_vertex, const float* pos, const int32_t* prim_mesh,
                           const int32_t* prim_material, const int32_t* prim_area_light, const PtrsMesh* meshes, float4* tri_verts, uint4* tri_index,
                           uint32_t* inv_perm);
 int validate_prims_on_device(cudaStream_t st, uint32_t n, const uint32_t* prim_vertex, const int32_t* prim_mesh, const int32_t* prim_material,
-                             const int32_t* prim_area_light, uint32_t n_verts, uint32_t n_meshes, uint32_t n_materials, uint32_t n_lights);
+                             const int32_t* prim_area_light, uint32_t n_verts, uint32_t n_meshes, uint32_t n_materials, uint32_t n_lights,
+                             const PtrsLight* lights);
 int pair_layout_on_device(cudaStream_t st, const float4* d_raw, uint32_t n, uint32_t n_interior, float4** out, uint32_t* n_out);
 void launch_remap_light_prims(cudaStream_t st, PtrsLight* lights, uint32_t n_lights, const uint32_t* inv_perm);
 
@@ -54,10 +61,24 @@ void launch_remap_light_prims(cudaStream_t st, PtrsLight* lights, uint32_t n_lig
 PT_DECL_SHADE(0) PT_DECL_SHADE(1) PT_DECL_SHADE(2) PT_DECL_SHADE(3) PT_DECL_SHADE(4) PT_DECL_SHADE(5)
 #undef PT_DECL_SHADE
 
+#define PT_MAX_DEVICES 64
+// resident CTAs per SM of `kernel` on the current device, looked up once per device (lock-free: a racing second
+// lookup stores the same value)
 template <class K>
-inline int persistent_grid(K kernel, int block, int sm_count) {
-  int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+inline int persistent_grid(std::atomic<int>* per_device, K kernel, int block, int sm_count, size_t smem = 0) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PT_MAX_DEVICES) dev = 0;
+  int per_sm = per_device[dev].load(std::memory_order_relaxed);
+  if (per_sm == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    per_device[dev].store(per_sm, std::memory_order_relaxed);
+  }
   return sm_count * per_sm;
 }
+// one cache per call site (the lambda's static is unique to it)
+#define PT_GRID(kernel, block, sm)                       \
+  ([&]() {                                               \
+    static std::atomic<int> cache__[PT_MAX_DEVICES];     \
+    return persistent_grid(cache__, kernel, block, sm);  \
+  }())
 }  // namespace ptrs

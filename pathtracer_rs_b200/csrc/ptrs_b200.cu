@@ -73,22 +73,73 @@ const SobolHost& sobol_host() {
   return h;
 }
 
-// Device buffers come from the device's default stream-ordered memory pool (cudaMallocAsync on the legacy
-// stream) with the release threshold raised, so that freeing and re-creating a scene or a multi-GB path
-// workspace re-uses the reservation instead of unmapping / mapping it (cudaFree of the 6 GB workspace alone
-// costs ~0.3 s).  ptrs_trim_memory() hands the cached memory back to the driver.
-inline void keep_pool_reserved() {
-  static std::once_flag once[64];
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
-  std::call_once(once[dev], [dev] {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t keep = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-  });
+// Device buffers come from a PRIVATE stream-ordered memory pool per device (cudaMemPoolCreate, release threshold
+// raised), so that freeing and re-creating a scene or a multi-GB path workspace re-uses the reservation instead
+// of unmapping / mapping it (cudaFree of the 6 GB workspace alone costs ~0.3 s) — without touching the device's
+// default pool, which other libraries in the process (PyTorch's cudaMallocAsync backend) share.
+// ptrs_trim_memory() hands the cached memory back to the driver.
+struct DevicePools {
+  std::mutex mu;
+  cudaMemPool_t pool[PT_MAX_DEVICES] = {};
+};
+DevicePools& device_pools() {
+  static DevicePools p;
+  return p;
 }
+cudaError_t pool_of_current_device(cudaMemPool_t* out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= PT_MAX_DEVICES) return cudaErrorInvalidDevice;
+  DevicePools& P = device_pools();
+  std::lock_guard<std::mutex> lock(P.mu);
+  if (!P.pool[dev]) {
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool;
+    e = cudaMemPoolCreate(&pool, &props);
+    if (e != cudaSuccess) return e;
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    P.pool[dev] = pool;
+  }
+  *out = P.pool[dev];
+  return cudaSuccess;
+}
+}  // namespace
+
+namespace ptrs {
+// stream-ordered allocation from the library's pool of the current device; freed with cudaFreeAsync
+cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t st) {
+  cudaMemPool_t pool;
+  cudaError_t e = pool_of_current_device(&pool);
+  if (e != cudaSuccess) return e;
+  return cudaMallocFromPoolAsync(p, bytes, pool, st);
+}
+}  // namespace ptrs
+
+namespace {
+
+// Entry points run on the device their handle lives on, whatever the calling thread's current device is, and
+// leave the thread's current device as they found it.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    else if (err == cudaSuccess) prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define ON_DEVICE_OF(handle)                                                                        \
+  DeviceGuard guard__((handle)->device);                                                            \
+  if (guard__.err != cudaSuccess) return fail(PTRS_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(guard__.err))
 
 template <class T>
 struct DevBuf {
@@ -98,8 +149,7 @@ struct DevBuf {
     release();
     n = count;
     if (count == 0) return cudaSuccess;
-    keep_pool_reserved();
-    return cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), (cudaStream_t)0);
+    return ptrs::pool_alloc(reinterpret_cast<void**>(&p), count * sizeof(T), (cudaStream_t)0);
   }
   cudaError_t upload(const T* src, size_t count) {
     cudaError_t e = alloc(count);
@@ -149,6 +199,7 @@ struct PtrsScene {
   DevBuf<uint32_t> prim_map;  // device-built BVH: BVH position -> caller's primitive index
   float bvh_build_ms = 0.f;
   uint32_t n_dev_nodes = 0;
+  uint32_t bvh_depth = 0;  // largest number of pending stack entries a traversal can need
   DevBuf<float> normal, tangent, uv, texels;
   DevBuf<PtrsMesh> meshes;
   DevBuf<PtrsMaterial> materials;
@@ -181,6 +232,7 @@ struct PtrsScene {
 };
 
 struct PtrsFilm {
+  int device = 0;
   int width = 0, height = 0;
   float4* d = nullptr;
   bool owned = false;
@@ -196,6 +248,10 @@ int32_t build_render_const(const PtrsCamera* cam, const PtrsRenderParams* rp, Re
   }
   if (cam->width <= 0 || cam->height <= 0 || rp->spp <= 0 || rp->max_depth < 0) {
     *why = "bad camera resolution / spp / max_depth";
+    return PTRS_ERR_INVALID_ARGUMENT;
+  }
+  if (!(rp->filter_radius[0] > 0.f) || !(rp->filter_radius[1] > 0.f) || !(rp->filter_radius[0] < 1024.f) || !(rp->filter_radius[1] < 1024.f)) {
+    *why = "filter radius must be positive (and finite)";
     return PTRS_ERR_INVALID_ARGUMENT;
   }
   if (rp->max_depth > 120) {  // 8 Sobol dimensions per bounce must stay below 1024 (sobol.rs:178-183 panics)
@@ -477,13 +533,19 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
   uint32_t n_interior = 0;
   if (!device_bvh && d->n_prims > 0) {
     if (d->n_nodes == 0) return fail(PTRS_ERR_INVALID_ARGUMENT, "missing geometry arrays");
-    std::vector<uint32_t> owed;
+    // The walk also measures the tree's depth: a ray's pending stack holds at most one entry per interior
+    // ancestor of the node in hand (whichever child it takes first), and the traversal stack has the reference's
+    // 64 entries (accelerator.rs:366).  The reference would panic on an out-of-range index there; a deeper tree
+    // is refused here instead of being traversed with dropped subtrees.
+    std::vector<std::pair<uint32_t, uint32_t>> owed;  // (second child still owed, its depth)
     bool prev_interior = false;
+    uint32_t depth = 0, max_interior_depth = 0;
     for (uint32_t i = 0; i < d->n_nodes; ++i) {
       const PtrsBvhNode& n = d->nodes[i];
       if (i > 0 && !prev_interior) {
         if (owed.empty()) return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH (records after the end of the tree)");
-        if (owed.back() != i) return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH node (second child must follow the first child's subtree)");
+        if (owed.back().first != i) return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH node (second child must follow the first child's subtree)");
+        depth = owed.back().second;
         owed.pop_back();
       }
       if (n.n_prims > 0) {
@@ -492,13 +554,21 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
       } else {
         if (n.offset >= d->n_nodes || i + 1 >= d->n_nodes || n.axis > 2) return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH node");
         if (n.offset <= i + 1) return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH node (second child must follow the first child's subtree)");
-        owed.push_back(n.offset);
+        max_interior_depth = std::max(max_interior_depth, depth);
+        owed.emplace_back(n.offset, depth + 1);
+        depth += 1;
         prev_interior = true;
         ++n_interior;
       }
     }
     if (prev_interior || !owed.empty()) return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed BVH (nodes are shared between subtrees)");
+    if (n_interior > 0 && max_interior_depth + 1 > PT_STACK_SIZE)
+      return fail(PTRS_ERR_UNSUPPORTED, "BVH deeper than the 64-entry traversal stack (accelerator.rs:366)");
+    s->bvh_depth = n_interior > 0 ? max_interior_depth + 1 : 0;
   }
+  if ((d->n_materials && !d->materials) || (d->n_textures && !d->textures) || (d->n_mipmaps && !d->mipmaps) || (d->n_texels && !d->texels) ||
+      (d->n_lights && !d->lights) || (d->n_infinite_lights && !d->infinite_lights) || (d->n_envs && !d->envs) || (d->n_meshes && !d->meshes))
+    return fail(PTRS_ERR_INVALID_ARGUMENT, "a table has a non-zero count and a NULL pointer");
   for (uint32_t i = 0; i < d->n_materials; ++i) {
     const PtrsMaterial& m = d->materials[i];
     if (m.type < 0 || m.type >= PTRS_MAT_COUNT) return fail(PTRS_ERR_UNSUPPORTED, "unknown material type");
@@ -508,9 +578,27 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
       if (m.tex[k] < 0 || (uint32_t)m.tex[k] >= d->n_textures) return fail(PTRS_ERR_INVALID_ARGUMENT, "material texture id out of range");
     if (m.normal_map >= (int32_t)d->n_textures) return fail(PTRS_ERR_INVALID_ARGUMENT, "normal map id out of range");
   }
-  for (uint32_t i = 0; i < d->n_textures; ++i)
-    if (d->textures[i].type == PTRS_TEX_IMAGE && (d->textures[i].mip < 0 || (uint32_t)d->textures[i].mip >= d->n_mipmaps))
-      return fail(PTRS_ERR_INVALID_ARGUMENT, "image texture without a MIP pyramid");
+  for (uint32_t i = 0; i < d->n_textures; ++i) {
+    const PtrsTexture& t = d->textures[i];
+    if (t.type < PTRS_TEX_CONSTANT || t.type > PTRS_TEX_IMAGE) return fail(PTRS_ERR_UNSUPPORTED, "unknown texture type");
+    if (t.type == PTRS_TEX_IMAGE && (t.mip < 0 || (uint32_t)t.mip >= d->n_mipmaps)) return fail(PTRS_ERR_INVALID_ARGUMENT, "image texture without a MIP pyramid");
+  }
+  for (uint32_t i = 0; i < d->n_mipmaps; ++i) {  // every texel a lookup can address lies inside the pool
+    const PtrsMipMap& m = d->mipmaps[i];
+    if (m.n_levels < 1 || m.n_levels > PTRS_MAX_MIP_LEVELS || (m.channels != 1 && m.channels != 3) || m.wrap < PTRS_WRAP_REPEAT || m.wrap > PTRS_WRAP_CLAMP)
+      return fail(PTRS_ERR_INVALID_ARGUMENT, "malformed MIP pyramid header");
+    for (int l = 0; l < m.n_levels; ++l) {
+      if (m.width[l] < 1 || m.height[l] < 1) return fail(PTRS_ERR_INVALID_ARGUMENT, "MIP level with a non-positive size");
+      const uint64_t need = (uint64_t)m.width[l] * (uint64_t)m.height[l] * (uint64_t)m.channels;
+      if (m.level_offset[l] > d->n_texels || need > d->n_texels - m.level_offset[l]) return fail(PTRS_ERR_INVALID_ARGUMENT, "MIP level outside the texel pool");
+    }
+  }
+  for (uint32_t i = 0; i < d->n_meshes; ++i)
+    if (d->meshes[i].alpha_tex >= (int32_t)d->n_textures) return fail(PTRS_ERR_INVALID_ARGUMENT, "alpha texture id out of range");
+  for (uint32_t i = 0; i < d->n_infinite_lights; ++i) {
+    const int32_t li = d->infinite_lights[i];
+    if (li < 0 || (uint32_t)li >= d->n_lights || d->lights[li].type != PTRS_LIGHT_INFINITE) return fail(PTRS_ERR_INVALID_ARGUMENT, "infinite_lights names something that is not an infinite light");
+  }
   for (uint32_t i = 0; i < d->n_lights; ++i) {
     const PtrsLight& l = d->lights[i];
     if (l.type < 0 || l.type > PTRS_LIGHT_INFINITE) return fail(PTRS_ERR_UNSUPPORTED, "unknown light type");
@@ -538,10 +626,11 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
     CUDA_TRY(pm.upload(d->prim_mesh, d->n_prims));
     CUDA_TRY(pmat.upload(d->prim_material, d->n_prims));
     CUDA_TRY(pal.upload(d->prim_area_light, d->n_prims));
-    const int bad = validate_prims_on_device(0, d->n_prims, pv.p, pm.p, pmat.p, pal.p, d->n_verts, d->n_meshes, d->n_materials, d->n_lights);
+    const int bad = validate_prims_on_device(0, d->n_prims, pv.p, pm.p, pmat.p, pal.p, d->n_verts, d->n_meshes, d->n_materials, d->n_lights, s->lights.p);
     if (bad < 0) return fail(PTRS_ERR_CUDA, std::string("primitive validation: ") + cudaGetErrorString((cudaError_t)(-bad)));
     if (bad & 1) return fail(PTRS_ERR_INVALID_ARGUMENT, "primitive references an out-of-range mesh / material / light");
     if (bad & 2) return fail(PTRS_ERR_INVALID_ARGUMENT, "vertex index out of range");
+    if (bad & 4) return fail(PTRS_ERR_INVALID_ARGUMENT, "prim_area_light names a light that is not an area light");
     CUDA_TRY(s->tri_verts.alloc((size_t)d->n_prims * 3));
     CUDA_TRY(s->tri_index.alloc(d->n_prims));
     if (device_bvh) {
@@ -553,12 +642,17 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
       CUDA_TRY(cudaEventRecord(e0, 0));
       float4* nodes = nullptr;
       uint32_t* perm = nullptr;
-      const int be = build_bvh_on_device(0, d->n_prims, pv.p, pos.p, &nodes, &n_dev_nodes, &perm);
+      uint32_t dev_depth = 0;
+      const int be = build_bvh_on_device(0, d->n_prims, pv.p, pos.p, &nodes, &n_dev_nodes, &perm, &dev_depth);
       if (be != (int)cudaSuccess) return fail(PTRS_ERR_CUDA, std::string("device BVH build: ") + cudaGetErrorString((cudaError_t)be));
       s->nodes.p = nodes;
       s->nodes.n = (size_t)n_dev_nodes * 2;
       s->prim_map.p = perm;
       s->prim_map.n = d->n_prims;
+      s->bvh_depth = dev_depth;
+      // a radix tree over clustered / coincident centroids can be deeper than the traversal stack (63 Morton bits +
+      // the index tie-break); the host-side SAH build (ptrs_scene_create) is the way out for such input
+      if (dev_depth > PT_STACK_SIZE) return fail(PTRS_ERR_UNSUPPORTED, "device-built BVH deeper than the 64-entry traversal stack; build the tree on the host");
       launch_assemble_tris(0, d->n_prims, perm, pv.p, pos.p, pm.p, pmat.p, pal.p, s->meshes.p, s->tri_verts.p, s->tri_index.p, inv.p);
       launch_remap_light_prims(0, s->lights.p, d->n_lights, inv.p);
       CUDA_TRY(cudaEventRecord(e1, 0));
@@ -711,6 +805,7 @@ int32_t ptrs_scene_bvh_info(const PtrsScene* scene, uint32_t* n_nodes, float* de
 int32_t ptrs_scene_download_nodes(const PtrsScene* scene, PtrsBvhNode* nodes, uint32_t capacity, uint32_t* prim_order) {
   if (!scene || !nodes) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
   if (capacity < scene->n_dev_nodes) return fail(PTRS_ERR_INVALID_ARGUMENT, "node capacity too small");
+  ON_DEVICE_OF(scene);
   CUDA_TRY(cudaMemcpy(nodes, scene->nodes.p, (size_t)scene->n_dev_nodes * 32, cudaMemcpyDeviceToHost));
   if (prim_order) {
     if (!scene->prim_map.p) return fail(PTRS_ERR_INVALID_ARGUMENT, "the scene keeps the caller's primitive order (host-built BVH)");
@@ -721,7 +816,7 @@ int32_t ptrs_scene_download_nodes(const PtrsScene* scene, PtrsBvhNode* nodes, ui
 
 int32_t ptrs_scene_destroy(PtrsScene* scene) {
   if (!scene) return PTRS_OK;
-  cudaSetDevice(scene->device);
+  ON_DEVICE_OF(scene);
   cudaDeviceSynchronize();
   delete scene;
   return PTRS_OK;
@@ -732,7 +827,7 @@ int32_t ptrs_trim_memory(void) {
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceSynchronize());
   cudaMemPool_t pool;
-  CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+  CUDA_TRY(pool_of_current_device(&pool));
   CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
   return PTRS_OK;
 }
@@ -782,6 +877,7 @@ uint64_t ptrs_scene_device_bytes(const PtrsScene* scene) { return scene ? scene-
 static int32_t do_intersect(PtrsScene* s, const PtrsRay* d_rays, size_t n, PtrsHit* d_hits, uint8_t* d_occ, bool any_hit, bool count,
                                 cudaStream_t st) {
   if (n > 0xfffffff0ull) return fail(PTRS_ERR_INVALID_ARGUMENT, "too many rays in one call");
+  ON_DEVICE_OF(s);
   CUDA_TRY(cudaMemsetAsync(s->ticket.p, 0, 16, st));
   if (count) CUDA_TRY(cudaMemsetAsync(s->gcount.p, 0, sizeof(GlobalCounters), st));
   launch_intersect(st, s->sm_count, any_hit, count, s->dev, d_rays, (uint32_t)n, d_hits, d_occ, s->ticket.p, s->gcount.p, s->prim_map.p);
@@ -803,6 +899,7 @@ int32_t ptrs_intersect_counted_device(PtrsScene* scene, const PtrsRay* d_rays, s
                                       uint64_t* nodes_tested, uint64_t* tris_tested, void* stream) {
   if (!scene || (n && !d_rays) || (n && (any_hit ? !d_occ : !d_hits))) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
   GlobalCounters g{};
+  ON_DEVICE_OF(scene);
   if (n) {
     int32_t rc = do_intersect(scene, d_rays, n, d_hits, d_occ, any_hit != 0, true, (cudaStream_t)stream);
     if (rc != PTRS_OK) return rc;
@@ -817,6 +914,7 @@ int32_t ptrs_intersect_counted_device(PtrsScene* scene, const PtrsRay* d_rays, s
 int32_t ptrs_intersect(PtrsScene* scene, const PtrsRay* rays, size_t n, PtrsHit* hits) {
   if (!scene || (n && (!rays || !hits))) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
   if (n == 0) return PTRS_OK;
+  ON_DEVICE_OF(scene);
   DevBuf<PtrsRay> dr;
   DevBuf<PtrsHit> dh;
   CUDA_TRY(dr.upload(rays, n));
@@ -829,6 +927,7 @@ int32_t ptrs_intersect(PtrsScene* scene, const PtrsRay* rays, size_t n, PtrsHit*
 int32_t ptrs_intersect_p(PtrsScene* scene, const PtrsRay* rays, size_t n, uint8_t* occluded) {
   if (!scene || (n && (!rays || !occluded))) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
   if (n == 0) return PTRS_OK;
+  ON_DEVICE_OF(scene);
   DevBuf<PtrsRay> dr;
   DevBuf<uint8_t> dh;
   CUDA_TRY(dr.upload(rays, n));
@@ -846,10 +945,10 @@ int32_t ptrs_film_create(int32_t width, int32_t height, PtrsFilm** out) {
   f->width = width;
   f->height = height;
   f->owned = true;
+  CUDA_TRY(cudaGetDevice(&f->device));
   // pooled, stream-ordered allocation like the scene buffers: creating / destroying a film per render does not
   // pay cudaMalloc / cudaFree (device-wide synchronisation, page mapping)
-  keep_pool_reserved();
-  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&f->d), (size_t)width * height * sizeof(float4), (cudaStream_t)0));
+  CUDA_TRY(ptrs::pool_alloc(reinterpret_cast<void**>(&f->d), (size_t)width * height * sizeof(float4), (cudaStream_t)0));
   CUDA_TRY(cudaMemsetAsync(f->d, 0, (size_t)width * height * sizeof(float4), (cudaStream_t)0));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));
   *out = f.release();
@@ -857,7 +956,13 @@ int32_t ptrs_film_create(int32_t width, int32_t height, PtrsFilm** out) {
 }
 int32_t ptrs_film_wrap_device(int32_t width, int32_t height, float* d_rgbw, PtrsFilm** out) {
   if (!out || !d_rgbw || width <= 0 || height <= 0 || ((uintptr_t)d_rgbw & 15)) return fail(PTRS_ERR_INVALID_ARGUMENT, "bad film buffer (needs 16-byte alignment)");
+  cudaPointerAttributes attr{};
+  if (cudaPointerGetAttributes(&attr, d_rgbw) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+    cudaGetLastError();
+    return fail(PTRS_ERR_INVALID_ARGUMENT, "film buffer is not device memory");
+  }
   PtrsFilm* f = new PtrsFilm();
+  f->device = attr.device;
   f->width = width;
   f->height = height;
   f->d = reinterpret_cast<float4*>(d_rgbw);
@@ -867,22 +972,26 @@ int32_t ptrs_film_wrap_device(int32_t width, int32_t height, float* d_rgbw, Ptrs
 }
 int32_t ptrs_film_destroy(PtrsFilm* film) {
   if (!film) return PTRS_OK;
+  ON_DEVICE_OF(film);
   if (film->owned && film->d) cudaFreeAsync(film->d, (cudaStream_t)0);
   delete film;
   return PTRS_OK;
 }
 int32_t ptrs_film_clear(PtrsFilm* film, void* stream) {
   if (!film) return fail(PTRS_ERR_INVALID_ARGUMENT, "null film");
+  ON_DEVICE_OF(film);
   CUDA_TRY(cudaMemsetAsync(film->d, 0, (size_t)film->width * film->height * sizeof(float4), (cudaStream_t)stream));
   return PTRS_OK;
 }
 int32_t ptrs_film_download(PtrsFilm* film, float* rgbw) {
   if (!film || !rgbw) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  ON_DEVICE_OF(film);
   CUDA_TRY(cudaMemcpy(rgbw, film->d, (size_t)film->width * film->height * sizeof(float4), cudaMemcpyDeviceToHost));
   return PTRS_OK;
 }
 int32_t ptrs_film_resolve(PtrsFilm* film, float* rgb) {
   if (!film || !rgb) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  ON_DEVICE_OF(film);
   const uint32_t n = (uint32_t)film->width * film->height;
   DevBuf<float> d;
   CUDA_TRY(d.alloc((size_t)n * 3));
@@ -893,6 +1002,7 @@ int32_t ptrs_film_resolve(PtrsFilm* film, float* rgb) {
 }
 int32_t ptrs_film_resolve_srgb8(PtrsFilm* film, uint8_t* rgba) {
   if (!film || !rgba) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  ON_DEVICE_OF(film);
   const uint32_t n = (uint32_t)film->width * film->height;
   DevBuf<uint8_t> d;
   CUDA_TRY(d.alloc((size_t)n * 4));
@@ -941,7 +1051,6 @@ static int32_t render_impl(PtrsScene* s, const PtrsCamera* cam, const PtrsRender
   std::string why;
   int32_t r = build_render_const(cam, rp, &rc, &why);
   if (r != PTRS_OK) return fail(r, why);
-  CUDA_TRY(cudaSetDevice(s->device));
   const uint32_t bw = ((uint32_t)rc.sb_ext[0] + 7u) >> 3, bh = ((uint32_t)rc.sb_ext[1] + 3u) >> 2;
   const uint64_t per_sample = (uint64_t)bw * bh * 32u;
   const uint64_t total = list_xy ? (uint64_t)n_list : per_sample * (uint64_t)rc.s_count;
@@ -1023,14 +1132,21 @@ static int32_t render_impl(PtrsScene* s, const PtrsCamera* cam, const PtrsRender
 int32_t ptrs_render(PtrsScene* scene, const PtrsCamera* camera, const PtrsRenderParams* params, PtrsFilm* film, void* stream) {
   if (!scene || !camera || !params || !film) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
   if (film->width != camera->width || film->height != camera->height) return fail(PTRS_ERR_INVALID_ARGUMENT, "film / camera resolution mismatch");
-  return render_impl(scene, camera, params, film, nullptr, nullptr, 0, nullptr, (cudaStream_t)stream);
+  if (film->device != scene->device) return fail(PTRS_ERR_INVALID_ARGUMENT, "film and scene live on different devices");
+  ON_DEVICE_OF(scene);
+  const int32_t r = render_impl(scene, camera, params, film, nullptr, nullptr, 0, nullptr, (cudaStream_t)stream);
+  if (r != PTRS_OK) cudaStreamSynchronize((cudaStream_t)stream);  // nothing of the failed call may still run when its buffers are released
+  return r;
 }
 
 int32_t ptrs_path_radiance(PtrsScene* scene, const PtrsCamera* camera, const PtrsRenderParams* params, const int32_t* pixels_xy,
                            const int32_t* sample_nums, size_t n, float* out_rgb) {
   if (!scene || !camera || !params || (n && (!pixels_xy || !sample_nums || !out_rgb))) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
   if (n == 0) return PTRS_OK;
-  return render_impl(scene, camera, params, nullptr, pixels_xy, sample_nums, n, out_rgb, 0);
+  ON_DEVICE_OF(scene);
+  const int32_t r = render_impl(scene, camera, params, nullptr, pixels_xy, sample_nums, n, out_rgb, 0);
+  if (r != PTRS_OK) cudaStreamSynchronize(0);
+  return r;
 }
 
 int32_t ptrs_stats(const PtrsScene* scene, PtrsStats* out) {

@@ -76,9 +76,10 @@ void read_scanline(Reader& r, int w, uint8_t* out) {
     uint8_t q[4] = {r.byte(), r.byte(), r.byte(), r.byte()};
     if (q[0] == 1 && q[1] == 1 && q[2] == 1) {
       if (x == 0) throw std::runtime_error("HDR: repeat marker at the start of a scanline");
-      int count = (int)q[3] << shift;
+      if (shift > 24) throw std::runtime_error("HDR: bad old-style run");  // a fifth consecutive repeat marker would shift out of the int
+      const int64_t count = (int64_t)q[3] << shift;
       if (x + count > w) throw std::runtime_error("HDR: bad old-style run");
-      for (int k = 0; k < count; ++k, ++x) std::memcpy(out + 4 * x, out + 4 * (x - 1), 4);
+      for (int64_t k = 0; k < count; ++k, ++x) std::memcpy(out + 4 * x, out + 4 * (x - 1), 4);
       shift += 8;
     } else {
       std::memcpy(out + 4 * x, q, 4);

@@ -112,6 +112,7 @@ struct Decoder {
   }
   int get_bits(int n) {
     if (n == 0) return 0;
+    if (n < 0 || n > 16) bad("bad bit count");  // never shift by 32 or more, whatever the tables say
     if (bitcnt < n) fill();
     const int v = (int)(bitbuf >> (32 - n));
     bitbuf <<= n;
@@ -209,6 +210,7 @@ struct Decoder {
   // ---- one block of one scan -------------------------------------------------------------------------
   void block_sequential(Component& c, int16_t* b) {
     const int t = decode(dc[c.td]);
+    if (t > 11) bad("bad DC category");  // T.81 F.1.2.1: SSSS <= 11 for 8-bit samples; a corrupt DHT can hold any byte
     c.pred += receive_extend(t);
     b[0] = (int16_t)c.pred;
     for (int k = 1; k < 64;) {
@@ -227,6 +229,7 @@ struct Decoder {
   }
   void block_dc_first(Component& c, int16_t* b, int al) {
     const int t = decode(dc[c.td]);
+    if (t > 11) bad("bad DC category");
     c.pred += receive_extend(t);
     b[0] = (int16_t)(c.pred * (1 << al));
   }

@@ -21,9 +21,9 @@ LIB  := pathtracer_rs_b200/lib
 OBJ  := build/obj
 BLOB := $(abspath pathtracer_rs_b200/data/sobol_tables.bin)
 
-DEV_HDRS  := $(wildcard $(CS)/*.cuh) $(CS)/launch.hpp include/ptrs_b200.h
+DEV_HDRS  := $(wildcard $(CS)/*.cuh) $(CS)/launch.hpp $(CS)/handles.hpp include/ptrs_b200.h
 SHADE_OBJ := $(foreach m,0 1 2 3 4 5,$(OBJ)/k_shade_$(m).o)
-CUDA_OBJ  := $(OBJ)/ptrs_b200.o $(OBJ)/k_trace.o $(OBJ)/k_misc.o $(OBJ)/k_bvh.o $(SHADE_OBJ) $(OBJ)/sobol_blob.o
+CUDA_OBJ  := $(OBJ)/ptrs_b200.o $(OBJ)/multi_gpu.o $(OBJ)/k_trace.o $(OBJ)/k_misc.o $(OBJ)/k_bvh.o $(SHADE_OBJ) $(OBJ)/sobol_blob.o
 
 all: $(LIB)/libptrs_b200.so $(LIB)/libptrs_host.so oracle/_build/liboracle.so examples
 
@@ -44,7 +44,7 @@ $(OBJ)/sobol_blob.o: $(CS)/sobol_blob.S $(BLOB)
 
 $(LIB)/libptrs_b200.so: $(CUDA_OBJ)
 	@mkdir -p $(LIB)
-	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $(CUDA_OBJ) -cudart static
+	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $(CUDA_OBJ) -cudart static -ldl -lpthread
 
 $(LIB)/libptrs_host.so: $(wildcard $(HS)/*.cpp) $(wildcard $(HS)/*.hpp) include/ptrs_b200.h
 	@mkdir -p $(LIB)

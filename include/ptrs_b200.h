@@ -34,13 +34,15 @@ extern "C" {
 #endif
 
 #define PTRS_ABI_VERSION 1
+#define PTRS_COMM_ID_BYTES 128 /* size of the communicator id ptrs_comm_unique_id hands out (ncclUniqueId) */
 
 typedef enum PtrsStatus {
   PTRS_OK = 0,
   PTRS_ERR_INVALID_ARGUMENT = -1,
   PTRS_ERR_CUDA = -2,
   PTRS_ERR_UNSUPPORTED = -3,
-  PTRS_ERR_OUT_OF_MEMORY = -4
+  PTRS_ERR_OUT_OF_MEMORY = -4,
+  PTRS_ERR_NCCL = -5
 } PtrsStatus;
 
 /* ------------------------------------------------------------------------------------------------
@@ -283,10 +285,14 @@ typedef struct PtrsStats {
   uint32_t launches; /* kernels launched by the last call */
   uint32_t batches;
   uint32_t extend_launches, connect_launches;
+  /* ms_shadow split into its two kernels: connect_kernel (shadow + MIS ray traversal) and connect_resolve_kernel */
+  float ms_connect_trace, ms_resolve;
 } PtrsStats;
 
 typedef struct PtrsScene PtrsScene; /* opaque */
 typedef struct PtrsFilm PtrsFilm;   /* opaque: W x H x (r, g, b, weight) f32 on the device */
+typedef struct PtrsComm PtrsComm;   /* opaque: one rank of an NCCL communicator over the GPUs that share a film */
+typedef struct PtrsMultiScene PtrsMultiScene; /* opaque: one scene replica, film and stream per device, one process */
 
 /* ------------------------------------------------------------------------------------------------
  * Entry points
@@ -363,6 +369,47 @@ int32_t ptrs_path_radiance(PtrsScene* scene, const PtrsCamera* camera, const Ptr
                            const int32_t* pixels_xy, const int32_t* sample_nums, size_t n, float* out_rgb);
 int32_t ptrs_stats(const PtrsScene* scene, PtrsStats* out);
 int32_t ptrs_set_stats_mode(PtrsScene* scene, int32_t count_visits); /* counted traversal in render */
+
+/* ------------------------------------------------------------------------------------------------
+ * Several GPUs of one node.  The reference parallelises PathIntegrator::render over
+ * 16x16 tiles with rayon and merges tiles into the one film under a lock (integrator.rs:617-637,
+ * film.rs:213-228); across GPUs the scene is replicated, the Sobol sample numbers of every pixel are
+ * dealt round-robin (device g of N renders s = g (mod N); the global Sobol index is a pure function
+ * of (pixel, sample number), sampler/sobol.rs:169-175) and the additive films are summed with ONE
+ * NCCL reduce over NVLink.  The result equals the single-GPU film up to float summation order.
+ * NCCL is loaded at run time (libnccl.so.2, or the file named by PTRS_NCCL_LIB); without it these
+ * calls fail with PTRS_ERR_NCCL and everything else keeps working.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* (a) one process, N devices: the library runs one host thread, stream, scene replica and film per
+ * device (ncclCommInitAll).  devices == NULL means devices 0 .. n_devices-1; device_bvh != 0 builds
+ * the tree on each device (ptrs_scene_create_device_bvh).  The film of devices[0] is the root. */
+int32_t ptrs_multi_create(const PtrsSceneDesc* desc, int32_t n_devices, const int32_t* devices,
+                          int32_t device_bvh, PtrsMultiScene** out);
+int32_t ptrs_multi_destroy(PtrsMultiScene* multi);
+int32_t ptrs_multi_device_count(const PtrsMultiScene* multi, int32_t* n_devices);
+/* PathIntegrator::render on all devices: clears the per-device films, renders shard g of the sample
+ * numbers selected by `params` on device g, reduces the films into the root film and — if host_rgbw is
+ * not NULL — downloads the raw sums (W*H*4 floats, as ptrs_film_download).  per_device_stats (may be
+ * NULL) receives n_devices records; total_ms (may be NULL) the wall time of the whole call. */
+int32_t ptrs_multi_render(PtrsMultiScene* multi, const PtrsCamera* camera, const PtrsRenderParams* params,
+                          float* host_rgbw, PtrsStats* per_device_stats, float* total_ms);
+/* the root film (owned by the handle; valid until the next ptrs_multi_render with another resolution) for
+ * ptrs_film_resolve / ptrs_film_resolve_srgb8 */
+int32_t ptrs_multi_root_film(PtrsMultiScene* multi, PtrsFilm** film);
+/* the replica on device index g, e.g. for ptrs_intersect */
+int32_t ptrs_multi_scene(PtrsMultiScene* multi, int32_t g, PtrsScene** scene);
+
+/* (b) one process per GPU (MPI / torchrun style): rank 0 obtains an id, ships its 128 bytes to the other
+ * ranks by whatever channel the host has, every rank joins on its current device; then each rank renders
+ * its shard (PtrsRenderParams.sample_stride / sample_phase) and calls ptrs_film_reduce. */
+int32_t ptrs_comm_unique_id(uint8_t id[PTRS_COMM_ID_BYTES]);
+int32_t ptrs_comm_init_rank(const uint8_t id[PTRS_COMM_ID_BYTES], int32_t n_ranks, int32_t rank, PtrsComm** out);
+int32_t ptrs_comm_destroy(PtrsComm* comm);
+int32_t ptrs_comm_info(const PtrsComm* comm, int32_t* n_ranks, int32_t* rank);
+/* Film::merge_film_tile across ranks (film.rs:213-228): sum of every rank's film into `root`'s film, in
+ * place, enqueued on `stream` (ncclReduce, f32 sum, W*H*4 elements).  Films of the other ranks are unchanged. */
+int32_t ptrs_film_reduce(PtrsComm* comm, PtrsFilm* film, int32_t root, void* stream);
 
 /* Parity probes: single stages of the path, for bit-level checks against the oracle. */
 /* SobolSampler::{start_pixel, get_index_for_sample, sample_dimension} (sampler/sobol.rs:81-193):

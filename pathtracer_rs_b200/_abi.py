@@ -89,7 +89,8 @@ class PtrsStats(C.Structure):
                 ("nee_nodes_tested", C.c_uint64), ("nee_tris_tested", C.c_uint64),
                 ("ms_generate", C.c_float), ("ms_extend", C.c_float), ("ms_shade", C.c_float), ("ms_shadow", C.c_float),
                 ("ms_accumulate", C.c_float), ("ms_total", C.c_float), ("launches", C.c_uint32), ("batches", C.c_uint32),
-                ("extend_launches", C.c_uint32), ("connect_launches", C.c_uint32)]
+                ("extend_launches", C.c_uint32), ("connect_launches", C.c_uint32),
+                ("ms_connect_trace", C.c_float), ("ms_resolve", C.c_float)]
 
 
 # material / texture / light / wrap enums

@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "handles.hpp"
 #include "launch.hpp"
 #include "wavefront.cuh"
 
@@ -29,6 +30,9 @@ int32_t fail(int32_t code, const std::string& msg) {
   g_err = msg;
   return code;
 }
+}  // namespace
+int32_t ptrs::set_error(int32_t code, const std::string& msg) { return fail(code, msg); }
+namespace {
 #define CUDA_TRY(expr)                                                                                         \
   do {                                                                                                         \
     cudaError_t e__ = (expr);                                                                                  \
@@ -231,13 +235,6 @@ struct PtrsScene {
   }
 };
 
-struct PtrsFilm {
-  int device = 0;
-  int width = 0, height = 0;
-  float4* d = nullptr;
-  bool owned = false;
-};
-
 namespace {
 
 int32_t build_render_const(const PtrsCamera* cam, const PtrsRenderParams* rp, RenderConst* rc, std::string* why) {
@@ -400,6 +397,7 @@ int32_t check_pixel_list(const RenderConst& rc, const int32_t* xy, const int32_t
   return PTRS_OK;
 }
 
+enum { ST_GENERATE, ST_EXTEND, ST_SHADE, ST_CONNECT, ST_ACCUMULATE, ST_RESOLVE, ST_COUNT };
 struct StageTimer {
   PtrsScene* s;
   cudaStream_t st;
@@ -418,7 +416,7 @@ struct StageTimer {
     cudaEventRecord(next(), st);
   }
   void end() { cudaEventRecord(next(), st); }
-  void collect(float ms[5]) {  // call after a stream sync
+  void collect(float ms[ST_COUNT]) {  // call after a stream sync
     for (auto& sp_ : spans) {
       float t = 0.f;
       cudaEventElapsedTime(&t, s->stage_events[sp_.second], s->stage_events[sp_.second + 1]);
@@ -428,7 +426,6 @@ struct StageTimer {
     used = 0;
   }
 };
-enum { ST_GENERATE, ST_EXTEND, ST_SHADE, ST_CONNECT, ST_ACCUMULATE };
 
 // One wavefront batch: `n_work` path slots already described by (work_base | lists); runs rounds until
 // every path has ended.  Leaves per-path radiance in ws.L.
@@ -473,6 +470,8 @@ int32_t run_batch(PtrsScene* s, const RenderConst& rc, uint64_t work_base, uint3
       tm.begin(ST_CONNECT);
       if (s->dev.n_lights > 0) {
         launch_connect(st, sm, s->count_visits, s->dev, P, c, w.gcount.p);
+        tm.end();
+        tm.begin(ST_RESOLVE);
         launch_connect_resolve(st, sm, s->dev, P, w.q_nee.p, c);
         s->stats.launches += 1;
         s->stats.connect_launches += 1;
@@ -1073,7 +1072,7 @@ static int32_t render_impl(PtrsScene* s, const PtrsCamera* cam, const PtrsRender
     CUDA_TRY(d_s.upload(list_s, n_list));
   }
   StageTimer tm{s, st};
-  float ms[5] = {0, 0, 0, 0, 0};
+  float ms[ST_COUNT] = {};
   uint64_t ext_rays = 0, paths = 0;
   CUDA_TRY(cudaEventRecord(s->ev[0], st));
   // equal batches (whole 8x4 blocks) rather than full ones and a remainder: a nearly empty last batch would
@@ -1123,7 +1122,9 @@ static int32_t render_impl(PtrsScene* s, const PtrsCamera* cam, const PtrsRender
   s->stats.ms_generate = ms[ST_GENERATE];
   s->stats.ms_extend = ms[ST_EXTEND];
   s->stats.ms_shade = ms[ST_SHADE];
-  s->stats.ms_shadow = ms[ST_CONNECT];
+  s->stats.ms_shadow = ms[ST_CONNECT] + ms[ST_RESOLVE];
+  s->stats.ms_connect_trace = ms[ST_CONNECT];
+  s->stats.ms_resolve = ms[ST_RESOLVE];
   s->stats.ms_accumulate = ms[ST_ACCUMULATE];
   s->stats.ms_total = total_ms;
   return PTRS_OK;

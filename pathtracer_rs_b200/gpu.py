@@ -30,6 +30,8 @@ EXPORTS = [
     "ptrs_film_sample_bounds", "ptrs_render_params_default", "ptrs_render", "ptrs_path_radiance", "ptrs_stats",
     "ptrs_set_stats_mode", "ptrs_sobol_samples", "ptrs_generate_rays", "ptrs_trim_memory", "ptrs_scene_create_device_bvh",
     "ptrs_scene_bvh_info", "ptrs_scene_download_nodes", "ptrs_read_bandwidth", "ptrs_gather_bandwidth",
+    "ptrs_multi_create", "ptrs_multi_destroy", "ptrs_multi_device_count", "ptrs_multi_render", "ptrs_multi_root_film", "ptrs_multi_scene",
+    "ptrs_comm_unique_id", "ptrs_comm_init_rank", "ptrs_comm_destroy", "ptrs_comm_info", "ptrs_film_reduce",
 ]
 
 
@@ -85,6 +87,17 @@ def lib():
         L.ptrs_gather_bandwidth.argtypes = [sz, i32, fp]
         L.ptrs_sobol_samples.argtypes = [camp, rpp, i32p, i32p, sz, i32p, sz, fp, u64p]
         L.ptrs_generate_rays.argtypes = [camp, rpp, i32p, i32p, sz, rayp, fp, fp]
+        L.ptrs_multi_create.argtypes = [descp, i32, i32p, i32, C.POINTER(vp)]
+        L.ptrs_multi_destroy.argtypes = [vp]
+        L.ptrs_multi_device_count.argtypes = [vp, i32p]
+        L.ptrs_multi_render.argtypes = [vp, camp, rpp, fp, C.POINTER(PtrsStats), fp]
+        L.ptrs_multi_root_film.argtypes = [vp, C.POINTER(vp)]
+        L.ptrs_multi_scene.argtypes = [vp, i32, C.POINTER(vp)]
+        L.ptrs_comm_unique_id.argtypes = [u8p]
+        L.ptrs_comm_init_rank.argtypes = [u8p, i32, i32, C.POINTER(vp)]
+        L.ptrs_comm_destroy.argtypes = [vp]
+        L.ptrs_comm_info.argtypes = [vp, i32p, i32p]
+        L.ptrs_film_reduce.argtypes = [vp, vp, i32, vp]
         _LIB = L
     return _LIB
 
@@ -259,6 +272,75 @@ class RenderScene:
         _check(lib().ptrs_path_radiance(self._h, C.byref(cam), C.byref(params), _p(px, C.c_int32), _p(sm, C.c_int32), px.shape[0],
                                         _p(out, C.c_float)))
         return out
+
+
+class Comm:
+    """One rank of the NCCL communicator the films are reduced over when every GPU has its own process
+    (ptrs_comm_*).  Rank 0 calls Comm.unique_id() and ships the 128 bytes to the others by any channel."""
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        _check(lib().ptrs_comm_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, unique_id, n_ranks, rank):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        h = C.c_void_p()
+        _check(lib().ptrs_comm_init_rank(buf, n_ranks, rank, C.byref(h)))
+        self._h, self.n_ranks, self.rank = h, n_ranks, rank
+
+    def reduce_film(self, film, root=0, stream=None):
+        """film.rs:213-228 across ranks: sum of all ranks' films into root's, on `stream`."""
+        _check(lib().ptrs_film_reduce(self._h, film._h, root, C.c_void_p(stream or 0)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ptrs_comm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class MultiScene:
+    """Scene replicas on several devices of this process + the films they reduce into (ptrs_multi_*)."""
+
+    def __init__(self, flat, n_devices, devices=None, device_bvh=False):
+        desc = flat.desc if isinstance(flat, FlatScene) else flat
+        h = C.c_void_p()
+        dv = (C.c_int32 * n_devices)(*devices) if devices is not None else None
+        _check(lib().ptrs_multi_create(desc, n_devices, dv, 1 if device_bvh else 0, C.byref(h)))
+        self._h, self.n_devices = h, n_devices
+
+    def render(self, camera, params, download=True):
+        """PathIntegrator::render over all devices.  Returns (raw film sums (H, W, 4) or None, per-device stats, total ms)."""
+        out = np.empty((camera.height, camera.width, 4), dtype=np.float32) if download else None
+        st = (PtrsStats * self.n_devices)()
+        ms = C.c_float(0)
+        _check(lib().ptrs_multi_render(self._h, C.byref(camera), C.byref(params), _p(out, C.c_float) if download else None, st, C.byref(ms)))
+        stats = [{k: getattr(s, k) for k, _ in PtrsStats._fields_} for s in st]
+        return out, stats, ms.value
+
+    def render_into(self, camera, params, host_rgbw):
+        """Same, into a caller-owned (H, W, 4) float32 array (e.g. pinned memory)."""
+        st = (PtrsStats * self.n_devices)()
+        ms = C.c_float(0)
+        _check(lib().ptrs_multi_render(self._h, C.byref(camera), C.byref(params), C.cast(C.c_void_p(host_rgbw), C.POINTER(C.c_float)), st, C.byref(ms)))
+        return [{k: getattr(s, k) for k, _ in PtrsStats._fields_} for s in st], ms.value
+
+    def to_channel_updates(self, width, height):
+        f = C.c_void_p()
+        _check(lib().ptrs_multi_root_film(self._h, C.byref(f)))
+        out = np.empty((height, width, 3), dtype=np.float32)
+        _check(lib().ptrs_film_resolve(f, _p(out, C.c_float)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ptrs_multi_destroy(self._h)
+            self._h = None
+
+    __del__ = close
 
 
 class SamplerBuilder:

@@ -50,6 +50,8 @@ def lib():
         L.ptrs_host_scene_bvh_seconds.argtypes = [vp]
         L.ptrs_host_make_scene.restype = vp
         L.ptrs_host_make_scene.argtypes = [i32, u64, u64, i32, i32, C.POINTER(PtrsCamera), i32]
+        L.ptrs_host_make_scene_env.restype = vp
+        L.ptrs_host_make_scene_env.argtypes = [i32, u64, u64, i32, i32, C.POINTER(PtrsCamera), i32, C.c_char_p]
         L.ptrs_host_synth_sky.argtypes = [i32, i32, u64, fp]
         L.ptrs_host_make_camera.argtypes = [fp, fp, f32, f32, f32, f32, i32, i32, C.POINTER(PtrsCamera)]
         L.ptrs_host_mitsuba_camera.argtypes = [fp, f32, i32, i32, i32, i32, C.POINTER(PtrsCamera)]
@@ -153,10 +155,16 @@ class FlatScene:
         return pos[idx]  # (n_prims, 3, 3)
 
 
-def make_scene(kind, seed=1, n_tris=0, res=(512, 512), n_threads=0):
-    """Ready-made scene + camera. kind: SCENE_* constant."""
+# The reference's environment map (data/abandoned_tank_farm_04_1k.hdr, what `<emitter type="sunsky"/>` loads:
+# pathtracer/importer/mitsuba.rs:400-418), kept as a test / bench fixture.
+TANK_FARM_HDR = os.path.join(os.path.dirname(_HERE), "tests", "golden", "abandoned_tank_farm_04_1k.hdr")
+
+
+def make_scene(kind, seed=1, n_tris=0, res=(512, 512), n_threads=0, env_hdr=None):
+    """Ready-made scene + camera. kind: SCENE_* constant.  env_hdr (SCENE_CORNELL_ENV only): Radiance .hdr file to
+    use as the environment map instead of the synthetic sky."""
     cam = PtrsCamera()
-    h = lib().ptrs_host_make_scene(kind, seed, n_tris, res[0], res[1], C.byref(cam), n_threads)
+    h = lib().ptrs_host_make_scene_env(kind, seed, n_tris, res[0], res[1], C.byref(cam), n_threads, os.fsencode(env_hdr) if env_hdr else None)
     return FlatScene(h), cam
 
 

@@ -127,8 +127,10 @@ double ptrs_host_scene_bvh_seconds(void* s) { return ((SceneBox*)s)->fs.bvh_buil
 
 // ---- ready-made scenes ------------------------------------------------------------------------
 // kind: 0 cornell, 1 cornell + synthetic sky, 2 material field (C3), 3 terrain (C4), 4 atrium (C5)
-void* ptrs_host_make_scene(int kind, uint64_t seed, uint64_t n_tris, int res_w, int res_h, PtrsCamera* cam,
-                           int n_threads) {
+// env_hdr (kind 1 only; may be NULL): Radiance .hdr file used as the environment map — the reference's
+// `<emitter type="sunsky"/>` maps to data/abandoned_tank_farm_04_1k.hdr (pathtracer/importer/mitsuba.rs:400-418)
+void* ptrs_host_make_scene_env(int kind, uint64_t seed, uint64_t n_tris, int res_w, int res_h, PtrsCamera* cam,
+                               int n_threads, const char* env_hdr) {
   SceneBox* box = nullptr;
   if (guard([&] {
         SceneBuilder b;
@@ -139,8 +141,13 @@ void* ptrs_host_make_scene(int kind, uint64_t seed, uint64_t n_tris, int res_w, 
             c = cornell_camera(res_w, res_h);
             break;
           case 1: {
-            std::vector<float> sky = synth_sky(1024, 512, seed);
-            build_cornell(b, sky.data(), 1024, 512);
+            if (env_hdr && *env_hdr) {
+              const ImageF32 img = load_hdr(env_hdr);
+              build_cornell(b, img.data.data(), img.width, img.height);
+            } else {
+              std::vector<float> sky = synth_sky(1024, 512, seed);
+              build_cornell(b, sky.data(), 1024, 512);
+            }
             c = cornell_camera(res_w, res_h);
             break;
           }
@@ -158,6 +165,10 @@ void* ptrs_host_make_scene(int kind, uint64_t seed, uint64_t n_tris, int res_w, 
     return nullptr;
   }
   return box;
+}
+
+void* ptrs_host_make_scene(int kind, uint64_t seed, uint64_t n_tris, int res_w, int res_h, PtrsCamera* cam, int n_threads) {
+  return ptrs_host_make_scene_env(kind, seed, n_tris, res_w, res_h, cam, n_threads, nullptr);
 }
 
 // ---- scene files (importers.hpp) and image files (image_io.hpp) ----------------------------------

@@ -56,6 +56,15 @@ def cornell(host):
 
 @pytest.fixture(scope="session")
 def cornell_env(host):
+    """BASELINE configs[1]'s scene: Cornell box + the reference's own environment map (data/abandoned_tank_farm_04_1k.hdr,
+    committed as a fixture), 2048 x 1024 Distribution2D per light.rs:375-387."""
+    assert os.path.exists(host.TANK_FARM_HDR)
+    return host.make_scene(host.SCENE_CORNELL_ENV, seed=1, res=(96, 96), env_hdr=host.TANK_FARM_HDR)
+
+
+@pytest.fixture(scope="session")
+def cornell_sky(host):
+    """The same box under the synthetic sky the larger procedural scenes (C3, C5) use."""
     return host.make_scene(host.SCENE_CORNELL_ENV, seed=1, res=(96, 96))
 
 

@@ -117,7 +117,7 @@ def test_traversal_counters_match_oracle(gpu, host, oracle, terrain_small):
     scene.close()
 
 
-@pytest.mark.parametrize("scene_name,depth", [("cornell", 15), ("cornell_env", 15), ("field_small", 8), ("atrium_small", 8), ("terrain_small", 4)])
+@pytest.mark.parametrize("scene_name,depth", [("cornell", 15), ("cornell_env", 15), ("cornell_sky", 15), ("field_small", 8), ("atrium_small", 8), ("terrain_small", 4)])
 def test_path_radiance(gpu, host, oracle, request, scene_name, depth):
     """li() per camera path.  Identical Sobol numbers and bit-identical hits mean almost every path matches
     to float rounding; a few diverge where a libm ulp flips a discrete decision."""
@@ -135,7 +135,7 @@ def test_path_radiance(gpu, host, oracle, request, scene_name, depth):
     scene.close()
 
 
-@pytest.mark.parametrize("scene_name,spp,depth", [("cornell", 64, 15), ("cornell_env", 64, 15), ("field_small", 32, 8), ("atrium_small", 32, 8)])
+@pytest.mark.parametrize("scene_name,spp,depth", [("cornell", 64, 15), ("cornell_env", 64, 15), ("cornell_sky", 64, 15), ("field_small", 32, 8), ("atrium_small", 32, 8)])
 def test_render_image_matches_oracle(gpu, host, oracle, request, scene_name, spp, depth):
     flat, cam = request.getfixturevalue(scene_name)
     scene = gpu.RenderScene(flat)
@@ -373,7 +373,8 @@ def test_full_size_workload_properties(gpu, host, oracle, name):
     properties: the path count of SURVEY.md §8; two sample shards sum to the whole render (the multi-GPU decomposition);
     a render is reproducible; and a strided sample of 16 x 16 tiles of the image, all spp, matches the oracle."""
     kind, n_tris, res, spp, tile_stride, n_paths = FULL_SIZE[name]
-    flat, cam = host.make_scene(getattr(host, kind), seed=1, n_tris=n_tris, res=res)
+    # C2 runs under the reference's own environment map (data/abandoned_tank_farm_04_1k.hdr), the procedural scenes under the synthetic sky
+    flat, cam = host.make_scene(getattr(host, kind), seed=1, n_tris=n_tris, res=res, env_hdr=host.TANK_FARM_HDR if kind == "SCENE_CORNELL_ENV" else None)
     scene = gpu.RenderScene(flat)
     integ = gpu.PathIntegrator(gpu.SamplerBuilder(spp), max_depth=15)
     full = gpu.Film(cam.width, cam.height)
@@ -402,6 +403,121 @@ def test_full_size_workload_properties(gpu, host, oracle, name):
     want = ref_film[..., :3][inner] / ref_film[..., 3:][inner]
     assert _rel_mse(got, want) < 1e-3
     scene.close()
+
+
+def test_c1_whole_image_matches_oracle(gpu, host, oracle):
+    """BASELINE configs[0] as the reference runs it: data/cornell-box.xml, 512 x 512, 16 spp, max_depth 15 — the whole
+    image (4.26 M camera paths) through both integrators, not a tile sample."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    flat, cam = host.import_scene(os.path.join(root, "tests", "golden", "cornell-box.xml"), res=(512, 512))
+    scene = gpu.RenderScene(flat)
+    integ = gpu.PathIntegrator(gpu.SamplerBuilder(16), max_depth=15)
+    film = gpu.Film(512, 512)
+    st = integ.render(cam, scene, film)
+    assert st["camera_paths"] == 516 * 516 * 16
+    ofilm, ost = oracle.render(flat, cam, integ.params)
+    raw = film.download()
+    assert np.allclose(raw[..., 3], ofilm[..., 3], rtol=1e-4)
+    img, oimg = film.to_channel_updates(), oracle.resolve(ofilm)
+    assert _rel_mse(img, oimg) < 1e-3  # north_star tolerance; measured far below
+    assert _rel_mse(img, oimg) < 1e-6
+    for k in ("extension_rays", "shadow_rays", "mis_rays"):
+        assert abs(st[k] - ost[k]) <= 0.002 * ost[k] + 8, (k, st[k], ost[k])
+    scene.close()
+
+
+def test_c4_hit_parity_at_full_size(gpu, host, oracle):
+    """BASELINE configs[3] at its real size: the 10 M-triangle terrain with the reference-built SAH tree (15.9 M nodes),
+    2^18 coherent camera rays and 2^18 incoherent rays, closest hit and any hit: primitive ids, t and barycentrics
+    bit-equal to the oracle, and the node / triangle test counters (the figures bench.py's roofline is computed from) equal."""
+    import torch
+
+    flat, cam = host.make_scene(host.SCENE_TERRAIN, seed=1, n_tris=10_000_000, res=(512, 512))
+    assert flat.n_prims > 9_900_000 and flat.bvh_depth <= 64
+    scene = gpu.RenderScene(flat)
+    bmin, bmax = flat.world_bound()
+    sets = {"coherent": host.coherent_rays(cam, 512), "incoherent": host.incoherent_rays(bmin, bmax, 42, 1 << 18)}
+    for name, rays in sets.items():
+        n = rays.shape[0]
+        assert n == 1 << 18
+        o, (onodes, otris) = oracle.intersect(flat, rays)
+        op, (pnodes, ptris) = oracle.intersect_p(flat, rays)
+        _check_hits(scene.intersect(rays), o)
+        assert np.array_equal(scene.intersect_p(rays), op)
+        assert 0.05 < (o["prim"] >= 0).mean() <= 1.0, name
+        d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).cuda()
+        d_hits = torch.empty(n * 20, dtype=torch.uint8, device="cuda")
+        d_occ = torch.empty(n, dtype=torch.uint8, device="cuda")
+        assert scene.intersect_counted_device(d_rays.data_ptr(), n, d_hits.data_ptr()) == (onodes, otris)
+        _check_hits(d_hits.cpu().numpy().view(host.HIT_DTYPE), o)
+        assert scene.intersect_counted_device(d_rays.data_ptr(), n, d_occ.data_ptr(), any_hit=True) == (pnodes, ptris)
+        assert np.array_equal(d_occ.cpu().numpy(), op)
+    # the same mesh with the tree built on the device: same closest hits up to near-ties (see the small-scene test)
+    dev = gpu.RenderScene(flat, device_bvh=True)
+    rays = sets["incoherent"]
+    a, b = scene.intersect(rays), dev.intersect(rays)
+    hit = a["prim"] >= 0
+    assert np.array_equal(hit, b["prim"] >= 0)
+    assert (a["t"][hit] != b["t"][hit]).mean() < 1e-4 and np.allclose(a["t"][hit], b["t"][hit], rtol=1e-6, atol=0)
+    dev.close()
+    scene.close()
+
+
+def test_bvh_deeper_than_the_traversal_stack_is_refused(gpu, host):
+    """The reference's traversal keeps 64 pending nodes (accelerator.rs:366) and would panic beyond; a description whose
+    tree needs more is refused (PTRS_ERR_UNSUPPORTED) instead of being traversed with dropped subtrees."""
+    import ctypes as C
+
+    from pathtracer_rs_b200._abi import PtrsBvhNode, PtrsSceneDesc
+
+    def chain(k):
+        """k interior nodes in a chain: interior 2i has the leaf 2i+1 as first child and node 2i+2 as second."""
+        b = host.SceneBuilder()
+        m = b.material(host.MAT_MATTE, [b.constant_texture([0.5, 0.5, 0.5])])
+        n_tri = k + 1
+        verts = np.concatenate([np.array([[i, 0, 0], [i + 0.8, 0, 0], [i, 0.8, 0]], dtype=np.float32) for i in range(n_tri)])
+        idx = np.arange(3 * n_tri, dtype=np.uint32).reshape(-1, 3)
+        b.mesh(verts, idx, material=m)
+        flat = b.finalize()
+        base = flat.desc.contents
+        d = PtrsSceneDesc()
+        C.memmove(C.byref(d), C.byref(base), C.sizeof(PtrsSceneDesc))
+        nodes = (PtrsBvhNode * (2 * k + 1))()
+        # the builder may have reordered the primitives: take each triangle's box from the flattened arrays
+        tv = flat.prim_vertices()
+        lo, hi = tv.min(axis=1), tv.max(axis=1)
+        order = np.argsort(lo[:, 0])
+        assert np.array_equal(order, np.arange(n_tri)), "chain triangles are expected in x order"
+        for i in range(k):
+            n = nodes[2 * i]
+            n.bounds_min[:] = lo[i:].min(axis=0).tolist()
+            n.bounds_max[:] = hi[i:].max(axis=0).tolist()
+            n.offset, n.n_prims, n.axis = 2 * i + 2, 0, 0
+            leaf = nodes[2 * i + 1]
+            leaf.bounds_min[:], leaf.bounds_max[:] = lo[i].tolist(), hi[i].tolist()
+            leaf.offset, leaf.n_prims = i, 1
+        last = nodes[2 * k]
+        last.bounds_min[:], last.bounds_max[:] = lo[k].tolist(), hi[k].tolist()
+        last.offset, last.n_prims = k, 1
+        d.nodes, d.n_nodes = nodes, 2 * k + 1
+        return flat, d, nodes
+
+    flat, d, keep = chain(64)  # needs exactly 64 pending entries: accepted, and every triangle is found
+    scene = gpu.RenderScene(C.pointer(d))
+    rays = np.zeros(65, dtype=host.RAY_DTYPE)
+    rays["o"] = [[i + 0.2, 0.2, 1.0] for i in range(65)]
+    rays["d"] = [0, 0, -1]
+    rays["t_max"] = np.inf
+    assert np.array_equal(scene.intersect(rays)["prim"], np.arange(65))
+    # a ray along the chain visits every level with the far child pending
+    along = np.zeros(1, dtype=host.RAY_DTYPE)
+    along["o"], along["d"], along["t_max"] = [70.0, 0.2, 0.0], [-1, 0, 0], np.inf
+    scene.intersect(along)
+    scene.close()
+    flat, d, keep = chain(65)
+    with pytest.raises(gpu.PtrsError) as e:
+        gpu.RenderScene(C.pointer(d))
+    assert e.value.code == -3
 
 
 def test_bandwidth_probes_are_ordered(gpu):

@@ -1,25 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — the reference's headline metric (camera samples/s and Mrays/s of the path integrator) on
-BASELINE.json's configs[1]: Cornell box + environment map, 1024x1024, 64 spp, max_depth 15.
+"""bench.py — the reference's headline metric (camera samples/s and Mrays/s of the path integrator) on the
+configuration BASELINE.json's north_star scales on: configs[4], the 262 k-triangle atrium at 3840x2160, max_depth 15,
+under STRONG scaling — a fixed total number of samples per pixel dealt over the GPUs.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c1|c2|c3|c5] [--spp S]
-    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU; the driver's way)
+    python bench.py --gpus N            (no torchrun: one process drives N devices through ptrs_multi_render)
 
-A step = one full render of the workload (67.6 M camera paths) accumulated into a cleared film.
-  value     paths/s with scene and film resident in HBM (CUDA events on the launching stream)
-  e2e       the same through the C ABI with HOST buffers: ptrs_scene_create from host arrays, render,
+A step = one full render of the workload into a cleared film: every rank renders the Sobol sample numbers
+s = rank (mod N) of every pixel, then the films are summed into rank 0's with ONE NCCL reduce inside the library
+(ptrs_film_reduce) — inside the timed region.
+  value     camera paths of all ranks / max-over-ranks step time, scene and film resident in HBM (CUDA events on the launching stream)
+  e2e       the same through the C ABI with HOST buffers: ptrs_scene_create from host arrays, render, film reduce,
             ptrs_film_download — host<->device copies inside the timed region
-  roofline  extend kernel (closest-hit BVH traversal, the kernel BASELINE.json's "% of L2/HBM roofline" is about):
-            algorithmic bytes (32 B x nodes tested + 36 B x triangles tested + 28 B ray + 20 B hit)
-            / its summed launch time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json;
-            roofline.stages adds the connect and shade stages the same way (shade is the largest share on C2);
-            roofline.probes are the memory system's own figures measured in the same process — streaming reads and
-            random 64-byte gathers from an L2-resident and from an HBM-sized buffer — and roofline.frac_of_l2_gather
-            is the extend kernel against the one that matches its access pattern
-  cpu_baseline  the C++ oracle (a restatement of the reference's rayon integrator; the Rust crate cannot
-            be built in this image) on a bounded, strided sample of the same workload's 16x16 tiles
-Multi-GPU (weak scaling): rank g renders Sobol sample numbers {s : s mod N == g} of a 64*N-spp render of
-the same image, then one NCCL reduce of the film to rank 0 — the only collective on the path.
+  roofline  the BVH traversal kernels (extend_kernel + connect_kernel, one traversal engine; the dominant kernels of the
+            workload): algorithmic bytes (32 B x nodes tested + 36 B x triangles tested + 28 B ray + 20 B / 1 B result,
+            SURVEY.md §8d) / their summed launch time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+            (frac), and against the memory system's own figures for this access pattern measured in the same process
+            (frac_of_l2_gather, frac_of_l2_stream: the tree is L2 resident on this workload); roofline.stages lists every
+            stage of the step; roofline.traffic is the measured DRAM traffic per launch of the same kernels on this
+            workload (ncu, profiles/traversal_dram_bytes.json)
+  cpu_baseline  the C++ oracle (a restatement of the reference's rayon integrator; the Rust crate cannot be built in
+            this image) on a bounded, strided sample of the same workload's 16x16 tiles
+  bvh_microbench  BASELINE configs[3] (10 M triangles, 2^24 coherent / incoherent rays): the HBM-bound traversal case
 """
 import argparse
 import ctypes as C
@@ -36,20 +39,21 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-WORKLOAD = {"name": "cornell+envmap 1024x1024 64spp depth15 (BASELINE configs[1])", "res": (1024, 1024), "spp": 64, "max_depth": 15,
-            "scene": "SCENE_CORNELL_ENV", "n_tris": 0}
-# The other BASELINE configs, selectable with --workload for the tables in DESIGN.md §6 (the default and
-# the driver's line stay configs[1]).  --spp overrides the per-GPU sample count (C5's 1024 spp is run in
-# full only when sharded; a reduced-spp run says so in config.workload).
+# BASELINE.json configs.  "spp" is the TOTAL over all GPUs (strong scaling).  The default is configs[4]; its 1024 spp
+# are run as 128: the largest power of two for which the driver's 25 steps at N=1 (~5 s each) fit its per-N time limit.
+# The metric is a rate; samples/s does not depend on how many of the 1024 sample numbers a step renders.
 WORKLOADS = {
     "c1": {"name": "cornell 512x512 16spp depth15 (BASELINE configs[0])", "res": (512, 512), "spp": 16, "max_depth": 15,
-           "scene": "SCENE_CORNELL", "n_tris": 0},
-    "c2": WORKLOAD,
+           "scene": "SCENE_CORNELL", "n_tris": 0, "data": "data/cornell-box.xml geometry, built procedurally"},
+    "c2": {"name": "cornell + abandoned_tank_farm_04_1k.hdr environment map 1024x1024 64spp depth15 (BASELINE configs[1])", "res": (1024, 1024),
+           "spp": 64, "max_depth": 15, "scene": "SCENE_CORNELL_ENV", "n_tris": 0, "env_hdr": True,
+           "data": "cornell box + the reference's own data/abandoned_tank_farm_04_1k.hdr (fixture under tests/golden)"},
     "c3": {"name": "1M-triangle material field (glass/substrate/metal/Disney/matte + env + area lights) 1920x1080 256spp depth15 (BASELINE configs[2])",
-           "res": (1920, 1080), "spp": 256, "max_depth": 15, "scene": "SCENE_MATERIAL_FIELD", "n_tris": 1000000},
-    "c5": {"name": "262k-triangle atrium 3840x2160 1024spp depth15 (BASELINE configs[4])", "res": (3840, 2160), "spp": 1024, "max_depth": 15,
-           "scene": "SCENE_ATRIUM", "n_tris": 262144},
+           "res": (1920, 1080), "spp": 256, "max_depth": 15, "scene": "SCENE_MATERIAL_FIELD", "n_tris": 1000000, "data": "synthetic (seeded procedural scene)"},
+    "c5": {"name": "262k-triangle atrium 3840x2160 depth15, 128 of the 1024 spp per step (BASELINE configs[4], strong scaling over the GPUs)",
+           "res": (3840, 2160), "spp": 128, "max_depth": 15, "scene": "SCENE_ATRIUM", "n_tris": 262144, "data": "synthetic (seeded procedural scene)"},
 }
+DEFAULT_WORKLOAD = "c5"
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -143,6 +147,28 @@ def cpu_sample_plan(oracle, flat, cam, params, target_s=12.0):
     return n_tiles, max(1, n_tiles // want)
 
 
+def load_workload(args):
+    w = dict(WORKLOADS[args.workload])
+    if args.spp:
+        w["name"] += f" [run at {args.spp} spp in total]"
+        w["spp"] = args.spp
+    return w
+
+
+def build_scene(host, w):
+    env = host.TANK_FARM_HDR if w.get("env_hdr") else None
+    return host.make_scene(getattr(host, w["scene"]), seed=1, n_tris=w["n_tris"], res=w["res"], env_hdr=env)
+
+
+def make_config(w, n_gpus):
+    """The same dict in both arms (the driver compares them)."""
+    W, H = w["res"]
+    return {"workload": w["name"], "resolution": [W, H], "spp_total": w["spp"], "max_depth": w["max_depth"],
+            "camera_paths_per_step": (W + 4) * (H + 4) * w["spp"],
+            "sharding": f"sample number mod {n_gpus} per GPU, films summed by one NCCL reduce inside the timed region",
+            "l2": "inputs larger than L2 (5.5 GB of path state per wavefront batch) and a 256 MiB buffer written between timed iterations"}
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU path (C++ oracle, tile-parallel like
     integrator.rs:617-637, all host threads) on this arm's config; each step = a bounded tile sample."""
@@ -152,13 +178,10 @@ def run_reference(args):
     import pathtracer_rs_b200.host as host
     from oracle import oracle
 
-    w = dict(WORKLOADS[args.workload])
-    if args.spp:
-        w["name"] += f" [run at {args.spp} spp per GPU]"
-        w["spp"] = args.spp
-    flat, cam = host.make_scene(getattr(host, w["scene"]), seed=1, n_tris=w["n_tris"], res=w["res"])
+    w = load_workload(args)
+    flat, cam = build_scene(host, w)
     params = host.default_render_params(spp=w["spp"], max_depth=w["max_depth"])
-    n_tiles, stride = cpu_sample_plan(oracle, flat, cam, params, target_s=8.0)
+    n_tiles, stride = cpu_sample_plan(oracle, flat, cam, params, target_s=6.0)
     cores = host_threads()
     for _ in range(args.warmup):
         oracle.render(flat, cam, params, n_threads=cores, tile_stride=stride * 8)
@@ -173,16 +196,16 @@ def run_reference(args):
     value = paths / t
     sample = f"every {stride}th of the {n_tiles} 16x16 tiles, all {w['spp']} spp ({paths} camera paths per step)"
     line = {"impl": "reference", "metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "mrays_per_s": rays / t / 1e6,
-            "config": {"workload": w["name"], "resolution": list(w["res"]), "spp": w["spp"], "max_depth": w["max_depth"], "sample": sample},
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": w["data"], "mrays_per_s": rays / t / 1e6,
+            "config": make_config(w, args.gpus),
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference = C++ restatement of the reference's rayon path integrator (oracle/); the Rust crate itself cannot be built in this image"}
     emit(line)
 
 
-def bvh_microbench(gpu, host, torch, peak_gbs):
+def bvh_microbench(gpu, host, torch, peak_gbs, checker=None):
     """BASELINE configs[3]: fixed-ray intersection microbenchmark on a synthetic 10 M-triangle mesh,
     2^24 coherent and 2^24 incoherent rays; HBM-bound for incoherent rays."""
     n_tris = int(os.environ.get("PTRS_BENCH_BVH_TRIS", "10000000"))
@@ -218,6 +241,19 @@ def bvh_microbench(gpu, host, torch, peak_gbs):
                     ms.append(e0.elapsed_time(e1))
             t = float(np.mean(ms)) * 1e-3
             key = f"{name}_{'any' if any_hit else 'closest'}"
+            if checker is not None:  # a strided sample of the results against the oracle: ids, t, barycentrics bit for bit
+                pick = np.arange(0, n, max(1, n // 4096))
+                if any_hit:
+                    got = d_occ.cpu().numpy()[pick]
+                    want, _ = checker.intersect_p(flat, rays[pick])
+                else:
+                    got = d_hits.cpu().numpy().view(host.HIT_DTYPE)[pick]
+                    want, _ = checker.intersect(flat, rays[pick])
+                same = np.array_equal(got, want) if any_hit else (
+                    np.array_equal(got["prim"], want["prim"]) and all(np.array_equal(got[f][want["prim"] >= 0], want[f][want["prim"] >= 0]) for f in ("t", "b0", "b1", "b2")))
+                if not same:
+                    raise RuntimeError(f"bvh_microbench {key}: device hits differ from the oracle's on the checked sample")
+                out.setdefault("hits_checked_against_oracle", {})[key] = int(pick.shape[0])
             out[key] = {"mrays_per_s": n / t / 1e6, "ms": t * 1e3, "nodes_per_ray": nodes / n, "tris_per_ray": tris / n,
                         "achieved_gbs": alg_bytes / t / 1e9, "frac": alg_bytes / t / 1e9 / peak_gbs}
         del d_rays, d_hits, d_occ
@@ -259,6 +295,16 @@ def bvh_microbench(gpu, host, torch, peak_gbs):
     return out
 
 
+def traffic_record(workload):
+    """Measured DRAM traffic per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum) of the traversal kernels on this
+    workload, from the committed capture; None when this workload was not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traversal_dram_bytes.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -266,7 +312,7 @@ def run_gpu(args):
     import pathtracer_rs_b200.gpu as gpu
     import pathtracer_rs_b200.host as host
     from pathtracer_rs_b200._abi import PtrsRenderParams
-    from pathtracer_rs_b200.dist import reduce_film, sample_shard
+    from pathtracer_rs_b200.dist import exchange_comm_id, sample_shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -275,87 +321,128 @@ def run_gpu(args):
         raise RuntimeError("no CUDA device: the rendering hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     gpu.set_device(local_rank)
-    if world > 1:
+    # "ranks": one process per GPU (torchrun); "threads": this process drives args.gpus devices through ptrs_multi_render
+    mode = "ranks" if world > 1 else ("threads" if args.gpus > 1 else "single")
+    n_gpus = world if world > 1 else args.gpus
+    comm = None
+    if mode == "ranks":
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n_gpus = world
+        comm = gpu.Comm(exchange_comm_id(gpu.Comm.unique_id, rank, world), world, rank)  # the film reduce lives in the library
     peak_gbs, peak_src = measured_peaks()
 
-    w = dict(WORKLOADS[args.workload])
-    if args.spp:
-        w["name"] += f" [run at {args.spp} spp per GPU]"
-        w["spp"] = args.spp
+    w = load_workload(args)
     W, H = w["res"]
-    flat, cam = host.make_scene(getattr(host, w["scene"]), seed=1, n_tris=w["n_tris"], res=w["res"])
-    scene = gpu.RenderScene(flat)
-    # weak scaling: the image is rendered at spp * N with rank g taking sample numbers s = g (mod N)
-    integ = gpu.PathIntegrator(gpu.SamplerBuilder(w["spp"] * n_gpus), max_depth=w["max_depth"])
-    integ.preprocess(scene)
-    film_t = torch.zeros(H, W, 4, dtype=torch.float32, device="cuda")
-    film = gpu.Film(W, H, device_ptr=film_t.data_ptr())
+    flat, cam = build_scene(host, w)
+    integ = gpu.PathIntegrator(gpu.SamplerBuilder(w["spp"]), max_depth=w["max_depth"])
+    shard = sample_shard(rank, n_gpus) if mode == "ranks" else (1, 0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     stream = torch.cuda.current_stream().cuda_stream
-
-    def step():
-        film_t.zero_()
-        st = integ.render(cam, scene, film, stream=stream, sample_stride=sample_shard(rank, n_gpus))
-        reduce_film(film_t, dst=0)
-        return st
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # one untimed pass with visit counters on: algorithmic bytes of the (deterministic) step
-    scene.set_stats_mode(True)
-    st_count = step()
-    scene.set_stats_mode(False)
+    def agg(per_device):
+        """one stats dict from the per-device ones: counts add, times take the slowest device"""
+        out = dict(per_device[0])
+        for st in per_device[1:]:
+            for k, v in st.items():
+                out[k] = max(out[k], v) if k.startswith("ms_") else out[k] + v
+        return out
+
+    if mode == "threads":
+        multi = gpu.MultiScene(flat, n_gpus)
+        scene = gpu.RenderScene(flat)  # device 0 replica for the counted pass
+
+        def step():
+            per_dev, ms = multi.render_into(cam, integ.params, None)
+            return agg(per_dev), ms
+
+        def counted():
+            scene.set_stats_mode(True)
+            f = gpu.Film(W, H)
+            st = integ.render(cam, scene, f, sample_stride=(n_gpus, 0))
+            scene.set_stats_mode(False)
+            return st
+    else:
+        scene = gpu.RenderScene(flat)
+        integ.preprocess(scene)
+        film_t = torch.zeros(H, W, 4, dtype=torch.float32, device="cuda")
+        film = gpu.Film(W, H, device_ptr=film_t.data_ptr())
+
+        def step():
+            film.clear(stream)
+            st = integ.render(cam, scene, film, stream=stream, sample_stride=shard)
+            if comm:
+                comm.reduce_film(film, root=0, stream=stream)
+            return st, None
+
+        def counted():
+            scene.set_stats_mode(True)
+            st, _ = step()
+            scene.set_stats_mode(False)
+            return st
+
+    # one untimed pass with visit counters on: algorithmic bytes of this rank's (deterministic) share of the step
+    st_count = counted()
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     barrier()
-    step_ms, ext_ms, stats = [], [], None
+    step_ms, stats = [], None
     for _ in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        stats = step()
+        stats, lib_ms = step()
         e1.record()
         barrier()
-        step_ms.append(e0.elapsed_time(e1))
-        ext_ms.append(stats["ms_extend"])
+        # "threads": the devices run on the library's own streams, so the step time is the library's clock around the whole
+        # call (all streams synchronised on both sides); otherwise CUDA events on the launching stream
+        step_ms.append(lib_ms if lib_ms is not None else e0.elapsed_time(e1))
     clocks = sampler.summary() if sampler else None
     t_local = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
+    paths_t = torch.tensor([float(stats["camera_paths"])], dtype=torch.float64, device="cuda")
+    rays_t = torch.tensor([float(stats["extension_rays"] + stats["shadow_rays"] + stats["mis_rays"])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_local, op=dist.ReduceOp.MAX)  # max over ranks
-    total_ms = float(t_local.item())
-    ms_per_step = total_ms / args.steps
-    paths_step = stats["camera_paths"] * n_gpus
-    rays_step = (stats["extension_rays"] + stats["shadow_rays"] + stats["mis_rays"]) * n_gpus
+        dist.all_reduce(paths_t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(rays_t, op=dist.ReduceOp.SUM)
+    ms_per_step = float(t_local.item()) / args.steps
+    paths_step, rays_step = int(paths_t.item()), int(rays_t.item())
     value = paths_step / (ms_per_step * 1e-3)
 
     # ---- end to end through the C ABI with host buffers -----------------------------------------------
     host_film = np.empty((H, W, 4), dtype=np.float32)
-    e2e_ms = []
+    e2e_ms, e2e_parts = [], {}
     for it in range(max(2, min(args.steps, 3)) + 1):
         barrier()
         t0 = time.perf_counter()
-        sc2 = gpu.RenderScene(flat)  # ptrs_scene_create: H2D of the whole flattened scene
-        f2 = gpu.Film(W, H)
-        t1 = time.perf_counter()
-        integ.render(cam, sc2, f2, sample_stride=sample_shard(rank, n_gpus))
-        t2 = time.perf_counter()
-        if world > 1:
-            reduce_film(torch.as_tensor(_CudaArray(f2.device_ptr, (H, W, 4)), device="cuda"), dst=0)
-            torch.cuda.synchronize()
-        if rank == 0:
-            gpu._check(gpu.lib().ptrs_film_download(f2._h, host_film.ctypes.data_as(C.POINTER(C.c_float))))
-        t3 = time.perf_counter()
-        sc2.close()
-        del f2
+        if mode == "threads":
+            m2 = gpu.MultiScene(flat, n_gpus)  # ptrs_multi_create: H2D of the whole flattened scene to every device
+            t1 = time.perf_counter()
+            m2.render_into(cam, integ.params, host_film.ctypes.data)  # render + reduce + D2H of the film
+            t2 = t3 = time.perf_counter()
+            m2.close()
+        else:
+            sc2 = gpu.RenderScene(flat)  # ptrs_scene_create: H2D of the whole flattened scene
+            f2 = gpu.Film(W, H)
+            t1 = time.perf_counter()
+            integ.render(cam, sc2, f2, sample_stride=shard)
+            t2 = time.perf_counter()
+            if comm:
+                comm.reduce_film(f2, root=0)
+            if rank == 0:
+                gpu._check(gpu.lib().ptrs_film_download(f2._h, host_film.ctypes.data_as(C.POINTER(C.c_float))))
+            else:
+                torch.cuda.synchronize()
+            t3 = time.perf_counter()
+            sc2.close()
+            del f2
         barrier()
         if it > 0:
             e2e_ms.append((time.perf_counter() - t0) * 1e3)
@@ -365,50 +452,52 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(e2e_local, op=dist.ReduceOp.MAX)
     e2e_value = paths_step / (float(e2e_local.item()) * 1e-3)
-    h2d = int(flat.host_bytes) + C.sizeof(type(cam)) + C.sizeof(PtrsRenderParams)
+    h2d = (int(flat.host_bytes) + C.sizeof(type(cam)) + C.sizeof(PtrsRenderParams)) * n_gpus
     d2h = H * W * 16
 
     if rank != 0:
+        if comm:
+            comm.close()
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (extend) ---------------------------------------------------
+    # ---- roofline of the dominant kernels: BVH traversal (extend + connect) -------------------------------------
+    # byte counts from the counted pass, times from the timed steps (this rank's / device 0's share: 1/N of the step)
     ext_rays = st_count["extension_rays"]
-    alg_bytes = 32 * st_count["nodes_tested"] + 36 * st_count["tris_tested"] + ext_rays * (28 + 20)
-    ext_s = float(np.mean(ext_ms)) * 1e-3
-    achieved = alg_bytes / ext_s / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "extend_dram_bytes.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": "extend_kernel<false> (closest-hit BVH traversal)", "achieved": achieved, "peak": peak_gbs,
-                "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_step": alg_bytes, "launches_per_step": stats["extend_launches"],
-                "avg_launch_ms": float(np.mean(ext_ms)) / max(1, stats["extend_launches"]),
-                "bytes_per_ray": alg_bytes / ext_rays, "nodes_per_ray": st_count["nodes_tested"] / ext_rays,
-                "tris_per_ray": st_count["tris_tested"] / ext_rays, "share_of_step": float(np.mean(ext_ms)) / (sum(step_ms) / len(step_ms)),
-                "note": f"scene ({flat.n_prims} triangles, {flat.n_nodes} nodes) is cache resident (L1/L2): the HBM-bound case is bvh_microbench"}
-
-    # the other two stages next to it, so the line shows where the rest of the step goes: the connect stage by the
-    # same traversal byte count (ms_shadow also contains connect_resolve), the shade stage by its record traffic
-    # (84 B in: queue entry, hit, 64 B path slot; up to 176 B out: slot, 96 B direct-lighting record, queue entries)
-    step_mean = sum(step_ms) / len(step_ms)
     nee_rays = st_count["shadow_rays"] + st_count["mis_rays"]
-    nee_bytes = 32 * st_count["nee_nodes_tested"] + 36 * st_count["nee_tris_tested"] + 32 * nee_rays + 1 * st_count["shadow_rays"] + 16 * st_count["mis_rays"]
+    ext_bytes = 32 * st_count["nodes_tested"] + 36 * st_count["tris_tested"] + ext_rays * (28 + 20)
+    nee_bytes = 32 * st_count["nee_nodes_tested"] + 36 * st_count["nee_tris_tested"] + 28 * nee_rays + 1 * st_count["shadow_rays"] + 20 * st_count["mis_rays"]
+    step_mean = sum(step_ms) / len(step_ms)
+    ext_ms, con_ms = stats["ms_extend"], stats["ms_connect_trace"]
+    trav_bytes, trav_ms = ext_bytes + nee_bytes, ext_ms + con_ms
+    trav_launches = stats["extend_launches"] + stats["connect_launches"]
+    achieved = trav_bytes / (trav_ms * 1e-3) / 1e9
+    tr = traffic_record(args.workload)
+    roofline = {"bound": "hbm", "kernel": "extend_kernel<false> + connect_kernel<false> (closest-hit / any-hit BVH traversal, one engine: dev_accel.cuh trace_fast)",
+                "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                "traffic": tr.get("dram_bytes_per_launch") if tr else None, "traffic_source": tr.get("source") if tr else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_step": trav_bytes, "algorithmic_bytes_per_launch": trav_bytes / max(1, trav_launches),
+                "launches_per_step": trav_launches, "avg_launch_ms": trav_ms / max(1, trav_launches),
+                "share_of_step": trav_ms / step_mean,
+                "extend": {"ms": ext_ms, "achieved_gbs": ext_bytes / (ext_ms * 1e-3) / 1e9, "bytes_per_ray": ext_bytes / max(1, ext_rays),
+                           "nodes_per_ray": st_count["nodes_tested"] / max(1, ext_rays), "tris_per_ray": st_count["tris_tested"] / max(1, ext_rays),
+                           "mrays_per_s": ext_rays / (ext_ms * 1e-3) / 1e6},
+                "connect": {"ms": con_ms, "achieved_gbs": nee_bytes / max(con_ms * 1e-3, 1e-9) / 1e9, "bytes_per_ray": nee_bytes / max(1, nee_rays),
+                            "nodes_per_ray": st_count["nee_nodes_tested"] / max(1, nee_rays), "mrays_per_s": nee_rays / max(con_ms * 1e-3, 1e-9) / 1e6},
+                "note": f"scene: {flat.n_prims} triangles, {flat.n_nodes} nodes ({(flat.n_nodes * 32 + flat.n_prims * 48) / 1e6:.1f} MB of nodes + triangles: L2 resident; "
+                        "`frac` is quoted against the HBM copy peak as the contract asks, frac_of_l2_gather is the roof of this access pattern); the HBM-bound case is bvh_microbench"}
     shade_bytes = (84 + 176) * ext_rays
-    stages = {
-        "extend": {"ms": float(np.mean(ext_ms)), "share_of_step": float(np.mean(ext_ms)) / step_mean, "achieved_gbs": achieved, "frac": achieved / peak_gbs},
-        "connect+resolve": {"ms": stats["ms_shadow"], "share_of_step": stats["ms_shadow"] / step_mean,
-                            "achieved_gbs": nee_bytes / (stats["ms_shadow"] * 1e-3) / 1e9, "frac": nee_bytes / (stats["ms_shadow"] * 1e-3) / 1e9 / peak_gbs,
-                            "nodes_per_ray": st_count["nee_nodes_tested"] / max(1, nee_rays)},
+    roofline["stages"] = {
+        "generate": {"ms": stats["ms_generate"], "share_of_step": stats["ms_generate"] / step_mean},
+        "extend": {"ms": ext_ms, "share_of_step": ext_ms / step_mean},
         "shade (all materials + miss)": {"ms": stats["ms_shade"], "share_of_step": stats["ms_shade"] / step_mean,
-                                         "achieved_gbs": shade_bytes / (stats["ms_shade"] * 1e-3) / 1e9, "frac": shade_bytes / (stats["ms_shade"] * 1e-3) / 1e9 / peak_gbs,
-                                         "note": "latency bound (dependent scene / table loads at 16 warps per SM), not a bandwidth kernel; upper-bound bytes"},
+                                         "achieved_gbs": shade_bytes / (stats["ms_shade"] * 1e-3) / 1e9,
+                                         "note": "latency bound (dependent scene / table loads), not a bandwidth kernel; record bytes are an upper bound"},
+        "connect (trace)": {"ms": con_ms, "share_of_step": con_ms / step_mean},
+        "connect_resolve": {"ms": stats["ms_resolve"], "share_of_step": stats["ms_resolve"] / step_mean},
+        "accumulate": {"ms": stats["ms_accumulate"], "share_of_step": stats["ms_accumulate"] / step_mean},
     }
-    roofline["stages"] = stages
     # What the memory system gives THIS access pattern, measured here and now (MEASURED_PEAKS.json has a copy
     # bandwidth only): streaming 256-bit reads and independent random 64-byte gathers (one sibling pair of nodes),
     # from an L2-resident buffer and from one far larger than L2 (ptrs_read_bandwidth / ptrs_gather_bandwidth).
@@ -416,7 +505,9 @@ def run_gpu(args):
         probes = {"l2_stream_read_gbs_64MiB": gpu.read_bandwidth(64 << 20, 30), "l2_gather64_gbs_64MiB": gpu.gather_bandwidth(64 << 20, 512),
                   "hbm_stream_read_gbs_4GiB": gpu.read_bandwidth(4 << 30, 2), "hbm_gather64_gbs_1GiB": gpu.gather_bandwidth(1 << 30, 256)}
         roofline["probes"] = probes
+        roofline["frac_of_hbm"] = achieved / peak_gbs
         roofline["frac_of_l2_gather"] = achieved / probes["l2_gather64_gbs_64MiB"]
+        roofline["frac_of_l2_stream"] = achieved / probes["l2_stream_read_gbs_64MiB"]
     except Exception as e:  # diagnostic only
         roofline["probes"] = {"error": str(e)}
 
@@ -436,33 +527,32 @@ def run_gpu(args):
 
     micro = None
     if n_gpus == 1 and not args.no_bvh_microbench:
-        del film, film_t
+        if mode != "threads":
+            del film, film_t
         scene.close()
         torch.cuda.empty_cache()
-        micro = bvh_microbench(gpu, host, torch, peak_gbs)
+        checker = None
+        if not args.no_cpu_baseline:  # the cpu_baseline leg's oracle doubles as the checker of the microbenchmark's hits
+            from oracle import oracle as checker
+        micro = bvh_microbench(gpu, host, torch, peak_gbs, checker)
 
     line = {"metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "mrays_per_s": rays_step / (ms_per_step * 1e-3) / 1e6,
-            "config": {"workload": w["name"], "resolution": [W, H], "spp_per_gpu": w["spp"], "max_depth": w["max_depth"],
-                       "camera_paths_per_step": paths_step, "rays_per_step": rays_step, "sharding": f"sample index mod {n_gpus}, film reduced with NCCL",
-                       "l2": "256 MiB buffer written between timed iterations (L2 flush)"},
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": w["data"], "mrays_per_s": rays_step / (ms_per_step * 1e-3) / 1e6,
+            "config": make_config(w, n_gpus), "launch": {"ranks": "one process per GPU (torchrun), ptrs_comm_* + ptrs_film_reduce", "threads": "one process, ptrs_multi_render",
+                                                         "single": "one GPU"}[mode],
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(e2e_local.item()), "includes": "ptrs_scene_create from host arrays + render + ptrs_film_download + ptrs_scene_destroy",
+                    "ms_per_step": float(e2e_local.item()),
+                    "includes": "ptrs_scene_create from host arrays (every rank) + render + NCCL film reduce + ptrs_film_download + ptrs_scene_destroy; excludes the host-side BVH build / scene assembly",
                     "parts_last_step": e2e_parts},
-            "gpu_launches": int(stats["launches"]) * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "stage_ms": {k: stats[k] for k in ("ms_generate", "ms_extend", "ms_shade", "ms_shadow", "ms_accumulate", "ms_total")},
-            "rays": {k: stats[k] for k in ("extension_rays", "shadow_rays", "mis_rays")}, "bvh_microbench": micro}
+            "gpu_launches": int(stats["launches"]) * args.steps * (n_gpus if mode == "ranks" else 1), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "stage_ms": {k: stats[k] for k in ("ms_generate", "ms_extend", "ms_shade", "ms_connect_trace", "ms_resolve", "ms_accumulate", "ms_total")},
+            "rays_per_step": rays_step, "rays_rank0": {k: stats[k] for k in ("extension_rays", "shadow_rays", "mis_rays")}, "bvh_microbench": micro}
     emit(line)
+    if comm:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
-
-
-class _CudaArray:
-    """Minimal __cuda_array_interface__ holder so torch can wrap a device pointer owned by the library."""
-
-    def __init__(self, ptr, shape):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
 
 
 def _claim_stdout():
@@ -493,8 +583,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bvh-microbench", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel per GPU")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="override the workload's total samples per pixel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

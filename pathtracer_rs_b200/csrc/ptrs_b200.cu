@@ -689,6 +689,7 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
       CUDA_TRY(cudaStreamSynchronize(0));  // the staging buffers above are released when this scope ends
     }
   }
+  if (n_dev_nodes > (1u << 30)) return fail(PTRS_ERR_UNSUPPORTED, "more than 2^30 BVH nodes");  // packed stack entries, dev_accel.cuh
   if (d->normal) CUDA_TRY(s->normal.upload(d->normal, (size_t)d->n_verts * 3));
   if (d->tangent) CUDA_TRY(s->tangent.upload(d->tangent, (size_t)d->n_verts * 3));
   if (d->uv) CUDA_TRY(s->uv.upload(d->uv, (size_t)d->n_verts * 2));

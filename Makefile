@@ -22,8 +22,8 @@ OBJ  := build/obj
 BLOB := $(abspath pathtracer_rs_b200/data/sobol_tables.bin)
 
 DEV_HDRS  := $(wildcard $(CS)/*.cuh) $(CS)/launch.hpp $(CS)/handles.hpp include/ptrs_b200.h
-SHADE_OBJ := $(foreach m,0 1 2 3 4 5,$(OBJ)/k_shade_$(m).o)
-CUDA_OBJ  := $(OBJ)/ptrs_b200.o $(OBJ)/multi_gpu.o $(OBJ)/k_trace.o $(OBJ)/k_misc.o $(OBJ)/k_bvh.o $(SHADE_OBJ) $(OBJ)/sobol_blob.o
+SHADE_OBJ := $(foreach m,0 1 2 3 4 5,$(OBJ)/k_shade_$(m).o $(OBJ)/k_shade_exact_$(m).o)
+CUDA_OBJ  := $(OBJ)/ptrs_b200.o $(OBJ)/multi_gpu.o $(OBJ)/k_probe_fast.o $(OBJ)/k_probe_exact.o $(OBJ)/k_trace.o $(OBJ)/k_misc.o $(OBJ)/k_bvh.o $(OBJ)/k_sort.o $(SHADE_OBJ) $(OBJ)/sobol_blob.o
 
 all: $(LIB)/libptrs_b200.so $(LIB)/libptrs_host.so oracle/_build/liboracle.so examples
 
@@ -33,6 +33,18 @@ examples: $(LIB)/libptrs_b200.so $(LIB)/libptrs_host.so
 $(OBJ)/%.o: $(CS)/%.cu $(DEV_HDRS)
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ > $(OBJ)/$*.ptxas.log 2>&1 || (cat $(OBJ)/$*.ptxas.log; false)
+
+$(OBJ)/k_probe_fast.o: $(CS)/k_probe.cu $(DEV_HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(SHADEFLAGS) -DPT_PROBE_EXACT=0 -c $< -o $@ > $(OBJ)/k_probe_fast.ptxas.log 2>&1 || (cat $(OBJ)/k_probe_fast.ptxas.log; false)
+$(OBJ)/k_probe_exact.o: $(CS)/k_probe.cu $(DEV_HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVCCFLAGS) -DPT_PROBE_EXACT=1 -c $< -o $@ > $(OBJ)/k_probe_exact.ptxas.log 2>&1 || (cat $(OBJ)/k_probe_exact.ptxas.log; false)
+
+# parity mode (PTRS_RENDER_EXACT_SHADING): the same shade kernels with the exact units' arithmetic
+$(OBJ)/k_shade_exact_%.o: $(CS)/k_shade.cu $(DEV_HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVCCFLAGS) -DPT_SHADE_EXACT=1 -DPT_SHADE_MAT=$* -c $< -o $@ > $(OBJ)/k_shade_exact_$*.ptxas.log 2>&1 || (cat $(OBJ)/k_shade_exact_$*.ptxas.log; false)
 
 $(OBJ)/k_shade_%.o: $(CS)/k_shade.cu $(DEV_HDRS)
 	@mkdir -p $(OBJ)

@@ -267,8 +267,15 @@ typedef struct PtrsRenderParams {
   float filter_radius[2];                                                 /* 2, 2 */
   float filter_table[PTRS_FILTER_TABLE_WIDTH * PTRS_FILTER_TABLE_WIDTH]; /* film.rs:135-144 */
   int32_t paths_per_batch; /* 0 = library default; wavefront batch size */
-  int32_t flags;           /* reserved, 0 */
+  int32_t flags;           /* PTRS_RENDER_* */
 } PtrsRenderParams;
+
+/* PtrsRenderParams.flags.  The traversal, sampler and camera kernels are always built with IEEE division / square
+ * root and without FMA contraction (that is what makes hits, rays and Sobol draws bit-identical to the CPU path);
+ * the shade kernels are by default built with contraction and the 2-ulp division / square root.
+ * PTRS_RENDER_EXACT_SHADING selects shade kernels built like the rest — the parity mode: what still differs from
+ * the reference is then its libm (sin, cos, atan2, acos, exp, ln, log2, pow) and nothing else. */
+#define PTRS_RENDER_EXACT_SHADING 1
 
 /* Counters of the last render on a scene handle. */
 typedef struct PtrsStats {
@@ -422,6 +429,59 @@ int32_t ptrs_sobol_samples(const PtrsCamera* camera, const PtrsRenderParams* par
 int32_t ptrs_generate_rays(const PtrsCamera* camera, const PtrsRenderParams* params,
                            const int32_t* pixels_xy, const int32_t* sample_nums, size_t n,
                            PtrsRay* rays, float* p_film, float* rxry_dir);
+
+/* Single BxDFs (bxdf/mod.rs:184-193 and the Fresnel / microfacet types they own), for lobe-by-lobe comparison with
+ * the CPU path.  kind / fresnel are the enums below; field use by kind:
+ *   r   Lambertian r, SpecularReflection r, FresnelSpecular r, MicrofacetReflection r, FresnelBlend rd, DisneyDiffuse r
+ *   t   SpecularTransmission t, FresnelSpecular t, MicrofacetTransmission t, FresnelBlend rs
+ *   fa, fb   Fresnel parameters: conductor (eta_t, k) with eta_i = 1; Disney (r0, {metallic, eta, -})
+ *   eta_a, eta_b   the dielectric indices of the specular / transmission lobes and of FRESNEL_DIELECTRIC
+ *   alpha_x, alpha_y, disney_g   TrowbridgeReitzDistribution (clamped to >= 1e-3 as microfacet.rs:113-116) / the
+ *                                separable-G DisneyMicrofacetDistribution (disney.rs:138-170) */
+typedef enum PtrsLobeKind {
+  PTRS_LOBE_LAMBERTIAN = 0,
+  PTRS_LOBE_SPECULAR_REFLECTION = 1,
+  PTRS_LOBE_SPECULAR_TRANSMISSION = 2,
+  PTRS_LOBE_FRESNEL_SPECULAR = 3,
+  PTRS_LOBE_MICROFACET_REFLECTION = 4,
+  PTRS_LOBE_MICROFACET_TRANSMISSION = 5,
+  PTRS_LOBE_FRESNEL_BLEND = 6,
+  PTRS_LOBE_DISNEY_DIFFUSE = 7
+} PtrsLobeKind;
+typedef enum PtrsFresnelKind {
+  PTRS_FRESNEL_DIELECTRIC = 0,
+  PTRS_FRESNEL_CONDUCTOR = 1,
+  PTRS_FRESNEL_DISNEY = 2,
+  PTRS_FRESNEL_NOOP = 3
+} PtrsFresnelKind;
+typedef struct PtrsLobeDesc {
+  int32_t kind;
+  int32_t fresnel;
+  float r[3];
+  float t[3];
+  float fa[3];
+  float fb[3];
+  float eta_a, eta_b;
+  float alpha_x, alpha_y;
+  int32_t disney_g;
+  int32_t pad;
+} PtrsLobeDesc;
+/* `flags`: PTRS_RENDER_EXACT_SHADING evaluates with the exact units' arithmetic (IEEE division / square root, no FMA
+ * contraction), 0 with the default shade kernels' arithmetic.  Directions are in the local shading frame (z = normal).
+ * BxDF::f and BxDF::pdf: out[4 i ..] = f.r, f.g, f.b, pdf */
+int32_t ptrs_bxdf_eval(const PtrsLobeDesc* lobe, const float* wo /* 3n */, const float* wi /* 3n */, size_t n,
+                       int32_t flags, float* out /* 4n */);
+/* BxDF::sample_f: out[8 i ..] = wi.x, wi.y, wi.z, f.r, f.g, f.b, pdf, sampled BxDFType bits (as a float) */
+int32_t ptrs_bxdf_sample(const PtrsLobeDesc* lobe, const float* wo /* 3n */, const float* u /* 2n */, size_t n,
+                         int32_t flags, float* out /* 8n */);
+/* Light::sample_li (light.rs) of light `light` from reference points ref_p with normals ref_n (p_error = 0), followed
+ * by the visibility segment VisibilityTester / Interaction::spawn_ray_to_it builds (light.rs:33-42, interaction.rs:50-59):
+ * out[16 i ..] = Li rgb, wi xyz, pdf, segment origin xyz, segment direction xyz (un-normalised), 3 x pad */
+int32_t ptrs_light_sample(PtrsScene* scene, int32_t light, const float* ref_p /* 3n */, const float* ref_n /* 3n */,
+                          const float* u /* 2n */, size_t n, int32_t flags, float* out /* 16n */);
+/* Light::pdf_li for directions wi from the same kind of reference points */
+int32_t ptrs_light_pdf(PtrsScene* scene, int32_t light, const float* ref_p /* 3n */, const float* ref_n /* 3n */,
+                       const float* wi /* 3n */, size_t n, int32_t flags, float* out /* n */);
 
 #ifdef __cplusplus
 }

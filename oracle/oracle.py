@@ -13,7 +13,7 @@ _ROOT = os.path.dirname(_HERE)
 if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 
-from pathtracer_rs_b200._abi import PtrsCamera, PtrsHit, PtrsRay, PtrsRenderParams, PtrsSceneDesc  # noqa: E402
+from pathtracer_rs_b200._abi import PtrsCamera, PtrsHit, PtrsLobeDesc, PtrsRay, PtrsRenderParams, PtrsSceneDesc  # noqa: E402
 from pathtracer_rs_b200.host import HIT_DTYPE, RAY_DTYPE  # noqa: E402
 
 _LIB = None
@@ -59,6 +59,11 @@ def lib():
         L.oracle_cosine_sample_hemisphere.argtypes = [C.c_float, C.c_float, fp]
         L.oracle_bxdf_eval.argtypes = [C.c_int, fp, fp, fp, fp]
         L.oracle_bxdf_sample.argtypes = [C.c_int, fp, fp, C.c_float, C.c_float, fp]
+        lobep = C.POINTER(PtrsLobeDesc)
+        L.oracle_lobe_eval.argtypes = [lobep, fp, fp, C.c_size_t, fp]
+        L.oracle_lobe_sample.argtypes = [lobep, fp, fp, C.c_size_t, fp]
+        L.oracle_light_sample.argtypes = [descp, C.c_int, fp, fp, fp, C.c_size_t, fp]
+        L.oracle_light_pdf.argtypes = [descp, C.c_int, fp, fp, fp, C.c_size_t, fp]
         tables = os.path.join(_ROOT, "pathtracer_rs_b200", "data", "sobol_tables.bin")
         if L.oracle_init(tables.encode()) != 0:
             raise RuntimeError(L.oracle_last_error().decode())
@@ -121,6 +126,36 @@ def path_radiance(scene, cam, params, pixels, samples, n_threads=0):
                                     px.shape[0], _p(out, C.c_float), n_threads)
     if rc != 0:
         raise RuntimeError(lib().oracle_last_error().decode())
+    return out
+
+
+def lobe_eval(lobe, wo, wi):
+    """BxDF::f / pdf, one row per (wo, wi): f rgb, pdf (mirrors ptrs_bxdf_eval)."""
+    o, w = np.ascontiguousarray(wo, dtype=np.float32), np.ascontiguousarray(wi, dtype=np.float32)
+    out = np.empty((o.shape[0], 4), dtype=np.float32)
+    lib().oracle_lobe_eval(C.byref(lobe), _p(o, C.c_float), _p(w, C.c_float), o.shape[0], _p(out, C.c_float))
+    return out
+
+
+def lobe_sample(lobe, wo, u):
+    """BxDF::sample_f: wi xyz, f rgb, pdf, sampled type (mirrors ptrs_bxdf_sample)."""
+    o, uu = np.ascontiguousarray(wo, dtype=np.float32), np.ascontiguousarray(u, dtype=np.float32)
+    out = np.empty((o.shape[0], 8), dtype=np.float32)
+    lib().oracle_lobe_sample(C.byref(lobe), _p(o, C.c_float), _p(uu, C.c_float), o.shape[0], _p(out, C.c_float))
+    return out
+
+
+def light_sample(scene, light, ref_p, ref_n, u):
+    p, nn, uu = (np.ascontiguousarray(a, dtype=np.float32) for a in (ref_p, ref_n, u))
+    out = np.empty((p.shape[0], 16), dtype=np.float32)
+    lib().oracle_light_sample(scene.desc, light, _p(p, C.c_float), _p(nn, C.c_float), _p(uu, C.c_float), p.shape[0], _p(out, C.c_float))
+    return out
+
+
+def light_pdf(scene, light, ref_p, ref_n, wi):
+    p, nn, w = (np.ascontiguousarray(a, dtype=np.float32) for a in (ref_p, ref_n, wi))
+    out = np.empty(p.shape[0], dtype=np.float32)
+    lib().oracle_light_pdf(scene.desc, light, _p(p, C.c_float), _p(nn, C.c_float), _p(w, C.c_float), p.shape[0], _p(out, C.c_float))
     return out
 
 

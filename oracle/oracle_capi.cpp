@@ -264,4 +264,109 @@ void oracle_bxdf_sample(int lobe, const float* p, const float* wo3, float u0, fl
   out7[6] = pdf;
 }
 
+// ---- lobe / light probes mirroring ptrs_bxdf_eval / ptrs_bxdf_sample / ptrs_light_sample / ptrs_light_pdf --------
+// PtrsLobeDesc -> the BxDF enum of bxdf/mod.rs:184-193 with the Fresnel / distribution objects the materials give it
+static BxDF lobe_from_desc(const PtrsLobeDesc& d) {
+  BxDF b;
+  b.kind = (BxDF::Kind)d.kind;
+  b.r = S(d.r[0], d.r[1], d.r[2]);
+  b.t = S(d.t[0], d.t[1], d.t[2]);
+  b.eta_a = d.eta_a;
+  b.eta_b = d.eta_b;
+  b.dist = Distribution::make(d.alpha_x, d.alpha_y, d.disney_g != 0);
+  switch (d.fresnel) {
+    case PTRS_FRESNEL_DIELECTRIC:
+      b.fresnel.kind = Fresnel::Dielectric;
+      b.fresnel.eta_i = d.eta_a;
+      b.fresnel.eta_t = d.eta_b;
+      break;
+    case PTRS_FRESNEL_CONDUCTOR:
+      b.fresnel.kind = Fresnel::Conductor;
+      b.fresnel.c_eta_i = S(1.f);
+      b.fresnel.c_eta_t = S(d.fa[0], d.fa[1], d.fa[2]);
+      b.fresnel.c_k = S(d.fb[0], d.fb[1], d.fb[2]);
+      break;
+    case PTRS_FRESNEL_DISNEY:
+      b.fresnel.kind = Fresnel::Disney;
+      b.fresnel.r0 = S(d.fa[0], d.fa[1], d.fa[2]);
+      b.fresnel.metallic = d.fb[0];
+      b.fresnel.d_eta = d.fb[1];
+      break;
+    default: b.fresnel.kind = Fresnel::NoOp; break;
+  }
+  return b;
+}
+void oracle_lobe_eval(const PtrsLobeDesc* lobe, const float* wo, const float* wi, size_t n, float* out) {
+  const BxDF b = lobe_from_desc(*lobe);
+  for (size_t i = 0; i < n; ++i) {
+    const Vec3 o = V(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]), w = V(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
+    const Spectrum f = b.f(o, w);
+    out[4 * i] = f.r;
+    out[4 * i + 1] = f.g;
+    out[4 * i + 2] = f.b;
+    out[4 * i + 3] = b.pdf(o, w);
+  }
+}
+void oracle_lobe_sample(const PtrsLobeDesc* lobe, const float* wo, const float* u, size_t n, float* out) {
+  const BxDF b = lobe_from_desc(*lobe);
+  for (size_t i = 0; i < n; ++i) {
+    const Vec3 o = V(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+    Vec3 w = V(0, 0, 0);
+    float pdf = 0.f;
+    uint32_t sampled = b.get_type();
+    const Spectrum f = b.sample_f(o, &w, Vec2{u[2 * i], u[2 * i + 1]}, &pdf, &sampled);
+    float* q = out + 8 * i;
+    q[0] = w.x;
+    q[1] = w.y;
+    q[2] = w.z;
+    q[3] = f.r;
+    q[4] = f.g;
+    q[5] = f.b;
+    q[6] = pdf;
+    q[7] = (float)sampled;
+  }
+}
+// Light::sample_li + VisibilityTester's segment (light.rs, interaction.rs:50-59), reference p_error = 0
+void oracle_light_sample(const PtrsSceneDesc* desc, int light, const float* ref_p, const float* ref_n, const float* u, size_t n, float* out) {
+  Scene sc{desc};
+  const PtrsLight& l = desc->lights[light];
+  for (size_t i = 0; i < n; ++i) {
+    Interaction ref;
+    ref.p = V(ref_p[3 * i], ref_p[3 * i + 1], ref_p[3 * i + 2]);
+    ref.n = V(ref_n[3 * i], ref_n[3 * i + 1], ref_n[3 * i + 2]);
+    Vec3 wi = V(0, 0, 0);
+    float pdf = 0.f;
+    VisibilityTester vis;
+    bool has_vis = true;
+    const Spectrum li = light_sample_li(sc, l, ref, Vec2{u[2 * i], u[2 * i + 1]}, &wi, &pdf, &vis, &has_vis);
+    float* q = out + 16 * i;
+    for (int k = 0; k < 16; ++k) q[k] = 0.f;
+    if (!has_vis) continue;  // the reference's caller would panic here (integrator.rs:51); the device reports zeros
+    const Ray seg = vis.p0.spawn_ray_to_it(vis.p1);
+    q[0] = li.r;
+    q[1] = li.g;
+    q[2] = li.b;
+    q[3] = wi.x;
+    q[4] = wi.y;
+    q[5] = wi.z;
+    q[6] = pdf;
+    q[7] = seg.o.x;
+    q[8] = seg.o.y;
+    q[9] = seg.o.z;
+    q[10] = seg.d.x;
+    q[11] = seg.d.y;
+    q[12] = seg.d.z;
+  }
+}
+void oracle_light_pdf(const PtrsSceneDesc* desc, int light, const float* ref_p, const float* ref_n, const float* wi, size_t n, float* out) {
+  Scene sc{desc};
+  const PtrsLight& l = desc->lights[light];
+  for (size_t i = 0; i < n; ++i) {
+    Interaction ref;
+    ref.p = V(ref_p[3 * i], ref_p[3 * i + 1], ref_p[3 * i + 2]);
+    ref.n = V(ref_n[3 * i], ref_n[3 * i + 1], ref_n[3 * i + 2]);
+    out[i] = light_pdf_li(sc, l, ref, V(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]));
+  }
+}
+
 }  // extern "C"

@@ -93,6 +93,17 @@ class PtrsStats(C.Structure):
                 ("ms_connect_trace", C.c_float), ("ms_resolve", C.c_float)]
 
 
+class PtrsLobeDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("fresnel", C.c_int32), ("r", C.c_float * 3), ("t", C.c_float * 3), ("fa", C.c_float * 3),
+                ("fb", C.c_float * 3), ("eta_a", C.c_float), ("eta_b", C.c_float), ("alpha_x", C.c_float), ("alpha_y", C.c_float),
+                ("disney_g", C.c_int32), ("pad", C.c_int32)]
+
+
+RENDER_EXACT_SHADING = 1
+(LOBE_LAMBERTIAN, LOBE_SPECULAR_REFLECTION, LOBE_SPECULAR_TRANSMISSION, LOBE_FRESNEL_SPECULAR, LOBE_MICROFACET_REFLECTION,
+ LOBE_MICROFACET_TRANSMISSION, LOBE_FRESNEL_BLEND, LOBE_DISNEY_DIFFUSE) = range(8)
+FRESNEL_DIELECTRIC, FRESNEL_CONDUCTOR, FRESNEL_DISNEY, FRESNEL_NOOP = range(4)
+
 # material / texture / light / wrap enums
 MAT_MATTE, MAT_MIRROR, MAT_GLASS, MAT_METAL, MAT_SUBSTRATE, MAT_DISNEY = range(6)
 TEX_CONSTANT, TEX_CHECKER, TEX_IMAGE = range(3)

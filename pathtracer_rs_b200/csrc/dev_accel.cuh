@@ -217,7 +217,7 @@ PT_DEV bool box_geom(const NodeLoad& n, V3 o, V3 inv_dir, bool nx, bool ny, bool
 //              re-validated with `t_entry < t_max` whenever a hit shrinks t_max, every stack entry when
 //              it is popped.  Leaves are processed first-in first-out, so each triangle is tested in the
 //              reference's order against the reference's t_max: hits, ties and barycentrics are identical.
-// Stack entries are 8 B {entry distance, packed node} (see StackEntry): a pop needs no node reload.
+// Stack entries are 16 B {entry distance, offset, n_prims | axis << 16, -}: a pop needs no node reload.
 //
 // Work is a functor object with
 //   bool begin(uint32_t item, LaneRay* r)                       first ray of a work item (false: nothing to trace)
@@ -266,49 +266,6 @@ PT_DEV void trace_empty(uint32_t n_items, uint32_t* ticket, Work& work) {
 #define PT_RB_KZ_SHIFT 3
 #define PT_RB_ANY 32u
 #define PT_RB_LIVE 64u
-
-// Pending-node stack entries are 8 bytes {entry distance, packed node}: half the local-memory footprint of a
-// (distance, offset, meta) triple, which is what keeps the hot top of 4096 stacks per SM inside L1 next to the
-// nodes.  Packed node word:
-//   bit 31 = 0   interior:  (first child slot >> 1) << 2 | split axis        (child pairs sit at even slots)
-//   bit 31 = 1, bit 30 = 0   leaf, packed:  (n_prims - 1) << 26 | first primitive   (n_prims <= 16, primitive < 2^26)
-//   bit 31 = 1, bit 30 = 1   leaf, by reference: the node's slot; (offset, n_prims) are re-read when it is popped
-#ifndef PT_STACK8
-#define PT_STACK8 1
-#endif
-#if PT_STACK8
-typedef uint2 StackEntry;
-PT_DEV StackEntry stack_pack(float t, uint32_t off, uint32_t meta, uint32_t slot) {
-  uint32_t w;
-  const uint32_t np = meta & 0xffffu;
-  if (np == 0) w = ((off >> 1) << 2) | ((meta >> 16) & 3u);
-  else if (np <= 16u && off < (1u << 26)) w = 0x80000000u | ((np - 1u) << 26) | off;
-  else w = 0xc0000000u | slot;
-  return make_uint2(__float_as_uint(t), w);
-}
-PT_DEV void stack_unpack(const float4* __restrict__ nodes, StackEntry e, uint32_t* off, uint32_t* meta) {
-  const uint32_t w = e.y;
-  if (!(w & 0x80000000u)) {
-    *off = (w >> 2) << 1;
-    *meta = (w & 3u) << 16;
-  } else if (!(w & 0x40000000u)) {
-    *off = w & 0x03ffffffu;
-    *meta = ((w >> 26) & 15u) + 1u;
-  } else {
-    const float2 om = __ldg(reinterpret_cast<const float2*>(nodes + 2 * (size_t)(w & 0x3fffffffu) + 1) + 1);
-    *off = __float_as_uint(om.x);
-    *meta = __float_as_uint(om.y);
-  }
-}
-#else
-typedef uint4 StackEntry;
-PT_DEV StackEntry stack_pack(float t, uint32_t off, uint32_t meta, uint32_t) { return make_uint4(__float_as_uint(t), off, meta, 0u); }
-PT_DEV void stack_unpack(const float4* __restrict__, StackEntry e, uint32_t* off, uint32_t* meta) {
-  *off = e.y;
-  *meta = e.z;
-}
-#endif
-
 template <class Work>
 PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, Work& work) {
   if (sc.n_nodes == 0) {
@@ -319,7 +276,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
   // fewer lanes than this able to take a box step -> the warp turns to its parked leaves.  Scheduling only (results do
   // not depend on it); measured: 12 is best on trees of a few dozen nodes, 20 on trees of 10^5 .. 10^7 nodes.
   const int box_min = (int)sc.box_min;
-  StackEntry stack[PT_STACK_SIZE];
+  uint4 stack[PT_STACK_SIZE];
   int sp_ = 0;
   // node in hand (its box test passed under the t_max current at that time): offset, meta, entry distance
   uint32_t cur_off = 0, cur_meta = PT_NO_NODE;
@@ -386,60 +343,57 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
       continue;
     }
 
-    // ---- box phase ---------------------------------------------------------------------------------------
-    // Each iteration has two steps.  ACQUIRE: a lane without an interior node in hand parks the leaf it holds (if its
-    // parking slot is free) and pops pending entries — the reference's box test at pop time, `t_entry < t_max` —
-    // until an interior node survives, a second leaf blocks it, or the stack is empty; a cheap, divergent loop.
-    // EXPAND: the lanes that hold an interior node load its two children (one 64-byte pair) and run both slab
-    // tests — the expensive step, which therefore runs with every lane that has one to take.
+    // ---- box phase: pop / park / expand ----------------------------------------------------------------
     for (;;) {
       const bool live = (rbits & PT_RB_LIVE) != 0;
-      if (live) {
-        for (;;) {
-          if (cur_meta != PT_NO_NODE) {
-            if ((cur_meta & 0xffffu) == 0) break;  // interior node in hand
-            if (pl_cnt != 0) break;                // a second leaf: blocked until the triangle phase
-            pl_off = cur_off;                      // park the leaf, keep descending
-            pl_cnt = cur_meta & 0xffffu;
-            cur_meta = PT_NO_NODE;
-          }
-          if (sp_ == 0) break;
+      const bool cur_leaf = cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0;
+      const bool can_box = live && ((cur_meta != PT_NO_NODE && !cur_leaf) || (cur_meta == PT_NO_NODE && sp_ > 0) || (cur_leaf && pl_cnt == 0));
+      const uint32_t bmask = __ballot_sync(FULL, can_box);
+      if (bmask == 0) break;
+      if (__popc(bmask) < box_min && __ballot_sync(FULL, live && !can_box) != 0) break;
+      if (can_box) {
+        if (cur_meta == PT_NO_NODE) {  // pop one entry; the reference's box test at pop time
           --sp_;
-          const StackEntry e = stack[sp_];
+          const uint4 e = stack[sp_];
           if (__uint_as_float(e.x) < t_max) {
             cur_t = __uint_as_float(e.x);
-            stack_unpack(sc.nodes, e, &cur_off, &cur_meta);
+            cur_off = e.y;
+            cur_meta = e.z;
           }
         }
-      }
-      const bool ready = live && cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) == 0;
-      const uint32_t bmask = __ballot_sync(FULL, ready);
-      if (bmask == 0) break;
-      if (__popc(bmask) < box_min && __ballot_sync(FULL, live && !ready) != 0) break;
-      if (ready) {
-        const NodeLoad L = load_node(sc.nodes, cur_off);
-        const NodeLoad R = load_node(sc.nodes, cur_off + 1);
-        const bool nx = rbits & PT_RB_NX, ny = rbits & PT_RB_NY, nz = rbits & PT_RB_NZ;
-        const bool neg = ((rbits >> ((cur_meta >> 16) & 3u)) & 1u) != 0;  // dir_is_neg[axis]
-        float tl, tr;
-        const bool gl = box_geom(L, o, inv_dir, nx, ny, nz, &tl);
-        const bool gr = box_geom(R, o, inv_dir, nx, ny, nz, &tr);
-        // near child first (accelerator.rs:393-404)
-        const bool gn = neg ? gr : gl, gf = neg ? gl : gr;
-        const float tn = neg ? tr : tl, tf = neg ? tl : tr;
-        const float4 nb = neg ? R.b : L.b, fb = neg ? L.b : R.b;
-        if (gf && tf < t_max) {
-          if (sp_ < PT_STACK_SIZE) {  // always true: ptrs_scene_create refuses trees deeper than the stack
-            stack[sp_] = stack_pack(tf, __float_as_uint(fb.z), __float_as_uint(fb.w), cur_off + (neg ? 0u : 1u));
-            ++sp_;
+        if (cur_meta != PT_NO_NODE) {
+          if ((cur_meta & 0xffffu) != 0) {
+            if (pl_cnt == 0) {  // park the leaf, keep descending
+              pl_off = cur_off;
+              pl_cnt = cur_meta & 0xffffu;
+              cur_meta = PT_NO_NODE;
+            }
+          } else {
+            const NodeLoad L = load_node(sc.nodes, cur_off);
+            const NodeLoad R = load_node(sc.nodes, cur_off + 1);
+            const bool nx = rbits & PT_RB_NX, ny = rbits & PT_RB_NY, nz = rbits & PT_RB_NZ;
+            const bool neg = ((rbits >> ((cur_meta >> 16) & 3u)) & 1u) != 0;  // dir_is_neg[axis]
+            float tl, tr;
+            const bool gl = box_geom(L, o, inv_dir, nx, ny, nz, &tl);
+            const bool gr = box_geom(R, o, inv_dir, nx, ny, nz, &tr);
+            // near child first (accelerator.rs:393-404)
+            const bool gn = neg ? gr : gl, gf = neg ? gl : gr;
+            const float tn = neg ? tr : tl, tf = neg ? tl : tr;
+            const float4 nb = neg ? R.b : L.b, fb = neg ? L.b : R.b;
+            if (gf && tf < t_max) {
+              if (sp_ < PT_STACK_SIZE) {  // always true: ptrs_scene_create refuses trees deeper than the stack
+                stack[sp_] = make_uint4(__float_as_uint(tf), __float_as_uint(fb.z), __float_as_uint(fb.w), 0u);
+                ++sp_;
+              }
+            }
+            if (gn && tn < t_max) {
+              cur_t = tn;
+              cur_off = __float_as_uint(nb.z);
+              cur_meta = __float_as_uint(nb.w);
+            } else {
+              cur_meta = PT_NO_NODE;
+            }
           }
-        }
-        if (gn && tn < t_max) {
-          cur_t = tn;
-          cur_off = __float_as_uint(nb.z);
-          cur_meta = __float_as_uint(nb.w);
-        } else {
-          cur_meta = PT_NO_NODE;
         }
       }
     }

@@ -394,4 +394,67 @@ PT_DEVN float triangle_pdf_at_point(const DevScene& sc, int prim, const Inter& r
   return norm_squared(ref.p - p_hit) / (fabsf(dot(n, -wi)) * area);
 }
 
+
+// Light::sample_li (light.rs:97-116 point, :176-196 directional, :262-280 area, :402-441 infinite): incident
+// direction, pdf, the far end of the visibility segment and the unoccluded radiance.  pdf == 0 with black Li is what
+// the infinite light's early return (map_pdf == 0, where the reference's caller would panic on the missing
+// VisibilityTester, integrator.rs:51) becomes here.
+struct LightSample {
+  V3 wi;
+  float pdf;
+  Inter p1;  // VisibilityTester.p1
+  Spec li;
+};
+PT_DEV bool light_is_delta(const PtrsLight& light) { return light.type == PTRS_LIGHT_POINT || light.type == PTRS_LIGHT_DIRECTIONAL; }
+PT_DEV void light_sample_li(const DevScene& sc, const PtrsLight& light, const Inter& ref, V2 u, LightSample* out) {
+  out->wi = mk3(0, 0, 0);
+  out->pdf = 0.0f;
+  out->p1.p = mk3(0, 0, 0);
+  out->p1.p_error = mk3(0, 0, 0);
+  out->p1.n = mk3(0, 0, 0);
+  out->li = sp(0.f);
+  if (light.type == PTRS_LIGHT_POINT) {
+    V3 pl = mk3(light.pos[0], light.pos[1], light.pos[2]);
+    out->wi = normalize(pl - ref.p);
+    out->pdf = 1.0f;
+    out->p1.p = pl;
+    out->li = sp(light.color[0], light.color[1], light.color[2]) / norm_squared(pl - ref.p);
+  } else if (light.type == PTRS_LIGHT_DIRECTIONAL) {
+    V3 wl = mk3(light.pos[0], light.pos[1], light.pos[2]);
+    out->wi = wl;
+    out->pdf = 1.0f;
+    out->p1.p = ref.p + wl * (2.0f * light.world_radius);
+    out->li = sp(light.color[0], light.color[1], light.color[2]);
+  } else if (light.type == PTRS_LIGHT_AREA) {
+    TriPoint tp = triangle_sample(sc, light.prim, u);
+    out->wi = normalize(tp.it.p - ref.p);
+    out->pdf = triangle_pdf_at_point(sc, light.prim, ref, out->wi, light.area);
+    out->p1 = tp.it;
+    if (dot(tp.it.n, -out->wi) > 0.0f) out->li = tex_spec(sc, light.ke_tex, TexCoord{tp.uv.x, tp.uv.y, 0.f, 0.f, 0.f, 0.f});
+  } else {  // PTRS_LIGHT_INFINITE
+    const DevEnv& e = sc.envs[light.env];
+    float map_pdf = 0.0f;
+    V2 uv = dist2d_sample(e, u, &map_pdf);
+    if (map_pdf != 0.0f) {
+      float theta = uv.y * PT_PI, phi = uv.x * 2.0f * PT_PI;
+      float cos_t = cosf(theta), sin_t = sinf(theta);
+      float sin_p = sinf(phi), cos_p = cosf(phi);
+      out->wi = xform_vec(e.light_to_world, mk3(sin_t * cos_p, sin_t * sin_p, cos_t));
+      out->pdf = sin_t == 0.0f ? 0.0f : map_pdf / (2.0f * PT_PI * PT_PI * sin_t);
+      out->p1.p = ref.p + out->wi * (2.0f * light.world_radius);
+      out->li = env_lookup(sc, e, uv.x, uv.y);
+    }
+  }
+}
+// Light::pdf_li for the lights that have one (area light.rs:286-288, infinite :447-461; delta lights return 0)
+PT_DEV float light_pdf_li(const DevScene& sc, const PtrsLight& light, const Inter& ref, V3 w) {
+  if (light.type == PTRS_LIGHT_AREA) return triangle_pdf_at_point(sc, light.prim, ref, w, light.area);
+  if (light.type != PTRS_LIGHT_INFINITE) return 0.0f;
+  const DevEnv& e = sc.envs[light.env];
+  V3 wl = xform_vec(e.world_to_light, w);
+  float theta = spherical_theta(wl), phi = spherical_phi(wl);
+  float sin_t = sinf(theta);
+  return sin_t == 0.0f ? 0.0f : dist2d_pdf(e, phi * PT_INV_2_PI, theta * PT_FRAC_1_PI) / (2.0f * PT_PI * PT_PI * sin_t);
+}
+
 }  // namespace ptrs

@@ -11,49 +11,14 @@ PT_DEV void nee_prepare(const DevScene& sc, const SurfInter& si, const Bsdf& bsd
                         float4* n0, float4* n1, float4* n2, float4* n3, float4* n4, float* scat_pdf_out, uint32_t* nee_flags) {
   const PtrsLight& light = sc.lights[light_idx];
   const uint32_t bsdf_flags = BSDF_ALL & ~BSDF_SPECULAR;
-  V3 wi = mk3(0, 0, 0);
-  float light_pdf = 0.0f, scattering_pdf = 0.0f;
-  Inter p1;  // VisibilityTester.p1
-  p1.p_error = mk3(0, 0, 0);
-  p1.n = mk3(0, 0, 0);
-  Spec li = sp(0.f);
-  const bool delta = light.type == PTRS_LIGHT_POINT || light.type == PTRS_LIGHT_DIRECTIONAL;
-  if (light.type == PTRS_LIGHT_POINT) {  // light.rs:97-116
-    V3 pl = mk3(light.pos[0], light.pos[1], light.pos[2]);
-    wi = normalize(pl - si.g.p);
-    light_pdf = 1.0f;
-    p1.p = pl;
-    li = sp(light.color[0], light.color[1], light.color[2]) / norm_squared(pl - si.g.p);
-  } else if (light.type == PTRS_LIGHT_DIRECTIONAL) {  // light.rs:176-196
-    V3 wl = mk3(light.pos[0], light.pos[1], light.pos[2]);
-    wi = wl;
-    light_pdf = 1.0f;
-    p1.p = si.g.p + wl * (2.0f * light.world_radius);
-    li = sp(light.color[0], light.color[1], light.color[2]);
-  } else if (light.type == PTRS_LIGHT_AREA) {  // light.rs:262-280
-    TriPoint tp = triangle_sample(sc, light.prim, u_light);
-    wi = normalize(tp.it.p - si.g.p);
-    light_pdf = triangle_pdf_at_point(sc, light.prim, si.g, wi, light.area);
-    p1 = tp.it;
-    if (dot(tp.it.n, -wi) > 0.0f) li = tex_spec(sc, light.ke_tex, TexCoord{tp.uv.x, tp.uv.y, 0.f, 0.f, 0.f, 0.f});
-  } else {  // PTRS_LIGHT_INFINITE, light.rs:402-441
-    const DevEnv& e = sc.envs[light.env];
-    float map_pdf = 0.0f;
-    V2 uv = dist2d_sample(e, u_light, &map_pdf);
-    if (map_pdf == 0.0f) {
-      // the reference panics here (visibility.unwrap() on None, integrator.rs:51); unreachable for a
-      // distribution with positive integral.  Contribute nothing.
-      light_pdf = 0.0f;
-    } else {
-      float theta = uv.y * PT_PI, phi = uv.x * 2.0f * PT_PI;
-      float cos_t = cosf(theta), sin_t = sinf(theta);
-      float sin_p = sinf(phi), cos_p = cosf(phi);
-      wi = xform_vec(e.light_to_world, mk3(sin_t * cos_p, sin_t * sin_p, cos_t));
-      light_pdf = sin_t == 0.0f ? 0.0f : map_pdf / (2.0f * PT_PI * PT_PI * sin_t);
-      p1.p = si.g.p + wi * (2.0f * light.world_radius);
-      li = env_lookup(sc, e, uv.x, uv.y);
-    }
-  }
+  float scattering_pdf = 0.0f;
+  const bool delta = light_is_delta(light);
+  LightSample ls;
+  light_sample_li(sc, light, si.g, u_light, &ls);
+  const V3 wi = ls.wi;
+  const float light_pdf = ls.pdf;
+  const Inter& p1 = ls.p1;
+  const Spec li = ls.li;
   uint32_t nf = (uint32_t)light_idx;
   Spec A = sp(0.f);
   V3 sh_o = mk3(0, 0, 0), sh_d = mk3(0, 0, 0);
@@ -79,16 +44,7 @@ PT_DEV void nee_prepare(const DevScene& sc, const SurfInter& si, const Bsdf& bsd
     if (!is_black(f2) && scattering_pdf > 0.0f) {
       bool go = true;
       if (!sampled_specular) {
-        float lp;
-        if (light.type == PTRS_LIGHT_AREA) {
-          lp = triangle_pdf_at_point(sc, light.prim, si.g, wi2, light.area);
-        } else {  // infinite, light.rs:447-461
-          const DevEnv& e = sc.envs[light.env];
-          V3 w = xform_vec(e.world_to_light, wi2);
-          float theta = spherical_theta(w), phi = spherical_phi(w);
-          float sin_t = sinf(theta);
-          lp = sin_t == 0.0f ? 0.0f : dist2d_pdf(e, phi * PT_INV_2_PI, theta * PT_FRAC_1_PI) / (2.0f * PT_PI * PT_PI * sin_t);
-        }
+        const float lp = light_pdf_li(sc, light, si.g, wi2);
         if (lp == 0.0f) go = false;  // `return ld` (integrator.rs:107-109)
         else weight = power_heuristic(scattering_pdf, lp);
       }
@@ -118,7 +74,13 @@ PT_DEV void nee_prepare(const DevScene& sc, const SurfInter& si, const Bsdf& bsd
 #define PT_SHADE_BLOCK 128
 #endif
 
-template <int MAT>
+// EXACT only names the build: the exact instantiation comes from a translation unit compiled with IEEE division /
+// square root and without FMA contraction (PtrsRenderParams.flags & PTRS_RENDER_EXACT_SHADING, Makefile EXACTSHADE),
+// the other from the fast-math-free but contracted default build; the source is the same.
+#ifndef PT_SHADE_EXACT
+#define PT_SHADE_EXACT 0
+#endif
+template <int MAT, bool EXACT>
 __global__ void __launch_bounds__(PT_SHADE_BLOCK, PT_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ RenderConst rc, PT_SHADE_PARAM DevScene sc, PT_SHADE_PARAM PathArrays P,
                                                      const int* __restrict__ q, const float4* __restrict__ q_hit, int* __restrict__ q_ext_next,
                                                      int* __restrict__ q_nee, RoundCounters* ctr, RoundCounters* ctr_next) {
@@ -317,9 +279,14 @@ __global__ void __launch_bounds__(PT_SHADE_BLOCK, PT_SHADE_MIN_BLOCKS) shade_ker
 #endif
 #define PT_CAT2(a, b) a##b
 #define PT_CAT(a, b) PT_CAT2(a, b)
-void PT_CAT(launch_shade_, PT_SHADE_MAT)(cudaStream_t st, int sm, const RenderConst& rc, const DevScene& sc, const PathArrays& P, const int* q,
+#if PT_SHADE_EXACT
+#define PT_SHADE_LAUNCHER PT_CAT(launch_shade_exact_, PT_SHADE_MAT)
+#else
+#define PT_SHADE_LAUNCHER PT_CAT(launch_shade_, PT_SHADE_MAT)
+#endif
+void PT_SHADE_LAUNCHER(cudaStream_t st, int sm, const RenderConst& rc, const DevScene& sc, const PathArrays& P, const int* q,
                                          const float4* q_hit, int* q_next, int* q_nee, RoundCounters* ctr, RoundCounters* ctr_next) {
-  shade_kernel<PT_SHADE_MAT><<<PT_GRID(shade_kernel<PT_SHADE_MAT>, PT_SHADE_BLOCK, sm), PT_SHADE_BLOCK, 0, st>>>(rc, sc, P, q, q_hit, q_next, q_nee, ctr, ctr_next);
+  shade_kernel<PT_SHADE_MAT, PT_SHADE_EXACT != 0><<<PT_GRID((shade_kernel<PT_SHADE_MAT, PT_SHADE_EXACT != 0>), PT_SHADE_BLOCK, sm), PT_SHADE_BLOCK, 0, st>>>(rc, sc, P, q, q_hit, q_next, q_nee, ctr, ctr_next);
 }
 
 }  // namespace ptrs

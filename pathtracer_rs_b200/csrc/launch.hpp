@@ -42,6 +42,12 @@ void launch_connect(cudaStream_t st, int sm, bool count, const DevScene& sc, con
 void launch_intersect(cudaStream_t st, int sm, bool any_hit, bool count, const DevScene& sc, const PtrsRay* rays, uint32_t n, PtrsHit* hits,
                       uint8_t* occluded, uint32_t* ticket, GlobalCounters* g, const uint32_t* prim_map);
 
+// k_sort.cu: ray reordering of an extend queue (see there)
+struct PathSlot;
+size_t queue_sort_temp_bytes(uint32_t cap);
+int sort_queue(cudaStream_t st, int sm, const PathSlot* slot, const int* q, const uint32_t* n_ptr, uint32_t m, const float world_bound[6], uint32_t* keys_a,
+               uint32_t* keys_b, int* q_sorted, void* temp, size_t temp_bytes, int begin_bit);
+
 // k_bvh.cu
 int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vertex, const float* d_pos, float4** nodes_out, uint32_t* n_nodes_out,
                         uint32_t** perm_out, uint32_t* depth_out);
@@ -54,11 +60,24 @@ int validate_prims_on_device(cudaStream_t st, uint32_t n, const uint32_t* prim_v
 int pair_layout_on_device(cudaStream_t st, const float4* d_raw, uint32_t n, uint32_t n_interior, float4** out, uint32_t* n_out);
 void launch_remap_light_prims(cudaStream_t st, PtrsLight* lights, uint32_t n_lights, const uint32_t* inv_perm);
 
+// k_probe.cu, built twice (shade-kernel arithmetic / exact arithmetic)
+#define PT_DECL_PROBES(SUF)                                                                                                                       \
+  void launch_bxdf_eval_probe_##SUF(cudaStream_t st, const PtrsLobeDesc& d, const float* wo, const float* wi, uint32_t n, float* out);             \
+  void launch_bxdf_sample_probe_##SUF(cudaStream_t st, const PtrsLobeDesc& d, const float* wo, const float* u, uint32_t n, float* out);            \
+  void launch_light_sample_probe_##SUF(cudaStream_t st, const DevScene& sc, int light, const float* p, const float* nn, const float* u, uint32_t n, \
+                                       float* out);                                                                                               \
+  void launch_light_pdf_probe_##SUF(cudaStream_t st, const DevScene& sc, int light, const float* p, const float* nn, const float* wi, uint32_t n,  \
+                                    float* out);
+PT_DECL_PROBES(fast) PT_DECL_PROBES(exact)
+#undef PT_DECL_PROBES
+
 // k_shade.cu, built once per PtrsMaterialType
 #define PT_DECL_SHADE(M)                                                                                                              \
   void launch_shade_##M(cudaStream_t st, int sm, const RenderConst& rc, const DevScene& sc, const PathArrays& P, const int* q, const float4* q_hit, \
                         int* q_next, int* q_nee, RoundCounters* ctr, RoundCounters* ctr_next);
 PT_DECL_SHADE(0) PT_DECL_SHADE(1) PT_DECL_SHADE(2) PT_DECL_SHADE(3) PT_DECL_SHADE(4) PT_DECL_SHADE(5)
+// the same kernels from translation units built with IEEE division / square root and no FMA contraction
+PT_DECL_SHADE(exact_0) PT_DECL_SHADE(exact_1) PT_DECL_SHADE(exact_2) PT_DECL_SHADE(exact_3) PT_DECL_SHADE(exact_4) PT_DECL_SHADE(exact_5)
 #undef PT_DECL_SHADE
 
 #define PT_MAX_DEVICES 64

@@ -176,6 +176,12 @@ struct Workspace {
   DevBuf<NeeRes> nee_res;
   DevBuf<int> q_ext[2], q_nee, q_class;
   DevBuf<uint32_t> q_ray;
+  // ray reordering (k_sort.cu): sorted copy of an extend queue, key double buffer, cub's scratch; and the queue
+  // lengths the previous batch saw per round (the host's estimate of how much there is to sort)
+  DevBuf<int> q_sorted;
+  DevBuf<uint32_t> sort_keys[2];
+  DevBuf<unsigned char> sort_temp;
+  std::vector<uint32_t> prev_len;
   DevBuf<RoundCounters> counters;
   DevBuf<GlobalCounters> gcount;
   PathArrays arrays() {
@@ -189,7 +195,7 @@ struct Workspace {
     return a;
   }
   uint64_t bytes() const {
-    return (uint64_t)cap * (sizeof(PathSlot) + 16 + sizeof(NeeRec) + sizeof(NeeRes) + 4 * 5 + (4 + 16) * PT_N_CLASSES) + (uint64_t)rounds * sizeof(RoundCounters);
+    return (uint64_t)cap * (sizeof(PathSlot) + 16 + sizeof(NeeRec) + sizeof(NeeRes) + 4 * 8 + (4 + 16) * PT_N_CLASSES) + (uint64_t)rounds * sizeof(RoundCounters) + sort_temp.n;
   }
 };
 
@@ -224,6 +230,10 @@ struct PtrsScene {
   Workspace ws;
   PtrsStats stats{};
   bool count_visits = false;
+  // ray reordering between bounces (k_sort.cu); PTRS_SORT_RAYS=0 switches it off, PTRS_SORT_MIN / PTRS_SORT_BEGIN_BIT tune it
+  bool sort_rays = true;
+  uint32_t sort_min = 1u << 20;
+  int sort_begin_bit = 0;
   bool has_mat[PTRS_MAT_COUNT] = {false, false, false, false, false, false};
   int sm_count = 148;
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -337,6 +347,11 @@ int32_t ensure_workspace(PtrsScene* s, uint32_t cap, uint32_t rounds) {
   WS_ALLOC(w.q_nee, cap);
   WS_ALLOC(w.q_ray, (size_t)cap * 2);
   WS_ALLOC(w.q_class, (size_t)cap * PT_N_CLASSES);
+  WS_ALLOC(w.q_sorted, cap);
+  WS_ALLOC(w.sort_keys[0], cap);
+  WS_ALLOC(w.sort_keys[1], cap);
+  WS_ALLOC(w.sort_temp, queue_sort_temp_bytes(cap));
+  w.prev_len.clear();
   WS_ALLOC(w.counters, rounds + 1);
   WS_ALLOC(w.gcount, 1);
 #undef WS_ALLOC
@@ -429,7 +444,7 @@ struct StageTimer {
 
 // One wavefront batch: `n_work` path slots already described by (work_base | lists); runs rounds until
 // every path has ended.  Leaves per-path radiance in ws.L.
-int32_t run_batch(PtrsScene* s, const RenderConst& rc, uint64_t work_base, uint32_t n_work, const int* d_list_xy, const int* d_list_s,
+int32_t run_batch(PtrsScene* s, const RenderConst& rc, bool exact_shading, uint64_t work_base, uint32_t n_work, const int* d_list_xy, const int* d_list_s,
                   cudaStream_t st, StageTimer& tm, uint64_t* ext_rays) {
   Workspace& w = s->ws;
   PathArrays P = w.arrays();
@@ -450,6 +465,22 @@ int32_t run_batch(PtrsScene* s, const RenderConst& rc, uint64_t work_base, uint3
       int* q_in = w.q_ext[round & 1].p;
       int* q_out = w.q_ext[(round + 1) & 1].p;
       tm.begin(ST_EXTEND);
+      // Ray reordering (k_sort.cu): from the second round on the queue is in append order, i.e. scattered over the
+      // scene.  How long it is is only known on the device; the previous batch of this render (same pixels, next
+      // sample numbers) had nearly the same lengths, the first batch falls back to "everything is still alive" for the
+      // rounds before Russian roulette starts.  Not worth it for short queues.
+      if (s->sort_rays && round >= 1) {
+        uint32_t est = 0;
+        if (round < w.prev_len.size()) est = (uint32_t)std::min<uint64_t>(n_work, (uint64_t)w.prev_len[round] + w.prev_len[round] / 32 + 1024);
+        else if (w.prev_len.empty() && (int)round <= rc.rr_start_depth + 1) est = n_work;
+        if (est >= s->sort_min) {
+          const int se = sort_queue(st, sm, P.slot, q_in, &c->n_ext, est, s->world_bound, w.sort_keys[0].p, w.sort_keys[1].p, w.q_sorted.p, w.sort_temp.p,
+                                    w.sort_temp.n, s->sort_begin_bit);
+          if (se != (int)cudaSuccess) return fail(PTRS_ERR_CUDA, std::string("queue sort: ") + cudaGetErrorString((cudaError_t)se));
+          q_in = w.q_sorted.p;
+          s->stats.launches += 5;  // key kernel + cub's histogram and 4 onesweep passes
+        }
+      }
       launch_extend(st, sm, s->count_visits, s->dev, P, q_in, w.q_class.p, cap, c, w.gcount.p);
       s->stats.extend_launches += 1;
       tm.end();
@@ -460,7 +491,10 @@ int32_t run_batch(PtrsScene* s, const RenderConst& rc, uint64_t work_base, uint3
       }
 #define SHADE(M)                                                                                                               \
   if (s_has_mat[M]) {                                                                                                          \
-    launch_shade_##M(st, sm, rc, s->dev, P, w.q_class.p + (size_t)(M)*cap, w.q_hit.p + (size_t)(M)*cap, q_out, w.q_nee.p, c, c + 1);                        \
+    if (exact_shading)                                                                                                         \
+      launch_shade_exact_##M(st, sm, rc, s->dev, P, w.q_class.p + (size_t)(M)*cap, w.q_hit.p + (size_t)(M)*cap, q_out, w.q_nee.p, c, c + 1); \
+    else                                                                                                                       \
+      launch_shade_##M(st, sm, rc, s->dev, P, w.q_class.p + (size_t)(M)*cap, w.q_hit.p + (size_t)(M)*cap, q_out, w.q_nee.p, c, c + 1);       \
     s->stats.launches += 1;                                                                                                    \
   }
       const bool* s_has_mat = s->has_mat;
@@ -487,6 +521,8 @@ int32_t run_batch(PtrsScene* s, const RenderConst& rc, uint64_t work_base, uint3
     if (host_ctr[round].n_ext == 0 || round >= w.rounds) break;  // only null-BSDF chains need extra rounds
   }
   for (uint32_t r = 0; r < round; ++r) *ext_rays += host_ctr[r].n_ext;
+  w.prev_len.resize(round);
+  for (uint32_t r = 0; r < round; ++r) w.prev_len[r] = host_ctr[r].n_ext;
   if (host_ctr[round].n_ext != 0) return fail(PTRS_ERR_UNSUPPORTED, "paths still alive after the maximum number of wavefront rounds");
   return PTRS_OK;
 }
@@ -771,6 +807,9 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
   v.n_infinite_lights = d->n_infinite_lights;
   v.box_min = n_dev_nodes <= 4096u ? 12u : 20u;
   if (const char* e = std::getenv("PTRS_BOX_MIN")) v.box_min = (uint32_t)std::max(1, std::min(32, std::atoi(e)));  // tuning only
+  if (const char* e = std::getenv("PTRS_SORT_RAYS")) s->sort_rays = std::atoi(e) != 0;
+  if (const char* e = std::getenv("PTRS_SORT_MIN")) s->sort_min = (uint32_t)std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("PTRS_SORT_BEGIN_BIT")) s->sort_begin_bit = std::max(0, std::min(24, std::atoi(e)));
   v.uses_differentials = 0;
   for (uint32_t i = 0; i < d->n_materials; ++i) {
     static const int n_tex[PTRS_MAT_COUNT] = {1, 0, 3, 5, 4, 4};
@@ -1074,6 +1113,7 @@ static int32_t render_impl(PtrsScene* s, const PtrsCamera* cam, const PtrsRender
   }
   StageTimer tm{s, st};
   float ms[ST_COUNT] = {};
+  s->ws.prev_len.clear();  // queue-length estimates are per render
   uint64_t ext_rays = 0, paths = 0;
   CUDA_TRY(cudaEventRecord(s->ev[0], st));
   // equal batches (whole 8x4 blocks) rather than full ones and a remainder: a nearly empty last batch would
@@ -1082,7 +1122,7 @@ static int32_t render_impl(PtrsScene* s, const PtrsCamera* cam, const PtrsRender
   const uint64_t per_batch = n_batches ? std::min<uint64_t>(s->ws.cap, (((total + n_batches - 1) / n_batches) + 31) & ~(uint64_t)31) : 0;
   for (uint64_t base = 0; base < total; base += per_batch) {
     const uint32_t n_work = (uint32_t)std::min<uint64_t>(per_batch, total - base);
-    r = run_batch(s, rc, base, n_work, list_xy ? d_xy.p + 2 * base : nullptr, list_xy ? d_s.p + base : nullptr, st, tm, &ext_rays);
+    r = run_batch(s, rc, (rp->flags & PTRS_RENDER_EXACT_SHADING) != 0, base, n_work, list_xy ? d_xy.p + 2 * base : nullptr, list_xy ? d_s.p + base : nullptr, st, tm, &ext_rays);
     if (r != PTRS_OK) return r;
     if (film) {
       tm.begin(ST_ACCUMULATE);
@@ -1235,6 +1275,81 @@ int32_t ptrs_generate_rays(const PtrsCamera* camera, const PtrsRenderParams* par
   CUDA_TRY(cudaMemcpy(rays, d_rays.p, n * sizeof(PtrsRay), cudaMemcpyDeviceToHost));
   if (p_film) CUDA_TRY(cudaMemcpy(p_film, d_pf.p, n * 8, cudaMemcpyDeviceToHost));
   if (rxry_dir) CUDA_TRY(cudaMemcpy(rxry_dir, d_rx.p, n * 24, cudaMemcpyDeviceToHost));
+  return PTRS_OK;
+}
+
+// ---- function-level probes (k_probe.cu) ------------------------------------------------------------------
+static int32_t check_lobe(const PtrsLobeDesc* l) {
+  if (l->kind < PTRS_LOBE_LAMBERTIAN || l->kind > PTRS_LOBE_DISNEY_DIFFUSE || l->fresnel < PTRS_FRESNEL_DIELECTRIC || l->fresnel > PTRS_FRESNEL_NOOP)
+    return fail(PTRS_ERR_INVALID_ARGUMENT, "unknown lobe / Fresnel kind");
+  return PTRS_OK;
+}
+
+int32_t ptrs_bxdf_eval(const PtrsLobeDesc* lobe, const float* wo, const float* wi, size_t n, int32_t flags, float* out) {
+  if (!lobe || (n && (!wo || !wi || !out))) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  if (n == 0) return PTRS_OK;
+  if (n > 0x7fffffffull) return fail(PTRS_ERR_INVALID_ARGUMENT, "too many samples in one call");
+  if (int32_t r = check_lobe(lobe)) return r;
+  DevBuf<float> d_wo, d_wi, d_out;
+  CUDA_TRY(d_wo.upload(wo, n * 3));
+  CUDA_TRY(d_wi.upload(wi, n * 3));
+  CUDA_TRY(d_out.alloc(n * 4));
+  if (flags & PTRS_RENDER_EXACT_SHADING) launch_bxdf_eval_probe_exact(0, *lobe, d_wo.p, d_wi.p, (uint32_t)n, d_out.p);
+  else launch_bxdf_eval_probe_fast(0, *lobe, d_wo.p, d_wi.p, (uint32_t)n, d_out.p);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(out, d_out.p, n * 16, cudaMemcpyDeviceToHost));
+  return PTRS_OK;
+}
+
+int32_t ptrs_bxdf_sample(const PtrsLobeDesc* lobe, const float* wo, const float* u, size_t n, int32_t flags, float* out) {
+  if (!lobe || (n && (!wo || !u || !out))) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  if (n == 0) return PTRS_OK;
+  if (n > 0x7fffffffull) return fail(PTRS_ERR_INVALID_ARGUMENT, "too many samples in one call");
+  if (int32_t r = check_lobe(lobe)) return r;
+  DevBuf<float> d_wo, d_u, d_out;
+  CUDA_TRY(d_wo.upload(wo, n * 3));
+  CUDA_TRY(d_u.upload(u, n * 2));
+  CUDA_TRY(d_out.alloc(n * 8));
+  if (flags & PTRS_RENDER_EXACT_SHADING) launch_bxdf_sample_probe_exact(0, *lobe, d_wo.p, d_u.p, (uint32_t)n, d_out.p);
+  else launch_bxdf_sample_probe_fast(0, *lobe, d_wo.p, d_u.p, (uint32_t)n, d_out.p);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(out, d_out.p, n * 32, cudaMemcpyDeviceToHost));
+  return PTRS_OK;
+}
+
+int32_t ptrs_light_sample(PtrsScene* scene, int32_t light, const float* ref_p, const float* ref_n, const float* u, size_t n, int32_t flags, float* out) {
+  if (!scene || (n && (!ref_p || !ref_n || !u || !out))) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  if (light < 0 || (uint32_t)light >= scene->dev.n_lights) return fail(PTRS_ERR_INVALID_ARGUMENT, "light index out of range");
+  if (n == 0) return PTRS_OK;
+  if (n > 0x7fffffffull) return fail(PTRS_ERR_INVALID_ARGUMENT, "too many samples in one call");
+  ON_DEVICE_OF(scene);
+  DevBuf<float> d_p, d_n, d_u, d_out;
+  CUDA_TRY(d_p.upload(ref_p, n * 3));
+  CUDA_TRY(d_n.upload(ref_n, n * 3));
+  CUDA_TRY(d_u.upload(u, n * 2));
+  CUDA_TRY(d_out.alloc(n * 16));
+  if (flags & PTRS_RENDER_EXACT_SHADING) launch_light_sample_probe_exact(0, scene->dev, light, d_p.p, d_n.p, d_u.p, (uint32_t)n, d_out.p);
+  else launch_light_sample_probe_fast(0, scene->dev, light, d_p.p, d_n.p, d_u.p, (uint32_t)n, d_out.p);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(out, d_out.p, n * 64, cudaMemcpyDeviceToHost));
+  return PTRS_OK;
+}
+
+int32_t ptrs_light_pdf(PtrsScene* scene, int32_t light, const float* ref_p, const float* ref_n, const float* wi, size_t n, int32_t flags, float* out) {
+  if (!scene || (n && (!ref_p || !ref_n || !wi || !out))) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  if (light < 0 || (uint32_t)light >= scene->dev.n_lights) return fail(PTRS_ERR_INVALID_ARGUMENT, "light index out of range");
+  if (n == 0) return PTRS_OK;
+  if (n > 0x7fffffffull) return fail(PTRS_ERR_INVALID_ARGUMENT, "too many samples in one call");
+  ON_DEVICE_OF(scene);
+  DevBuf<float> d_p, d_n, d_w, d_out;
+  CUDA_TRY(d_p.upload(ref_p, n * 3));
+  CUDA_TRY(d_n.upload(ref_n, n * 3));
+  CUDA_TRY(d_w.upload(wi, n * 3));
+  CUDA_TRY(d_out.alloc(n));
+  if (flags & PTRS_RENDER_EXACT_SHADING) launch_light_pdf_probe_exact(0, scene->dev, light, d_p.p, d_n.p, d_w.p, (uint32_t)n, d_out.p);
+  else launch_light_pdf_probe_fast(0, scene->dev, light, d_p.p, d_n.p, d_w.p, (uint32_t)n, d_out.p);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(out, d_out.p, n * 4, cudaMemcpyDeviceToHost));
   return PTRS_OK;
 }
 

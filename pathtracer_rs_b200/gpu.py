@@ -32,6 +32,7 @@ EXPORTS = [
     "ptrs_scene_bvh_info", "ptrs_scene_download_nodes", "ptrs_read_bandwidth", "ptrs_gather_bandwidth",
     "ptrs_multi_create", "ptrs_multi_destroy", "ptrs_multi_device_count", "ptrs_multi_render", "ptrs_multi_root_film", "ptrs_multi_scene",
     "ptrs_comm_unique_id", "ptrs_comm_init_rank", "ptrs_comm_destroy", "ptrs_comm_info", "ptrs_film_reduce",
+    "ptrs_bxdf_eval", "ptrs_bxdf_sample", "ptrs_light_sample", "ptrs_light_pdf",
 ]
 
 
@@ -98,6 +99,11 @@ def lib():
         L.ptrs_comm_destroy.argtypes = [vp]
         L.ptrs_comm_info.argtypes = [vp, i32p, i32p]
         L.ptrs_film_reduce.argtypes = [vp, vp, i32, vp]
+        lobep = C.POINTER(PtrsLobeDesc)
+        L.ptrs_bxdf_eval.argtypes = [lobep, fp, fp, sz, i32, fp]
+        L.ptrs_bxdf_sample.argtypes = [lobep, fp, fp, sz, i32, fp]
+        L.ptrs_light_sample.argtypes = [vp, i32, fp, fp, fp, sz, i32, fp]
+        L.ptrs_light_pdf.argtypes = [vp, i32, fp, fp, fp, sz, i32, fp]
         _LIB = L
     return _LIB
 
@@ -265,6 +271,22 @@ class RenderScene:
         _check(lib().ptrs_stats(self._h, C.byref(st)))
         return {k: getattr(st, k) for k, _ in PtrsStats._fields_}
 
+    def light_sample(self, light, ref_p, ref_n, u, exact=False):
+        """Light::sample_li + the visibility segment for reference points (ptrs_light_sample): (n, 16) rows of
+        Li rgb, wi xyz, pdf, segment origin xyz, segment direction xyz, 3 x pad."""
+        p, nn, uu = (np.ascontiguousarray(a, dtype=np.float32) for a in (ref_p, ref_n, u))
+        n = p.shape[0]
+        out = np.empty((n, 16), dtype=np.float32)
+        _check(lib().ptrs_light_sample(self._h, light, _p(p, C.c_float), _p(nn, C.c_float), _p(uu, C.c_float), n, 1 if exact else 0, _p(out, C.c_float)))
+        return out
+
+    def light_pdf(self, light, ref_p, ref_n, wi, exact=False):
+        p, nn, w = (np.ascontiguousarray(a, dtype=np.float32) for a in (ref_p, ref_n, wi))
+        n = p.shape[0]
+        out = np.empty(n, dtype=np.float32)
+        _check(lib().ptrs_light_pdf(self._h, light, _p(p, C.c_float), _p(nn, C.c_float), _p(w, C.c_float), n, 1 if exact else 0, _p(out, C.c_float)))
+        return out
+
     def path_radiance(self, cam, params, pixels, samples):
         px = np.ascontiguousarray(pixels, dtype=np.int32).reshape(-1, 2)
         sm = np.ascontiguousarray(samples, dtype=np.int32).reshape(-1)
@@ -365,15 +387,34 @@ class PathIntegrator:
     def preprocess(self, scene):  # integrator.rs:250-258
         self.too_many_lights = scene.n_lights > 16
 
-    def render(self, camera, scene, film, stream=None, sample_range=None, sample_stride=(1, 0)):
+    def render(self, camera, scene, film, stream=None, sample_range=None, sample_stride=(1, 0), exact_shading=False):
         """integrator.rs:536 — accumulates into `film` (the reference's camera.film).  sample_range /
-        sample_stride select a shard of the Sobol sample numbers (multi-GPU)."""
+        sample_stride select a shard of the Sobol sample numbers (multi-GPU); exact_shading selects the parity
+        build of the shade kernels (PTRS_RENDER_EXACT_SHADING)."""
         p = PtrsRenderParams.from_buffer_copy(self.params)
+        if exact_shading:
+            p.flags |= RENDER_EXACT_SHADING
         if sample_range is not None:
             p.sample_begin, p.sample_end = sample_range
         p.sample_stride, p.sample_phase = sample_stride
         _check(lib().ptrs_render(scene._h, C.byref(camera), C.byref(p), film._h, C.c_void_p(stream or 0)))
         return scene.stats()
+
+
+def bxdf_eval(lobe, wo, wi, exact=False):
+    """BxDF::f and BxDF::pdf of one lobe (ptrs_bxdf_eval): (n, 4) rows of f rgb, pdf."""
+    o, w = np.ascontiguousarray(wo, dtype=np.float32), np.ascontiguousarray(wi, dtype=np.float32)
+    out = np.empty((o.shape[0], 4), dtype=np.float32)
+    _check(lib().ptrs_bxdf_eval(C.byref(lobe), _p(o, C.c_float), _p(w, C.c_float), o.shape[0], 1 if exact else 0, _p(out, C.c_float)))
+    return out
+
+
+def bxdf_sample(lobe, wo, u, exact=False):
+    """BxDF::sample_f of one lobe (ptrs_bxdf_sample): (n, 8) rows of wi xyz, f rgb, pdf, sampled type bits."""
+    o, uu = np.ascontiguousarray(wo, dtype=np.float32), np.ascontiguousarray(u, dtype=np.float32)
+    out = np.empty((o.shape[0], 8), dtype=np.float32)
+    _check(lib().ptrs_bxdf_sample(C.byref(lobe), _p(o, C.c_float), _p(uu, C.c_float), o.shape[0], 1 if exact else 0, _p(out, C.c_float)))
+    return out
 
 
 def sobol_samples(cam, params, pixels, samples, dims):

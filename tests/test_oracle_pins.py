@@ -136,8 +136,7 @@ def test_next_float_quirk(oracle):
 # ---- camera ---------------------------------------------------------------------------------------------
 def test_camera_conventions(host, oracle):
     """Raster (0, 0) is the top-left corner, +x right, camera looks down -z (common/mod.rs:33-62,
-    pathtracer/mod.rs:59-81).  The reference's own camera tests (common/mod.rs:103-164) look stale
-    (640x360 centre for a 640x480 default) and cannot be run here, so they are not used as vectors."""
+    pathtracer/mod.rs:59-81)."""
     cam = host.look_at_camera((0, 0, 0), (0, 0, -1), (0, 1, 0), 90.0, 640, 480)
     m = np.array(cam.raster_to_screen).reshape(4, 4)
     assert np.allclose(m @ [0, 0, 0, 1], [-1, 1, 0, 1]) and np.allclose(m @ [640, 480, 0, 1], [1, -1, 0, 1])
@@ -148,6 +147,61 @@ def test_camera_conventions(host, oracle):
     assert np.allclose(cam.persp[1], 1.0, atol=1e-6) and np.allclose(cam.persp[0], 0.75, atol=1e-6)  # 1/tan(45), /aspect
     c2 = host.make_scene(host.SCENE_CORNELL, res=(64, 64))[1]
     assert np.allclose(c2.trans, [0, 1, 6.8]) and abs(abs(c2.rot[3]) - 1) < 1e-6  # Cornell sensor: identity rotation
+
+
+def _quat_matrix(q):
+    i, j, k, w = q
+    return np.array([[1 - 2 * (j * j + k * k), 2 * (i * j - k * w), 2 * (i * k + j * w)],
+                     [2 * (i * j + k * w), 1 - 2 * (i * i + k * k), 2 * (j * k - i * w)],
+                     [2 * (i * k - j * w), 2 * (j * k + i * w), 1 - 2 * (i * i + j * j)]], dtype=np.float64)
+
+
+def test_reference_camera_unit_tests(host):
+    """The reference's three camera tests (src/common/mod.rs:103-164) as known answers for look_at_camera / make_camera —
+    the one reference-held check on the restated nalgebra arithmetic (Isometry3::look_at_rh(..).inverse(), Perspective3::new,
+    the glm screen_to_raster product).  Each assertion is taken over where it can hold for Camera::new AS WRITTEN
+    (mod.rs:33-62, the code render() runs); where the reference's expectation contradicts its own constructor the
+    arithmetic is spelled out and the constructor wins:
+      * test_camera_wold_to_screen (:118-140): camera-space position — taken over verbatim (epsilon 1e-6, relative).  Its
+        z_screen = (z - n) f / ((f - n) z) is the [0, 1] depth convention; nalgebra's Perspective3 (m22 = (f + n)/(n - f),
+        m23 = 2 f n/(n - f)) projects to [-1, 1]: ((f + n) z - 2 f n) / ((f - n) z).  Both are evaluated below; x = y = 0 holds.
+      * test_camera_screen_to_raster (:142-161) expects screen (1, 1) -> raster (640, 480) and (-1, -1) -> (0, 0), but
+        mod.rs:38-40 multiplies by scaling(1/2, -1/2, 1): y is flipped, (1, 1) -> (640, 0) and (-1, -1) -> (0, 480).
+        The x halves of both assertions hold and are checked; y follows the constructor.
+      * test_camera_raster_to_screen (:163-178) unprojects raster (640, 360) of a 640 x 480 film and expects the view
+        axis: written for a 1280 x 720 default resolution; at (320, 240) the same assertion (x = y = 0, z = -near-plane
+        distance of the unprojected point) holds and is checked."""
+    n, f = 0.01, 1000.0
+    eye = np.array([10.0, 10.0, 10.0])
+    cam = host.look_at_camera(eye, (0, 0, 0), (0, 1, 0), 90.0, 640, 480)
+    # cam_to_world.inverse() * origin
+    R, t = _quat_matrix(list(cam.rot)), np.array(list(cam.trans), dtype=np.float64)
+    p_cam = R.T @ (np.zeros(3) - t)
+    z = float(np.linalg.norm(eye))
+    assert np.allclose(p_cam, [0.0, 0.0, -z], rtol=1e-6, atol=1e-6)
+    # Perspective3::new(640/480, pi/2, 0.01, 1000): look_at_camera uses the same near plane and 10000 as far (the importer's
+    # values, common/importer/mitsuba.rs:698-703), so m00 / m11 are pinned here and the depth terms by formula below
+    m00, m11, m22, m23 = list(cam.persp)
+    assert abs(m11 - 1.0) < 1e-6 and abs(m00 - 0.75) < 1e-6
+    inv = -1.0 / p_cam[2]
+    assert abs(m00 * p_cam[0] * inv) < 1e-6 and abs(m11 * p_cam[1] * inv) < 1e-6  # screen x = y = 0
+    z_gl = ((f + n) * z - 2 * f * n) / ((f - n) * z)  # nalgebra (documented matrix)
+    z_01 = ((z - n) * f) / ((f - n) * z)              # what the reference's test writes down
+    assert abs(z_gl - z_01) > 1e-4                    # they cannot both hold: the reference's depth assertion is stale
+    # screen_to_raster = inverse of the raster_to_screen the kernels use
+    cam2 = host.look_at_camera((0, 0, 0), (1, 0, 0), (0, 1, 0), 90.0, 640, 480)
+    r2s = np.array(list(cam2.raster_to_screen), dtype=np.float64).reshape(4, 4)
+    s2r = np.linalg.inv(r2s)
+    a = s2r @ [1.0, 1.0, 0.5, 1.0]
+    b = s2r @ [-1.0, -1.0, 0.5, 1.0]
+    assert abs(a[0] - 640.0) < 1e-3 and abs(a[2] - 0.5) < 1e-6 and abs(b[0]) < 1e-3 and abs(b[2] - 0.5) < 1e-6  # as the reference asserts
+    assert abs(a[1]) < 1e-3 and abs(b[1] - 480.0) < 1e-3  # y per mod.rs:38-40 (flipped), not per the stale test
+    # unproject_point(raster_to_screen * centre): on the view axis, on the near plane
+    s = r2s @ [320.0, 240.0, 0.0, 1.0]
+    m00, m11, m22, m23 = list(cam2.persp)
+    k = m23 / (s[2] + m22)
+    p = np.array([s[0] * k / m00, s[1] * k / m11, -k])
+    assert abs(p[0]) < 1e-6 and abs(p[1]) < 1e-6 and p[2] < 0
 
 
 # ---- BVH ------------------------------------------------------------------------------------------------

@@ -423,13 +423,13 @@ def run_gpu(args):
         barrier()
         t0 = time.perf_counter()
         if mode == "threads":
-            m2 = gpu.MultiScene(flat, n_gpus)  # ptrs_multi_create: H2D of the whole flattened scene to every device
+            m2 = gpu.MultiScene(flat, n_gpus, device_tables=True)  # ptrs_multi_create: H2D of the flattened scene to every device
             t1 = time.perf_counter()
             m2.render_into(cam, integ.params, host_film.ctypes.data)  # render + reduce + D2H of the film
             t2 = t3 = time.perf_counter()
             m2.close()
         else:
-            sc2 = gpu.RenderScene(flat)  # ptrs_scene_create: H2D of the whole flattened scene
+            sc2 = gpu.RenderScene(flat, device_tables=True)  # ptrs_scene_create: H2D of the flattened scene; MIP pyramids / env distribution built on the device
             f2 = gpu.Film(W, H)
             t1 = time.perf_counter()
             integ.render(cam, sc2, f2, sample_stride=shard)
@@ -452,7 +452,7 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(e2e_local, op=dist.ReduceOp.MAX)
     e2e_value = paths_step / (float(e2e_local.item()) * 1e-3)
-    h2d = (int(flat.host_bytes) + C.sizeof(type(cam)) + C.sizeof(PtrsRenderParams)) * n_gpus
+    h2d = (int(flat.host_bytes_device_tables) + C.sizeof(type(cam)) + C.sizeof(PtrsRenderParams)) * n_gpus
     d2h = H * W * 16
 
     if rank != 0:

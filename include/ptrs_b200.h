@@ -120,7 +120,10 @@ typedef struct PtrsTexture {
 
 /* MIPMap pyramid as built by MIPMap::new (texture.rs:279-405), already resampled to powers of two
  * and box-filtered by the host.  Level l is `height[l]` rows of `width[l]` texels of `channels`
- * floats, row-major, starting at texels[level_offset[l]] (offset counted in floats). */
+ * floats, row-major, starting at texels[level_offset[l]] (offset counted in floats).
+ * A description may instead carry LEVEL 0 ONLY (n_levels == 1 for an image larger than one texel, both
+ * extents powers of two): ptrs_scene_create then builds the box-filtered levels on the device
+ * (texture.rs:345-405), bit-identical to the host's. */
 #define PTRS_MAX_MIP_LEVELS 16
 typedef struct PtrsMipMap {
   int32_t channels;
@@ -178,7 +181,10 @@ typedef struct PtrsLight {
 } PtrsLight;
 
 /* InfiniteAreaLight state: light.rs:321-399.  The Distribution2D (sampling.rs:185-230) is passed
- * exactly as the reference builds it: nv conditional rows of nu entries. */
+ * exactly as the reference builds it: nv conditional rows of nu entries.
+ * With all five array pointers NULL the library tabulates the density from the environment map and builds
+ * the distribution on the device (light.rs:372-387, sampling.rs:133-162, 185-209), bit-identical to the
+ * host's; nu / nv <= 0 then default to twice the map's resolution (light.rs:375-376). */
 typedef struct PtrsEnvLight {
   float light_to_world[16]; /* row-major 4x4, Projective3 */
   float world_to_light[16];
@@ -326,6 +332,12 @@ int32_t ptrs_scene_bvh_info(const PtrsScene* scene, uint32_t* n_nodes, float* de
  * unused, the two children of an interior node at offset and offset + 1); prim_order (optional, device-built trees
  * only) maps BVH primitive positions to the caller's primitive indices. */
 int32_t ptrs_scene_download_nodes(const PtrsScene* scene, PtrsBvhNode* nodes, uint32_t capacity, uint32_t* prim_order);
+/* The texture tables as the device holds them (pyramids completed by the library included): headers, pool size in
+ * floats, and — if `texels` is not NULL — the pool itself; and an env light's Distribution2D (any array may be NULL). */
+int32_t ptrs_scene_download_mipmaps(const PtrsScene* scene, PtrsMipMap* mipmaps, uint32_t capacity, uint64_t* n_texels,
+                                    float* texels, uint64_t texel_capacity);
+int32_t ptrs_scene_download_env(const PtrsScene* scene, int32_t env, int32_t* nu, int32_t* nv, float* cond_func,
+                                float* cond_cdf, float* cond_func_int, float* marg_cdf, float* marg_func_int);
 int32_t ptrs_scene_destroy(PtrsScene* scene);
 int32_t ptrs_scene_world_bound(const PtrsScene* scene, float out_min_max[6]); /* mod.rs:100-102 */
 uint64_t ptrs_scene_device_bytes(const PtrsScene* scene);

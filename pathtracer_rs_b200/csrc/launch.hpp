@@ -42,11 +42,10 @@ void launch_connect(cudaStream_t st, int sm, bool count, const DevScene& sc, con
 void launch_intersect(cudaStream_t st, int sm, bool any_hit, bool count, const DevScene& sc, const PtrsRay* rays, uint32_t n, PtrsHit* hits,
                       uint8_t* occluded, uint32_t* ticket, GlobalCounters* g, const uint32_t* prim_map);
 
-// k_sort.cu: ray reordering of an extend queue (see there)
-struct PathSlot;
-size_t queue_sort_temp_bytes(uint32_t cap);
-int sort_queue(cudaStream_t st, int sm, const PathSlot* slot, const int* q, const uint32_t* n_ptr, uint32_t m, const float world_bound[6], uint32_t* keys_a,
-               uint32_t* keys_b, int* q_sorted, void* temp, size_t temp_bytes, int begin_bit);
+// k_tables.cu: MIP pyramid levels, env-light density and Distribution1D rows built on the device
+void launch_mip_level(cudaStream_t st, const float* prev, int pw, int ph, int channels, int wrap, float* out, int sres, int tres);
+void launch_env_density(cudaStream_t st, const DevScene& sc, int mip, int nu, int nv, const float* row_sin, int mode, int il, float delta, float* func);
+void launch_row_cdf(cudaStream_t st, const float* func, int n, int rows, float* cdf, float* func_int);
 
 // k_bvh.cu
 int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vertex, const float* d_pos, float4** nodes_out, uint32_t* n_nodes_out,

@@ -20,6 +20,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -101,6 +102,22 @@ int32_t nccl_fail(const char* what, ncclResult_t r) {
     if (e__ != cudaSuccess) return set_error(PTRS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
   } while (0)
 
+// Communicators are per device LIST and live as long as the process: creating one costs hundreds of milliseconds and the
+// first collective on it another second or so (NCCL connects lazily), which a host that re-creates its scene for every
+// frame must not pay per frame.  `busy` serialises the collectives of handles that share an entry.
+struct CommSet {
+  std::vector<ncclComm_t> comm;
+  std::mutex busy;
+};
+struct CommCache {
+  std::mutex mu;
+  std::map<std::vector<int>, std::unique_ptr<CommSet>> sets;
+};
+CommCache& comm_cache() {
+  static CommCache* c = new CommCache();  // intentionally not destroyed: NCCL may already be unloading at exit
+  return *c;
+}
+
 struct DeviceScope {  // the calling thread's current device is restored on exit
   int prev = -1;
   explicit DeviceScope(int dev) {
@@ -126,13 +143,12 @@ struct PtrsMultiScene {
   std::vector<PtrsScene*> scene;
   std::vector<PtrsFilm*> film;
   std::vector<cudaStream_t> stream;
-  std::vector<ncclComm_t> comm;  // empty when n == 1
+  CommSet* comms = nullptr;  // null when n == 1; owned by the process-wide cache
   int film_w = 0, film_h = 0;
   ~PtrsMultiScene() {
     for (int g = 0; g < n; ++g) {
       DeviceScope on(device[g]);
       if (g < (int)stream.size() && stream[g]) cudaStreamSynchronize(stream[g]);
-      if (g < (int)comm.size() && comm[g]) nccl().CommDestroy(comm[g]);
       if (g < (int)film.size() && film[g]) ptrs_film_destroy(film[g]);
       if (g < (int)scene.size() && scene[g]) ptrs_scene_destroy(scene[g]);
       if (g < (int)stream.size() && stream[g]) cudaStreamDestroy(stream[g]);
@@ -206,8 +222,16 @@ int32_t ptrs_multi_create(const PtrsSceneDesc* desc, int32_t n_devices, const in
   });
   if (r != PTRS_OK) return r;
   if (n_devices > 1) {
-    m->comm.assign(n_devices, nullptr);
-    NCCL_TRY(nccl().CommInitAll(m->comm.data(), n_devices, m->device.data()));
+    CommCache& cache = comm_cache();
+    std::lock_guard<std::mutex> lock(cache.mu);
+    std::unique_ptr<CommSet>& slot = cache.sets[m->device];
+    if (!slot) {
+      std::unique_ptr<CommSet> cs(new CommSet());
+      cs->comm.assign(n_devices, nullptr);
+      NCCL_TRY(nccl().CommInitAll(cs->comm.data(), n_devices, m->device.data()));
+      slot = std::move(cs);
+    }
+    m->comms = slot.get();
   }
   *out = m.release();
   return PTRS_OK;
@@ -264,9 +288,10 @@ int32_t ptrs_multi_render(PtrsMultiScene* multi, const PtrsCamera* camera, const
     // every device's render has been enqueued and joined: the reduce of all devices goes out as one NCCL group from
     // this thread (the single-thread multi-device pattern), each part ordered on its device's stream
     const size_t count = (size_t)m.film_w * m.film_h * 4;
+    std::lock_guard<std::mutex> one_collective_at_a_time(m.comms->busy);
     NCCL_TRY(nccl().GroupStart());
     for (int g = 0; g < m.n; ++g) {
-      const ncclResult_t nr = nccl().Reduce(m.film[g]->d, m.film[g]->d, count, ncclFloat32, ncclSum, 0, m.comm[g], m.stream[g]);
+      const ncclResult_t nr = nccl().Reduce(m.film[g]->d, m.film[g]->d, count, ncclFloat32, ncclSum, 0, m.comms->comm[g], m.stream[g]);
       if (nr != ncclSuccess) {
         nccl().GroupEnd();
         return nccl_fail("ncclReduce", nr);

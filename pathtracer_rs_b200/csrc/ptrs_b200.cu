@@ -176,12 +176,6 @@ struct Workspace {
   DevBuf<NeeRes> nee_res;
   DevBuf<int> q_ext[2], q_nee, q_class;
   DevBuf<uint32_t> q_ray;
-  // ray reordering (k_sort.cu): sorted copy of an extend queue, key double buffer, cub's scratch; and the queue
-  // lengths the previous batch saw per round (the host's estimate of how much there is to sort)
-  DevBuf<int> q_sorted;
-  DevBuf<uint32_t> sort_keys[2];
-  DevBuf<unsigned char> sort_temp;
-  std::vector<uint32_t> prev_len;
   DevBuf<RoundCounters> counters;
   DevBuf<GlobalCounters> gcount;
   PathArrays arrays() {
@@ -195,7 +189,7 @@ struct Workspace {
     return a;
   }
   uint64_t bytes() const {
-    return (uint64_t)cap * (sizeof(PathSlot) + 16 + sizeof(NeeRec) + sizeof(NeeRes) + 4 * 8 + (4 + 16) * PT_N_CLASSES) + (uint64_t)rounds * sizeof(RoundCounters) + sort_temp.n;
+    return (uint64_t)cap * (sizeof(PathSlot) + 16 + sizeof(NeeRec) + sizeof(NeeRes) + 4 * 5 + (4 + 16) * PT_N_CLASSES) + (uint64_t)rounds * sizeof(RoundCounters);
   }
 };
 
@@ -227,13 +221,12 @@ struct PtrsScene {
   DevBuf<GlobalCounters> gcount;
   float world_bound[6] = {0, 0, 0, 0, 0, 0};
   uint64_t scene_bytes = 0;
+  uint64_t n_texels = 0;                  // floats in the device texel pool
+  std::vector<PtrsMipMap> host_mipmaps;   // the headers as the device holds them (pyramids completed)
+  std::vector<DevEnv> host_envs;          // device pointers of the env tables, for ptrs_scene_download_env
   Workspace ws;
   PtrsStats stats{};
   bool count_visits = false;
-  // ray reordering between bounces (k_sort.cu); PTRS_SORT_RAYS=0 switches it off, PTRS_SORT_MIN / PTRS_SORT_BEGIN_BIT tune it
-  bool sort_rays = true;
-  uint32_t sort_min = 1u << 20;
-  int sort_begin_bit = 0;
   bool has_mat[PTRS_MAT_COUNT] = {false, false, false, false, false, false};
   int sm_count = 148;
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -347,11 +340,6 @@ int32_t ensure_workspace(PtrsScene* s, uint32_t cap, uint32_t rounds) {
   WS_ALLOC(w.q_nee, cap);
   WS_ALLOC(w.q_ray, (size_t)cap * 2);
   WS_ALLOC(w.q_class, (size_t)cap * PT_N_CLASSES);
-  WS_ALLOC(w.q_sorted, cap);
-  WS_ALLOC(w.sort_keys[0], cap);
-  WS_ALLOC(w.sort_keys[1], cap);
-  WS_ALLOC(w.sort_temp, queue_sort_temp_bytes(cap));
-  w.prev_len.clear();
   WS_ALLOC(w.counters, rounds + 1);
   WS_ALLOC(w.gcount, 1);
 #undef WS_ALLOC
@@ -465,22 +453,6 @@ int32_t run_batch(PtrsScene* s, const RenderConst& rc, bool exact_shading, uint6
       int* q_in = w.q_ext[round & 1].p;
       int* q_out = w.q_ext[(round + 1) & 1].p;
       tm.begin(ST_EXTEND);
-      // Ray reordering (k_sort.cu): from the second round on the queue is in append order, i.e. scattered over the
-      // scene.  How long it is is only known on the device; the previous batch of this render (same pixels, next
-      // sample numbers) had nearly the same lengths, the first batch falls back to "everything is still alive" for the
-      // rounds before Russian roulette starts.  Not worth it for short queues.
-      if (s->sort_rays && round >= 1) {
-        uint32_t est = 0;
-        if (round < w.prev_len.size()) est = (uint32_t)std::min<uint64_t>(n_work, (uint64_t)w.prev_len[round] + w.prev_len[round] / 32 + 1024);
-        else if (w.prev_len.empty() && (int)round <= rc.rr_start_depth + 1) est = n_work;
-        if (est >= s->sort_min) {
-          const int se = sort_queue(st, sm, P.slot, q_in, &c->n_ext, est, s->world_bound, w.sort_keys[0].p, w.sort_keys[1].p, w.q_sorted.p, w.sort_temp.p,
-                                    w.sort_temp.n, s->sort_begin_bit);
-          if (se != (int)cudaSuccess) return fail(PTRS_ERR_CUDA, std::string("queue sort: ") + cudaGetErrorString((cudaError_t)se));
-          q_in = w.q_sorted.p;
-          s->stats.launches += 5;  // key kernel + cub's histogram and 4 onesweep passes
-        }
-      }
       launch_extend(st, sm, s->count_visits, s->dev, P, q_in, w.q_class.p, cap, c, w.gcount.p);
       s->stats.extend_launches += 1;
       tm.end();
@@ -521,8 +493,6 @@ int32_t run_batch(PtrsScene* s, const RenderConst& rc, bool exact_shading, uint6
     if (host_ctr[round].n_ext == 0 || round >= w.rounds) break;  // only null-BSDF chains need extra rounds
   }
   for (uint32_t r = 0; r < round; ++r) *ext_rays += host_ctr[r].n_ext;
-  w.prev_len.resize(round);
-  for (uint32_t r = 0; r < round; ++r) w.prev_len[r] = host_ctr[r].n_ext;
   if (host_ctr[round].n_ext != 0) return fail(PTRS_ERR_UNSUPPORTED, "paths still alive after the maximum number of wavefront rounds");
   return PTRS_OK;
 }
@@ -731,18 +701,72 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
   if (d->uv) CUDA_TRY(s->uv.upload(d->uv, (size_t)d->n_verts * 2));
   CUDA_TRY(s->materials.upload(d->materials, d->n_materials));
   CUDA_TRY(s->textures.upload(d->textures, d->n_textures));
-  CUDA_TRY(s->mipmaps.upload(d->mipmaps, d->n_mipmaps));
-  CUDA_TRY(s->texels.upload(d->texels, d->n_texels));
+  {
+    // MIP pyramids.  A PtrsMipMap that carries level 0 only (n_levels == 1 for an image larger than one texel) gets the
+    // rest of its pyramid built here, on the device (k_tables.cu; MIPMap::new, texture.rs:345-405).
+    std::vector<PtrsMipMap> mips(d->mipmaps, d->mipmaps + d->n_mipmaps);
+    std::vector<int> have(d->n_mipmaps, 0);
+    bool build_any = false;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < d->n_mipmaps; ++i) {
+      PtrsMipMap& m = mips[i];
+      have[i] = m.n_levels;
+      int want = 1;
+      for (int e = std::max(m.width[0], m.height[0]); e > 1; e >>= 1) ++want;  // 1 + log2_int(max extent), texture.rs:345
+      if (m.n_levels == 1 && want > 1) {
+        if ((m.width[0] & (m.width[0] - 1)) || (m.height[0] & (m.height[0] - 1)))
+          return fail(PTRS_ERR_UNSUPPORTED, "level 0 of a pyramid to be completed on the device must be a power of two in both axes (the Lanczos resample of MIPMap::new stays with the host)");
+        if (want > PTRS_MAX_MIP_LEVELS) return fail(PTRS_ERR_INVALID_ARGUMENT, "MIP pyramid too deep");
+        build_any = true;
+        m.n_levels = want;
+        for (int l = 1; l < want; ++l) {
+          m.width[l] = std::max(1, m.width[l - 1] / 2);
+          m.height[l] = std::max(1, m.height[l - 1] / 2);
+        }
+      }
+      for (int l = 0; l < m.n_levels; ++l) total += (uint64_t)m.width[l] * m.height[l] * m.channels;
+    }
+    if (!build_any) {
+      CUDA_TRY(s->mipmaps.upload(d->mipmaps, d->n_mipmaps));
+      CUDA_TRY(s->texels.upload(d->texels, d->n_texels));
+    } else {
+      DevBuf<float> in_pool;
+      CUDA_TRY(in_pool.upload(d->texels, d->n_texels));
+      CUDA_TRY(s->texels.alloc(total));
+      uint64_t at = 0;
+      for (uint32_t i = 0; i < d->n_mipmaps; ++i) {
+        PtrsMipMap& m = mips[i];
+        for (int l = 0; l < m.n_levels; ++l) {
+          const uint64_t n = (uint64_t)m.width[l] * m.height[l] * m.channels;
+          if (l < have[i]) CUDA_TRY(cudaMemcpyAsync(s->texels.p + at, in_pool.p + d->mipmaps[i].level_offset[l], n * 4, cudaMemcpyDeviceToDevice, 0));
+          else launch_mip_level(0, s->texels.p + m.level_offset[l - 1], m.width[l - 1], m.height[l - 1], m.channels, m.wrap, s->texels.p + at, m.width[l], m.height[l]);
+          m.level_offset[l] = at;
+          at += n;
+        }
+      }
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(s->mipmaps.upload(mips.data(), mips.size()));
+      CUDA_TRY(cudaStreamSynchronize(0));  // in_pool is released when this scope ends
+    }
+    s->n_texels = build_any ? total : d->n_texels;
+    s->host_mipmaps = mips;
+  }
   CUDA_TRY(s->infinite_lights.upload(d->infinite_lights, d->n_infinite_lights));
   {
     std::vector<DevEnv> envs(d->n_envs);
     s->env_arrays.resize((size_t)d->n_envs * 5);
     s->env_guides.resize((size_t)d->n_envs * 2);
     for (uint32_t i = 0; i < d->n_envs; ++i) {
-      const PtrsEnvLight& e = d->envs[i];
-      if (e.nu <= 0 || e.nv <= 0 || !e.cond_func || !e.cond_cdf || !e.cond_func_int || !e.marg_func || !e.marg_cdf || e.mip < 0 ||
-          (uint32_t)e.mip >= d->n_mipmaps)
+      PtrsEnvLight e = d->envs[i];
+      if (e.mip < 0 || (uint32_t)e.mip >= d->n_mipmaps) return fail(PTRS_ERR_INVALID_ARGUMENT, "incomplete env light");
+      const bool build_dist = !e.cond_func && !e.cond_cdf && !e.cond_func_int && !e.marg_func && !e.marg_cdf;
+      if (build_dist && (e.nu <= 0 || e.nv <= 0)) {  // light.rs:375-376: twice the map's resolution
+        e.nu = 2 * s->host_mipmaps[e.mip].width[0];
+        e.nv = 2 * s->host_mipmaps[e.mip].height[0];
+      }
+      if (e.nu <= 0 || e.nv <= 0 || (!build_dist && (!e.cond_func || !e.cond_cdf || !e.cond_func_int || !e.marg_func || !e.marg_cdf)))
         return fail(PTRS_ERR_INVALID_ARGUMENT, "incomplete env light");
+      if ((uint64_t)e.nu * (uint64_t)e.nv > 0x7fffffffull) return fail(PTRS_ERR_UNSUPPORTED, "env distribution too large");
       DevEnv& o = envs[i];
       std::memcpy(o.light_to_world, e.light_to_world, 64);
       std::memcpy(o.world_to_light, e.world_to_light, 64);
@@ -751,11 +775,52 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
       o.nv = e.nv;
       o.marg_func_int = e.marg_func_int;
       DevBuf<float>* a = &s->env_arrays[(size_t)i * 5];
-      CUDA_TRY(a[0].upload(e.cond_func, (size_t)e.nu * e.nv));
-      CUDA_TRY(a[1].upload(e.cond_cdf, (size_t)(e.nu + 1) * e.nv));
-      CUDA_TRY(a[2].upload(e.cond_func_int, e.nv));
-      CUDA_TRY(a[3].upload(e.marg_func, e.nv));
-      CUDA_TRY(a[4].upload(e.marg_cdf, (size_t)e.nv + 1));
+      if (!build_dist) {
+        CUDA_TRY(a[0].upload(e.cond_func, (size_t)e.nu * e.nv));
+        CUDA_TRY(a[1].upload(e.cond_cdf, (size_t)(e.nu + 1) * e.nv));
+        CUDA_TRY(a[2].upload(e.cond_func_int, e.nv));
+        CUDA_TRY(a[3].upload(e.marg_func, e.nv));
+        CUDA_TRY(a[4].upload(e.marg_cdf, (size_t)e.nv + 1));
+      } else {
+        // InfiniteAreaLight::new's density and Distribution2D::new on the device (k_tables.cu).  The two libm values of
+        // the host path are evaluated here, by the same glibc: sin(pi v') per row and log2 of the filter width.
+        if (s->host_mipmaps[e.mip].channels != 3) return fail(PTRS_ERR_INVALID_ARGUMENT, "environment map must be a Spectrum MIPMap");
+        CUDA_TRY(a[0].alloc((size_t)e.nu * e.nv));
+        CUDA_TRY(a[1].alloc((size_t)(e.nu + 1) * e.nv));
+        CUDA_TRY(a[2].alloc(e.nv));
+        CUDA_TRY(a[4].alloc((size_t)e.nv + 1));
+        std::vector<float> row_sin((size_t)e.nv);
+        for (int vv = 0; vv < e.nv; ++vv) {
+          const float vp = ((float)vv + 0.5f) / (float)e.nv;
+          row_sin[vv] = std::sin(3.14159265358979323846f * vp);
+        }
+        DevBuf<float> d_sin, d_int;
+        CUDA_TRY(d_sin.upload(row_sin.data(), row_sin.size()));
+        CUDA_TRY(d_int.alloc(1));
+        const float f_width = 0.5f / (float)std::min(e.nu, e.nv);
+        const int n_lv = s->host_mipmaps[e.mip].n_levels;
+        const float level = (float)n_lv - 1.0f + std::log2(std::fmax(f_width, 1e-8f));  // texture.rs:448-449
+        int mode = 2, il = 0;
+        float delta = 0.f;
+        if (level < 0.0f) mode = 0;
+        else if (level >= (float)(n_lv - 1)) mode = 1;
+        else {
+          const float fl = std::floor(level);
+          il = (int)fl;
+          delta = level - fl;
+        }
+        DevScene tmp{};
+        tmp.texels = s->texels.p;
+        tmp.mipmaps = s->mipmaps.p;
+        launch_env_density(0, tmp, e.mip, e.nu, e.nv, d_sin.p, mode, il, delta, a[0].p);
+        launch_row_cdf(0, a[0].p, e.nu, e.nv, a[1].p, a[2].p);
+        launch_row_cdf(0, a[2].p, e.nv, 1, a[4].p, d_int.p);  // marginal: Distribution1D over the row integrals
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpy(&o.marg_func_int, d_int.p, 4, cudaMemcpyDeviceToHost));
+        // marg_func is the row-integral array itself (sampling.rs:196-203): a second device copy keeps ownership simple
+        CUDA_TRY(a[3].alloc(e.nv));
+        CUDA_TRY(cudaMemcpy(a[3].p, a[2].p, (size_t)e.nv * 4, cudaMemcpyDeviceToDevice));
+      }
       o.cond_func = a[0].p;
       o.cond_cdf = a[1].p;
       o.cond_func_int = a[2].p;
@@ -779,6 +844,7 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
       s->scene_bytes += ((size_t)e.nu * e.nv * 2 + e.nv * 4 + 1) * 4;
     }
     CUDA_TRY(s->envs.upload(envs.data(), envs.size()));
+    s->host_envs = envs;
     if (d->n_envs > 0) CUDA_TRY(cudaDeviceSynchronize());  // guide tables built
   }
   CUDA_TRY(s->sobol.upload(sh.matrices, (size_t)sh.n_dims * sh.n_cols));
@@ -807,9 +873,6 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
   v.n_infinite_lights = d->n_infinite_lights;
   v.box_min = n_dev_nodes <= 4096u ? 12u : 20u;
   if (const char* e = std::getenv("PTRS_BOX_MIN")) v.box_min = (uint32_t)std::max(1, std::min(32, std::atoi(e)));  // tuning only
-  if (const char* e = std::getenv("PTRS_SORT_RAYS")) s->sort_rays = std::atoi(e) != 0;
-  if (const char* e = std::getenv("PTRS_SORT_MIN")) s->sort_min = (uint32_t)std::max(1, std::atoi(e));
-  if (const char* e = std::getenv("PTRS_SORT_BEGIN_BIT")) s->sort_begin_bit = std::max(0, std::min(24, std::atoi(e)));
   v.uses_differentials = 0;
   for (uint32_t i = 0; i < d->n_materials; ++i) {
     static const int n_tex[PTRS_MAT_COUNT] = {1, 0, 3, 5, 4, 4};
@@ -824,7 +887,7 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
     std::memcpy(s->world_bound + 3, d->nodes[0].bounds_max, 12);
   }
   s->scene_bytes += (uint64_t)d->n_prims * 64 + (uint64_t)d->n_verts * 4 * ((d->normal ? 3 : 0) + (d->tangent ? 3 : 0) + (d->uv ? 2 : 0)) +
-                    d->n_texels * 4 + (uint64_t)sh.n_dims * sh.n_cols * 4;
+                    s->n_texels * 4 + (uint64_t)sh.n_dims * sh.n_cols * 4;
   CUDA_TRY(cudaEventCreate(&s->ev[0]));
   CUDA_TRY(cudaEventCreate(&s->ev[1]));
   CUDA_TRY(cudaDeviceSynchronize());
@@ -850,6 +913,36 @@ int32_t ptrs_scene_download_nodes(const PtrsScene* scene, PtrsBvhNode* nodes, ui
     if (!scene->prim_map.p) return fail(PTRS_ERR_INVALID_ARGUMENT, "the scene keeps the caller's primitive order (host-built BVH)");
     CUDA_TRY(cudaMemcpy(prim_order, scene->prim_map.p, scene->prim_map.n * 4, cudaMemcpyDeviceToHost));
   }
+  return PTRS_OK;
+}
+
+int32_t ptrs_scene_download_mipmaps(const PtrsScene* scene, PtrsMipMap* mipmaps, uint32_t capacity, uint64_t* n_texels, float* texels, uint64_t texel_capacity) {
+  if (!scene) return fail(PTRS_ERR_INVALID_ARGUMENT, "null argument");
+  ON_DEVICE_OF(scene);
+  if (n_texels) *n_texels = scene->n_texels;
+  if (mipmaps) {
+    if (capacity < scene->host_mipmaps.size()) return fail(PTRS_ERR_INVALID_ARGUMENT, "mipmap capacity too small");
+    std::memcpy(mipmaps, scene->host_mipmaps.data(), scene->host_mipmaps.size() * sizeof(PtrsMipMap));
+  }
+  if (texels) {
+    if (texel_capacity < scene->n_texels) return fail(PTRS_ERR_INVALID_ARGUMENT, "texel capacity too small");
+    CUDA_TRY(cudaMemcpy(texels, scene->texels.p, scene->n_texels * 4, cudaMemcpyDeviceToHost));
+  }
+  return PTRS_OK;
+}
+
+int32_t ptrs_scene_download_env(const PtrsScene* scene, int32_t env, int32_t* nu, int32_t* nv, float* cond_func, float* cond_cdf, float* cond_func_int,
+                                float* marg_cdf, float* marg_func_int) {
+  if (!scene || env < 0 || (size_t)env >= scene->host_envs.size()) return fail(PTRS_ERR_INVALID_ARGUMENT, "env index out of range");
+  ON_DEVICE_OF(scene);
+  const DevEnv& e = scene->host_envs[env];
+  if (nu) *nu = e.nu;
+  if (nv) *nv = e.nv;
+  if (cond_func) CUDA_TRY(cudaMemcpy(cond_func, e.cond_func, (size_t)e.nu * e.nv * 4, cudaMemcpyDeviceToHost));
+  if (cond_cdf) CUDA_TRY(cudaMemcpy(cond_cdf, e.cond_cdf, (size_t)(e.nu + 1) * e.nv * 4, cudaMemcpyDeviceToHost));
+  if (cond_func_int) CUDA_TRY(cudaMemcpy(cond_func_int, e.cond_func_int, (size_t)e.nv * 4, cudaMemcpyDeviceToHost));
+  if (marg_cdf) CUDA_TRY(cudaMemcpy(marg_cdf, e.marg_cdf, ((size_t)e.nv + 1) * 4, cudaMemcpyDeviceToHost));
+  if (marg_func_int) *marg_func_int = e.marg_func_int;
   return PTRS_OK;
 }
 
@@ -1113,7 +1206,6 @@ static int32_t render_impl(PtrsScene* s, const PtrsCamera* cam, const PtrsRender
   }
   StageTimer tm{s, st};
   float ms[ST_COUNT] = {};
-  s->ws.prev_len.clear();  // queue-length estimates are per render
   uint64_t ext_rays = 0, paths = 0;
   CUDA_TRY(cudaEventRecord(s->ev[0], st));
   // equal batches (whole 8x4 blocks) rather than full ones and a remainder: a nearly empty last batch would

@@ -32,7 +32,7 @@ EXPORTS = [
     "ptrs_scene_bvh_info", "ptrs_scene_download_nodes", "ptrs_read_bandwidth", "ptrs_gather_bandwidth",
     "ptrs_multi_create", "ptrs_multi_destroy", "ptrs_multi_device_count", "ptrs_multi_render", "ptrs_multi_root_film", "ptrs_multi_scene",
     "ptrs_comm_unique_id", "ptrs_comm_init_rank", "ptrs_comm_destroy", "ptrs_comm_info", "ptrs_film_reduce",
-    "ptrs_bxdf_eval", "ptrs_bxdf_sample", "ptrs_light_sample", "ptrs_light_pdf",
+    "ptrs_bxdf_eval", "ptrs_bxdf_sample", "ptrs_light_sample", "ptrs_light_pdf", "ptrs_scene_download_mipmaps", "ptrs_scene_download_env",
 ]
 
 
@@ -61,6 +61,8 @@ def lib():
         L.ptrs_scene_bvh_info.argtypes = [vp, C.POINTER(C.c_uint32), fp]
         L.ptrs_scene_download_nodes.argtypes = [vp, C.POINTER(PtrsBvhNode), C.c_uint32, C.POINTER(C.c_uint32)]
         L.ptrs_scene_destroy.argtypes = [vp]
+        L.ptrs_scene_download_mipmaps.argtypes = [vp, C.POINTER(PtrsMipMap), C.c_uint32, u64p, fp, C.c_uint64]
+        L.ptrs_scene_download_env.argtypes = [vp, i32, i32p, i32p, fp, fp, fp, fp, fp]
         L.ptrs_scene_world_bound.argtypes = [vp, fp]
         L.ptrs_scene_device_bytes.restype = C.c_uint64
         L.ptrs_scene_device_bytes.argtypes = [vp]
@@ -197,9 +199,10 @@ class Film:
 class RenderScene:
     """Device copy of a flattened scene (src/pathtracer/mod.rs:84-106)."""
 
-    def __init__(self, flat, device_bvh=False):
-        """device_bvh=True ignores the description's nodes and builds a linear BVH on the GPU (ptrs_scene_create_device_bvh)."""
-        desc = flat.desc if isinstance(flat, FlatScene) else flat
+    def __init__(self, flat, device_bvh=False, device_tables=False):
+        """device_bvh=True ignores the description's nodes and builds a linear BVH on the GPU (ptrs_scene_create_device_bvh);
+        device_tables=True hands over level 0 of every MIP pyramid only and no env Distribution2D: the library builds them."""
+        desc = (flat.desc_device_tables if device_tables else flat.desc) if isinstance(flat, FlatScene) else flat
         h = C.c_void_p()
         _check((lib().ptrs_scene_create_device_bvh if device_bvh else lib().ptrs_scene_create)(desc, C.byref(h)))
         self._h = h
@@ -222,6 +225,27 @@ class RenderScene:
         order = np.empty(self.n_prims, dtype=np.uint32) if self.device_bvh else None
         _check(lib().ptrs_scene_download_nodes(self._h, _p(nodes, PtrsBvhNode), n, _p(order, C.c_uint32) if self.device_bvh else None))
         return nodes, order
+
+    def download_mipmaps(self):
+        """(list of PtrsMipMap headers, texel pool) as the device holds them."""
+        n = C.c_uint64(0)
+        _check(lib().ptrs_scene_download_mipmaps(self._h, None, 0, C.byref(n), None, 0))
+        cap = 4096
+        hdr = (PtrsMipMap * cap)()
+        pool = np.empty(n.value, dtype=np.float32)
+        _check(lib().ptrs_scene_download_mipmaps(self._h, hdr, cap, C.byref(n), _p(pool, C.c_float), n.value))
+        return hdr, pool
+
+    def download_env(self, env):
+        """Distribution2D of env light `env` as the device holds it: dict of cond_func, cond_cdf, cond_func_int, marg_cdf, marg_func_int."""
+        nu, nv, mi = C.c_int32(0), C.c_int32(0), C.c_float(0)
+        _check(lib().ptrs_scene_download_env(self._h, env, C.byref(nu), C.byref(nv), None, None, None, None, None))
+        f = np.empty((nv.value, nu.value), dtype=np.float32)
+        c = np.empty((nv.value, nu.value + 1), dtype=np.float32)
+        fi = np.empty(nv.value, dtype=np.float32)
+        mc = np.empty(nv.value + 1, dtype=np.float32)
+        _check(lib().ptrs_scene_download_env(self._h, env, C.byref(nu), C.byref(nv), _p(f, C.c_float), _p(c, C.c_float), _p(fi, C.c_float), _p(mc, C.c_float), C.byref(mi)))
+        return {"cond_func": f, "cond_cdf": c, "cond_func_int": fi, "marg_cdf": mc, "marg_func_int": mi.value}
 
     def close(self):
         if getattr(self, "_h", None):
@@ -327,8 +351,8 @@ class Comm:
 class MultiScene:
     """Scene replicas on several devices of this process + the films they reduce into (ptrs_multi_*)."""
 
-    def __init__(self, flat, n_devices, devices=None, device_bvh=False):
-        desc = flat.desc if isinstance(flat, FlatScene) else flat
+    def __init__(self, flat, n_devices, devices=None, device_bvh=False, device_tables=False):
+        desc = (flat.desc_device_tables if device_tables else flat.desc) if isinstance(flat, FlatScene) else flat
         h = C.c_void_p()
         dv = (C.c_int32 * n_devices)(*devices) if devices is not None else None
         _check(lib().ptrs_multi_create(desc, n_devices, dv, 1 if device_bvh else 0, C.byref(h)))

@@ -45,6 +45,10 @@ def lib():
         L.ptrs_host_scene_desc.argtypes = [vp]
         L.ptrs_host_scene_bytes.restype = u64
         L.ptrs_host_scene_bytes.argtypes = [vp]
+        L.ptrs_host_scene_desc_device_tables.restype = C.POINTER(PtrsSceneDesc)
+        L.ptrs_host_scene_desc_device_tables.argtypes = [vp]
+        L.ptrs_host_scene_bytes_device_tables.restype = u64
+        L.ptrs_host_scene_bytes_device_tables.argtypes = [vp]
         L.ptrs_host_scene_bvh_depth.argtypes = [vp]
         L.ptrs_host_scene_bvh_seconds.restype = C.c_double
         L.ptrs_host_scene_bvh_seconds.argtypes = [vp]
@@ -131,6 +135,16 @@ class FlatScene:
     @property
     def host_bytes(self):
         return lib().ptrs_host_scene_bytes(self._h)
+
+    @property
+    def desc_device_tables(self):
+        """The same scene without the tables the device library builds itself: level-0-only MIP pyramids and env lights
+        without Distribution2D arrays (ptrs_scene_create completes them on the device)."""
+        return lib().ptrs_host_scene_desc_device_tables(self._h)
+
+    @property
+    def host_bytes_device_tables(self):
+        return lib().ptrs_host_scene_bytes_device_tables(self._h)
 
     @property
     def bvh_depth(self):

@@ -18,6 +18,7 @@ thread_local std::string g_err;
 struct SceneBox {
   FlatScene fs;
   PtrsSceneDesc desc;
+  PtrsSceneDesc slim;
 };
 template <class F>
 int guard(F&& f) {
@@ -121,6 +122,13 @@ void* ptrs_host_finalize(void* b, int max_prims_in_node, int n_threads) {
 }
 void ptrs_host_scene_free(void* s) { delete (SceneBox*)s; }
 const PtrsSceneDesc* ptrs_host_scene_desc(void* s) { return &((SceneBox*)s)->desc; }
+// the same scene without the tables the device library builds itself (level-0-only pyramids, no Distribution2D arrays)
+const PtrsSceneDesc* ptrs_host_scene_desc_device_tables(void* s) {
+  SceneBox* b = (SceneBox*)s;
+  b->slim = b->fs.desc_device_tables();
+  return &b->slim;
+}
+uint64_t ptrs_host_scene_bytes_device_tables(void* s) { return ((SceneBox*)s)->fs.host_bytes_device_tables(); }
 uint64_t ptrs_host_scene_bytes(void* s) { return ((SceneBox*)s)->fs.host_bytes(); }
 int ptrs_host_scene_bvh_depth(void* s) { return ((SceneBox*)s)->fs.bvh_max_depth; }
 double ptrs_host_scene_bvh_seconds(void* s) { return ((SceneBox*)s)->fs.bvh_build_seconds; }

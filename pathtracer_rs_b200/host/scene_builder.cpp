@@ -587,6 +587,45 @@ PtrsSceneDesc FlatScene::desc() const {
   return d;
 }
 
+PtrsSceneDesc FlatScene::desc_device_tables() const {
+  PtrsSceneDesc d = desc();
+  if (slim_mipmaps.size() != mipmaps.size()) {
+    slim_mipmaps.clear();
+    slim_texels.clear();
+    for (const PtrsMipMap& m : mipmaps) {
+      PtrsMipMap o{};
+      o.channels = m.channels;
+      o.wrap = m.wrap;
+      o.n_levels = 1;
+      o.width[0] = m.width[0];
+      o.height[0] = m.height[0];
+      o.level_offset[0] = slim_texels.size();
+      const size_t n = (size_t)m.width[0] * m.height[0] * m.channels;
+      slim_texels.insert(slim_texels.end(), texels.begin() + m.level_offset[0], texels.begin() + m.level_offset[0] + n);
+      slim_mipmaps.push_back(o);
+    }
+  }
+  slim_envs = envs;
+  for (PtrsEnvLight& e : slim_envs) {
+    e.cond_func = e.cond_cdf = e.cond_func_int = e.marg_func = e.marg_cdf = nullptr;
+    e.marg_func_int = 0.f;
+  }
+  d.mipmaps = slim_mipmaps.data();
+  d.n_texels = slim_texels.size();
+  d.texels = slim_texels.data();
+  d.envs = slim_envs.data();
+  return d;
+}
+
+uint64_t FlatScene::host_bytes_device_tables() const {
+  uint64_t b = host_bytes();
+  desc_device_tables();
+  b -= (texels.size() - slim_texels.size()) * 4;
+  for (const auto& d : env_dists)
+    b -= (d.cond_func.size() + d.cond_cdf.size() + d.cond_func_int.size() + d.marg_func.size() + d.marg_cdf.size()) * 4;
+  return b;
+}
+
 uint64_t FlatScene::host_bytes() const {
   uint64_t b = nodes.size() * sizeof(PtrsBvhNode) + prim_vertex.size() * 4 + prim_mesh.size() * 12 +
                (pos.size() + normal.size() + tangent.size() + uv.size() + texels.size()) * 4 +

@@ -68,7 +68,15 @@ struct FlatScene {
   double bvh_build_seconds = 0.0;
 
   PtrsSceneDesc desc() const;  // pointers into this object; valid while it is alive and unmoved
+  // The same scene with the tables the device library can build itself left out (include/ptrs_b200.h): every MIP
+  // pyramid carries level 0 only and the env lights carry no Distribution2D arrays.
+  PtrsSceneDesc desc_device_tables() const;
   uint64_t host_bytes() const;
+  uint64_t host_bytes_device_tables() const;
+  // storage behind desc_device_tables()
+  mutable std::vector<PtrsMipMap> slim_mipmaps;
+  mutable std::vector<float> slim_texels;
+  mutable std::vector<PtrsEnvLight> slim_envs;
 };
 
 class SceneBuilder {

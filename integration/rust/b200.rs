@@ -4,10 +4,14 @@
 //!   * `PathIntegrator::render(&self, &Camera, &RenderScene)`      src/pathtracer/integrator.rs:536
 //!   * `RenderScene::{intersect, intersect_p}`                     src/pathtracer/mod.rs:92-98
 //!   * the unused `OptixAccelerator::new(&RenderScene)` hook       src/pathtracer/gpu/optix.rs:160
-//! The one intrusive change is `BVH::export_flat` (accelerator.rs keeps `nodes` / `primitives` private).
-//! This file is written against the reference's types and has NOT been compiled: the pathtracer-b200 image has
-//! no Rust toolchain.  `ffi.rs` next to it is generated from include/ptrs_b200.h.
+//! The intrusive part is small and additive: read-only exporters on the reference's own types
+//! (`reference_additions.rs`: `BVH::export_flat`, `Texture::export`, `Material::export`, `Light::export`, a few
+//! accessors), because accelerator.rs, primitive.rs, shape.rs, texture.rs, material/*.rs and light.rs keep the fields
+//! private.  `tables.rs` interns meshes / materials / textures / lights into the flat pools; `ffi.rs` is generated from
+//! include/ptrs_b200.h.  Written against the reference's types and NOT compiled: the pathtracer-b200 image has no Rust
+//! toolchain; `examples/c_abi_shim.c` fills a PtrsSceneDesc the same way from plain C and runs in the GPU tests.
 use super::ffi;
+use super::tables::Tables;
 use crate::common::{film::Film, Camera};
 use crate::pathtracer::{accelerator::LinearBVHNode, RenderScene};
 use std::ffi::CStr;
@@ -54,19 +58,76 @@ impl FlatScene {
     /// the layout of `PtrsBvhNode` (accelerator.rs:83-95) — and the primitives in `BVH::primitives` order.
     pub fn from_render_scene(scene: &RenderScene) -> Self {
         let mut flat = FlatScene::default();
-        let (nodes, prims) = scene.scene.export_flat();
+        let (nodes, prims) = scene.bvh().export_flat(); // reference_additions.rs
         flat.nodes = nodes.iter().map(node_to_ffi).collect();
-        let mut tables = crate::pathtracer::gpu::tables::Tables::new(&scene.meshes, &scene.lights);
-        for prim in prims {
-            let tri = prim.shape();
+        let mut tables = Tables::new(&scene.meshes, &scene.lights, &scene.infinite_lights);
+        for (i, prim) in prims.iter().enumerate() {
+            let tri = prim.get_shape();
             let base = tables.vertex_base(tri.mesh());
-            flat.prim_vertex.extend(tri.indices().iter().map(|i| base + *i));
+            flat.prim_vertex.extend(tri.indices().iter().map(|v| base + *v));
             flat.prim_mesh.push(tables.mesh_id(tri.mesh()));
-            flat.prim_material.push(tables.material_id(prim.material()));
-            flat.prim_area_light.push(prim.area_light().map_or(-1, |l| tables.light_id(l)));
+            flat.prim_material.push(tables.material_id(prim.get_material_arc()));
+            flat.prim_area_light.push(prim.get_area_light().map_or(-1, |l| tables.light_id(l)));
+            if prim.get_area_light().is_some() {
+                tables.note_prim(tri, i);
+            }
         }
         tables.write_pools(&mut flat); // pos / normal / s / uv, materials, textures + MIP pyramids, lights, envs
         flat
+    }
+
+    /// InfiniteAreaLight (light.rs:321-399): the transforms, the map's pyramid and the Distribution2D exactly as the
+    /// reference built them (sampling.rs:185-209).  Leaving the five arrays empty instead makes the library build the
+    /// distribution on the device (include/ptrs_b200.h, PtrsEnvLight).
+    pub fn push_env(
+        &mut self,
+        tables: &mut Tables,
+        light_to_world: &na::Projective3<f32>,
+        world_to_light: &na::Projective3<f32>,
+        l_map: &crate::pathtracer::texture::MIPMap<crate::common::spectrum::Spectrum>,
+        distribution: &crate::pathtracer::sampling::Distribution2D,
+    ) -> i32 {
+        let row_major = |m: &na::Projective3<f32>| {
+            let mut o = [0f32; 16];
+            for r in 0..4 {
+                for c in 0..4 {
+                    o[4 * r + c] = m.matrix()[(r, c)];
+                }
+            }
+            o
+        };
+        let (rows, marginal) = distribution.parts();
+        let (marg_func, marg_cdf, marg_func_int) = marginal.parts();
+        let nv = rows.len();
+        let nu = rows[0].parts().0.len();
+        let mut cond_func = Vec::with_capacity(nu * nv);
+        let mut cond_cdf = Vec::with_capacity((nu + 1) * nv);
+        let mut cond_func_int = Vec::with_capacity(nv);
+        for row in rows {
+            let (f, c, fi) = row.parts();
+            cond_func.extend_from_slice(f);
+            cond_cdf.extend_from_slice(c);
+            cond_func_int.push(fi);
+        }
+        let base = self.env_arrays.len();
+        self.env_arrays.extend([cond_func, cond_cdf, cond_func_int, marg_func.to_vec(), marg_cdf.to_vec()]);
+        let a = &self.env_arrays[base..];
+        self.envs.push(ffi::PtrsEnvLight {
+            light_to_world: row_major(light_to_world),
+            world_to_light: row_major(world_to_light),
+            mip: tables.push_env_mip(l_map),
+            nu: nu as i32,
+            nv: nv as i32,
+            pad: 0,
+            cond_func: a[0].as_ptr(),
+            cond_cdf: a[1].as_ptr(),
+            cond_func_int: a[2].as_ptr(),
+            marg_func: a[3].as_ptr(),
+            marg_cdf: a[4].as_ptr(),
+            marg_func_int,
+            pad2: 0.0,
+        });
+        self.envs.len() as i32 - 1
     }
 
     pub fn desc(&self) -> ffi::PtrsSceneDesc {

@@ -156,6 +156,16 @@ __global__ void __launch_bounds__(256) radix_tree_kernel(const uint64_t* __restr
 
 #define PT_BVH_MAX_LEAF 4u  // BVH::new(.., &4), importer/mitsuba.rs:362
 
+__device__ __forceinline__ float box_area(float4 mn, float4 mx) {
+  const float dx = mx.x - mn.x, dy = mx.y - mn.y, dz = mx.z - mn.z;
+  return 2.0f * (dx * dy + dy * dz + dz * dx);
+}
+
+// Bottom-up pass over the radix tree: boxes, and which subtrees become leaves.  A subtree of at most PT_BVH_MAX_LEAF
+// primitives whose two halves are leaves themselves collapses into ONE leaf only if that is not more expensive than
+// keeping the split, by the reference builder's own criterion (accelerator.rs:240-254: leaf iff
+// 1 + (n0 A0 + n1 A1) / A >= n): a Morton split that separates two clusters of triangles stays a node instead of
+// becoming a 4-triangle leaf whose box is mostly empty.
 __global__ void __launch_bounds__(256) refit_kernel(uint32_t n, BuildArrays A) {
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const uint32_t prim = A.perm[j];
@@ -164,7 +174,8 @@ __global__ void __launch_bounds__(256) refit_kernel(uint32_t n, BuildArrays A) {
     A.box[node] = NodeBox{mn, mx};
     if (n == 1) return;
     uint32_t p = A.leaf_parent[j];
-    uint32_t ni_self = 0;  // emitted interior nodes below (and including) `node`
+    uint32_t ni_self = 0;   // emitted interior nodes below (and including) `node`
+    uint32_t cnt_self = 1;  // primitives below `node`
     for (;;) {
       __threadfence();
       TreeNode* pn = A.node + p;
@@ -174,16 +185,22 @@ __global__ void __launch_bounds__(256) refit_kernel(uint32_t n, BuildArrays A) {
       const uint4 w1 = __ldcg(reinterpret_cast<const uint4*>(pn) + 1);  // last, arrivals, n_interior, pad
       const uint32_t other = w0.x == node ? w0.y : w0.x;
       const float4 omn = __ldcg(&A.box[other].mn), omx = __ldcg(&A.box[other].mx);
+      const float a_self = box_area(mn, mx), a_other = box_area(omn, omx);
       mn = make_float4(fminf(mn.x, omn.x), fminf(mn.y, omn.y), fminf(mn.z, omn.z), 0.f);
       mx = make_float4(fmaxf(mx.x, omx.x), fmaxf(mx.y, omx.y), fmaxf(mx.z, omx.z), 0.f);
       A.box[p] = NodeBox{mn, mx};
-      uint32_t ni = 0;
-      if (w1.x - w0.w + 1u > PT_BVH_MAX_LEAF) {
-        ni = 1u + ni_self;
-        if (other < n - 1) ni += __ldcg(&A.node[other].n_interior);
+      const uint32_t count = w1.x - w0.w + 1u;
+      const uint32_t ni_other = other < n - 1 ? __ldcg(&A.node[other].n_interior) : 0u;
+      bool leaf = count <= PT_BVH_MAX_LEAF && ni_self == 0u && ni_other == 0u;
+      if (leaf) {
+        const float a = box_area(mn, mx);
+        const float cost = 1.0f + ((float)cnt_self * a_self + (float)(count - cnt_self) * a_other) / a;
+        leaf = !(cost < (float)count);  // also a leaf when the box has no area (cost is NaN or inf)
       }
+      const uint32_t ni = leaf ? 0u : 1u + ni_self + ni_other;
       pn->n_interior = ni;
       ni_self = ni;
+      cnt_self = count;
       node = p;
       p = w0.z;
       if (p == 0xffffffffu) break;

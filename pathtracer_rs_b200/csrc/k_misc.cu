@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256, PT_RESOLVE_MIN_BLOCKS) connect_resolve_ke
     if ((nf & PT_NEE_SHADOW) && !res.occluded) ld = ld + sp(rec->n0.w, rec->n1.w, rec->n2.w);
     const float4 n5 = rec->n5;
     if (nf & PT_NEE_MIS) {
-      const int light_idx = (int)(nf & 0x3fffffffu);
+      const int light_idx = (int)(nf & PT_NEE_LIGHT_MASK);
       const V3 md = mk3(n3);
       Spec li = sp(0.0f);
       if (res.prim >= 0) {

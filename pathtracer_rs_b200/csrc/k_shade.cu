@@ -51,7 +51,7 @@ PT_DEV void nee_prepare(const DevScene& sc, const SurfInter& si, const Bsdf& bsd
       if (go) {
         spawn_ray(si.g, wi2, &mo);
         md = wi2;
-        nf |= PT_NEE_MIS;
+        nf |= PT_NEE_MIS | (light.type == PTRS_LIGHT_INFINITE ? PT_NEE_MIS_ANY : 0u);
       }
     }
   }

@@ -79,7 +79,7 @@ struct ConnectWork {
       r->o = mk3(n23.a);
       r->d = mk3(n23.b);
       r->t_max = CUDART_INF_F;
-      r->any_hit = false;
+      r->any_hit = (__float_as_uint(n23.b.w) & PT_NEE_MIS_ANY) != 0;  // infinite light: only "does it escape" matters
       ++n_mis;
     } else {
       const F8 n01 = ld256(reinterpret_cast<const F8*>(&P.nee[rec].n0));

@@ -604,6 +604,7 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
     const int32_t li = d->infinite_lights[i];
     if (li < 0 || (uint32_t)li >= d->n_lights || d->lights[li].type != PTRS_LIGHT_INFINITE) return fail(PTRS_ERR_INVALID_ARGUMENT, "infinite_lights names something that is not an infinite light");
   }
+  if (d->n_lights > PT_NEE_LIGHT_MASK) return fail(PTRS_ERR_UNSUPPORTED, "more than 2^29 lights");  // the light id shares a word with flags in the direct-lighting record
   for (uint32_t i = 0; i < d->n_lights; ++i) {
     const PtrsLight& l = d->lights[i];
     if (l.type < 0 || l.type > PTRS_LIGHT_INFINITE) return fail(PTRS_ERR_UNSUPPORTED, "unknown light type");

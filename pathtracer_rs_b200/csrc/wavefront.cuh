@@ -81,6 +81,13 @@ struct PathArrays {
 #define PT_F_HAS_DIFF (1u << 17)
 #define PT_NEE_SHADOW (1u << 30)
 #define PT_NEE_MIS (1u << 31)
+// The MIS ray of an INFINITE light only asks whether it escapes: estimate_direct (integrator.rs:113-135) adds
+// light.le(ray) when scene.intersect finds nothing and, when it finds something, compares the hit primitive's area light
+// with the sampled light — which an infinite light never is.  scene.intersect(ray) and scene.intersect_p(ray) agree on
+// "something is hit" (same triangle test; the closest-hit path's extra rejection of degenerate partials is unreachable,
+// a zero-area triangle fails det != 0 first), so such a ray is traced as an any-hit ray and stops at the first hit.
+#define PT_NEE_MIS_ANY (1u << 29)
+#define PT_NEE_LIGHT_MASK 0x1fffffffu
 PT_DEV uint32_t pack_state(uint32_t dim_and_flags, int bounces) { return (dim_and_flags & 0x00ffffffu) | ((uint32_t)(bounces & 0xff) << 24); }
 PT_DEV int packed_bounces(uint32_t packed) { return (int)(int8_t)(packed >> 24); }
 PT_DEV uint32_t pack_pixel(int x, int y) { return ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16); }

@@ -32,6 +32,11 @@ def _worker(rank, world, port, out_path):
     params.sample_stride, params.sample_phase = sample_shard(rank, world)
     film, st = oracle.render(flat, cam, params, n_threads=1)
     t = torch.from_numpy(film)
+    # the communicator id travels from rank 0 to every rank through the process group (what bench.py does under torchrun)
+    from pathtracer_rs_b200.dist import exchange_comm_id
+
+    uid = exchange_comm_id(lambda: bytes(range(128)), rank, world)
+    assert uid == bytes(range(128))
     reduce_film(t, dst=0)
     paths = torch.tensor([st["camera_paths"]], dtype=torch.int64)
     dist.reduce(paths, dst=0)
@@ -53,6 +58,35 @@ def test_two_rank_sample_sharding_sums_to_the_full_render(tmp_path, host, oracle
     full, st = oracle.render(flat, cam, params, n_threads=1)
     assert int(got["paths"][0]) == st["camera_paths"]
     assert np.allclose(got["film"], full, rtol=1e-5, atol=1e-6)
+
+
+def test_strong_scaling_plan_and_id_exchange_through_a_store():
+    from pathtracer_rs_b200.dist import exchange_comm_id, strong_scaling_plan
+
+    for spp, world in ((128, 8), (128, 3), (5, 8)):
+        plan = strong_scaling_plan(spp, world)
+        assert sum(n for _, _, n in plan) == spp and max(n for _, _, n in plan) - min(n for _, _, n in plan) <= 1
+        covered = sorted(s for stride, phase, _ in plan for s in range(phase, spp, stride))
+        assert covered == list(range(spp))  # every sample number exactly once
+
+    class Store(dict):
+        def set(self, k, v):
+            self[k] = v
+
+        def get(self, k):
+            return self[k]
+
+    store = Store()
+    made = []
+
+    def make():
+        made.append(1)
+        return b"\x07" * 128
+
+    assert exchange_comm_id(make, 0, 4, store) == b"\x07" * 128
+    assert all(exchange_comm_id(make, r, 4, store) == b"\x07" * 128 for r in (1, 2, 3))
+    assert len(made) == 1  # only rank 0 asks NCCL for an id
+    assert exchange_comm_id(make, 0, 1) == b"\x07" * 128  # a world of one needs no channel
 
 
 def test_reduce_film_is_a_noop_without_a_process_group():

@@ -266,6 +266,19 @@ PT_DEV void trace_empty(uint32_t n_items, uint32_t* ticket, Work& work) {
 #define PT_RB_KZ_SHIFT 3
 #define PT_RB_ANY 32u
 #define PT_RB_LIVE 64u
+#ifndef PT_PAIR_PARK
+#define PT_PAIR_PARK 1
+#endif
+#ifndef PT_DIRECT_FAR
+#define PT_DIRECT_FAR 1
+#endif
+#ifndef PT_PARK_EARLY
+#define PT_PARK_EARLY 1
+#endif
+// parked pair of sibling leaves, in pl_cnt: bit 31 pair, bit 30 right leaf first, bits 23..29 triangles of both,
+// bits 16..22 triangles of the left leaf, bits 0..15 triangles left to test (as for a single parked leaf)
+#define PT_PL_PAIR 0x80000000u
+#define PT_PL_SWAPPED 0x40000000u
 template <class Work>
 PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, Work& work) {
   if (sc.n_nodes == 0) {
@@ -281,7 +294,10 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
   // node in hand (its box test passed under the t_max current at that time): offset, meta, entry distance
   uint32_t cur_off = 0, cur_meta = PT_NO_NODE;
   float cur_t = 0.f;
-  uint32_t pl_off = 0, pl_cnt = 0;  // parked leaf: next primitive, triangles left (0 = none)
+  uint32_t pl_off = 0, pl_cnt = 0;  // parked leaf: next primitive, triangles left (0 = none); or a pair of sibling leaves (PT_PL_*)
+#if PT_PAIR_PARK
+  float pl_tfar = 0.f;              // pair: the far leaf's entry distance
+#endif
   uint32_t rbits = 0;               // PT_RB_*
   bool exhausted = n_items == 0;
   uint32_t item = 0;
@@ -380,18 +396,56 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
             const bool gn = neg ? gr : gl, gf = neg ? gl : gr;
             const float tn = neg ? tr : tl, tf = neg ? tl : tr;
             const float4 nb = neg ? R.b : L.b, fb = neg ? L.b : R.b;
-            if (gf && tf < t_max) {
-              if (sp_ < PT_STACK_SIZE) {  // always true: ptrs_scene_create refuses trees deeper than the stack
-                stack[sp_] = make_uint4(__float_as_uint(tf), __float_as_uint(fb.z), __float_as_uint(fb.w), 0u);
-                ++sp_;
-              }
-            }
-            if (gn && tn < t_max) {
-              cur_t = tn;
-              cur_off = __float_as_uint(nb.z);
-              cur_meta = __float_as_uint(nb.w);
-            } else {
+            const bool an = gn && tn < t_max, af = gf && tf < t_max;
+#if PT_PAIR_PARK
+            // Both children are leaves and both are entered (the usual case at the bottom of an SAH tree, where leaves
+            // hold one or two triangles): the reference tests the near leaf's triangles, then pops the far leaf — it is
+            // on top of the stack —, repeats its box test against the possibly smaller t_max and tests its triangles.
+            // The two leaves are parked as ONE unit that keeps the far leaf's entry distance for that re-test; sibling
+            // leaves cover one contiguous primitive range [l_off, l_off + l_cnt + r_cnt), walked from its middle when
+            // the right leaf is the near one.  No push, no pop, and the lane stays free to descend elsewhere.
+            const uint32_t l_off = __float_as_uint(L.b.z), l_cnt = __float_as_uint(L.b.w) & 0xffffu;
+            const uint32_t r_off = __float_as_uint(R.b.z), r_cnt = __float_as_uint(R.b.w) & 0xffffu;
+            if (an && af && l_cnt != 0u && r_cnt != 0u && pl_cnt == 0u && r_off == l_off + l_cnt && l_cnt + r_cnt <= 127u) {
+              pl_off = l_off;
+              pl_cnt = PT_PL_PAIR | (neg ? PT_PL_SWAPPED : 0u) | ((l_cnt + r_cnt) << 23) | (l_cnt << 16) | (l_cnt + r_cnt);
+              pl_tfar = tf;
               cur_meta = PT_NO_NODE;
+            } else
+#endif
+            {
+#if PT_DIRECT_FAR
+              // near child rejected, far child entered: the reference pushes the far child and pops it straight away; the
+              // pop's re-test against t_max is what the node in hand gets anyway whenever a hit shrinks t_max
+              if (af && !an) {
+                cur_t = tf;
+                cur_off = __float_as_uint(fb.z);
+                cur_meta = __float_as_uint(fb.w);
+              } else
+#endif
+              {
+                if (af) {
+                  if (sp_ < PT_STACK_SIZE) {  // always true: ptrs_scene_create refuses trees deeper than the stack
+                    stack[sp_] = make_uint4(__float_as_uint(tf), __float_as_uint(fb.z), __float_as_uint(fb.w), 0u);
+                    ++sp_;
+                  }
+                }
+                if (an) {
+                  cur_t = tn;
+                  cur_off = __float_as_uint(nb.z);
+                  cur_meta = __float_as_uint(nb.w);
+                } else {
+                  cur_meta = PT_NO_NODE;
+                }
+              }
+#if PT_PARK_EARLY
+              // the node now in hand is a leaf and the parking slot is free: park it here instead of in the next iteration
+              if (cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0u && pl_cnt == 0u) {
+                pl_off = cur_off;
+                pl_cnt = cur_meta & 0xffffu;
+                cur_meta = PT_NO_NODE;
+              }
+#endif
             }
           }
         }
@@ -409,31 +463,52 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
       const bool has = live && pl_cnt != 0;
       if (__ballot_sync(FULL, has) == 0) break;
       if (has) {
-        const uint32_t prim = pl_off;
-        const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim);
-        const float4 v1 = __ldg(sc.tri_verts + 3 * (size_t)prim + 1);
-        const float4 v2 = __ldg(sc.tri_verts + 3 * (size_t)prim + 2);
-        ++pl_off;
-        --pl_cnt;
-        RayPre rp;
-        rp.kz = (int)((rbits >> PT_RB_KZ_SHIFT) & 3u);
-        rp.sx = sx;
-        rp.sy = sy;
-        rp.sz = sz;
-        float t, b0, b1, b2;
-        if (tri_core(mk3(v0), mk3(v1), mk3(v2), o, rp, t_max, &t, &b0, &b1, &b2) &&
-            !tri_post_reject(sc, (int)prim, mk3(v0), mk3(v1), mk3(v2), __float_as_uint(v2.w), b0, b1, b2, !(rbits & PT_RB_ANY))) {
-          hit_prim = (int)prim;
-          hit_b0 = b0;
-          hit_b1 = b1;
-          hit_b2 = b2;
-          t_max = t;
-          if (rbits & PT_RB_ANY) {  // intersect_p returns at the first hit (accelerator.rs:435-442)
+        uint32_t prim = pl_off;
+        bool culled = false;
+#if PT_PAIR_PARK
+        if (pl_cnt & PT_PL_PAIR) {  // a pair of sibling leaves: near leaf's triangles, far leaf's box re-test, far leaf's triangles
+          const uint32_t total = (pl_cnt >> 23) & 127u, cl = (pl_cnt >> 16) & 127u;
+          const bool sw = (pl_cnt & PT_PL_SWAPPED) != 0;
+          const uint32_t pos = total - (pl_cnt & 0xffffu);
+          if (pos == (sw ? total - cl : cl) && !(pl_tfar < t_max)) {  // the far leaf fails the box test of its pop
+            culled = true;
             pl_cnt = 0;
-            sp_ = 0;
-            cur_meta = PT_NO_NODE;
-          } else if (cur_meta != PT_NO_NODE && !(cur_t < t_max)) {
-            cur_meta = PT_NO_NODE;  // the node in hand was accepted under the old t_max: re-validate
+          } else {
+            uint32_t idx = sw ? pos + cl : pos;
+            if (idx >= total) idx -= total;
+            prim = pl_off + idx;
+          }
+        } else
+#endif
+        {
+          ++pl_off;
+        }
+        if (!culled) {
+          const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim);
+          const float4 v1 = __ldg(sc.tri_verts + 3 * (size_t)prim + 1);
+          const float4 v2 = __ldg(sc.tri_verts + 3 * (size_t)prim + 2);
+          --pl_cnt;
+          if ((pl_cnt & 0xffffu) == 0u) pl_cnt = 0u;
+          RayPre rp;
+          rp.kz = (int)((rbits >> PT_RB_KZ_SHIFT) & 3u);
+          rp.sx = sx;
+          rp.sy = sy;
+          rp.sz = sz;
+          float t, b0, b1, b2;
+          if (tri_core(mk3(v0), mk3(v1), mk3(v2), o, rp, t_max, &t, &b0, &b1, &b2) &&
+              !tri_post_reject(sc, (int)prim, mk3(v0), mk3(v1), mk3(v2), __float_as_uint(v2.w), b0, b1, b2, !(rbits & PT_RB_ANY))) {
+            hit_prim = (int)prim;
+            hit_b0 = b0;
+            hit_b1 = b1;
+            hit_b2 = b2;
+            t_max = t;
+            if (rbits & PT_RB_ANY) {  // intersect_p returns at the first hit (accelerator.rs:435-442)
+              pl_cnt = 0;
+              sp_ = 0;
+              cur_meta = PT_NO_NODE;
+            } else if (cur_meta != PT_NO_NODE && !(cur_t < t_max)) {
+              cur_meta = PT_NO_NODE;  // the node in hand was accepted under the old t_max: re-validate
+            }
           }
         }
       }

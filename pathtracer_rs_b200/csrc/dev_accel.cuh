@@ -266,19 +266,14 @@ PT_DEV void trace_empty(uint32_t n_items, uint32_t* ticket, Work& work) {
 #define PT_RB_KZ_SHIFT 3
 #define PT_RB_ANY 32u
 #define PT_RB_LIVE 64u
-#ifndef PT_PAIR_PARK
-#define PT_PAIR_PARK 1
+// box steps per scheduling decision (measured on B200, round 2: 1 -> 3 steps takes 3 % off the traversal kernels on every
+// scene; 4 is level with 3)
+#ifndef PT_BOX_STEPS
+#define PT_BOX_STEPS 3
 #endif
-#ifndef PT_DIRECT_FAR
-#define PT_DIRECT_FAR 1
+#ifndef PT_TRI_STEPS
+#define PT_TRI_STEPS 1
 #endif
-#ifndef PT_PARK_EARLY
-#define PT_PARK_EARLY 1
-#endif
-// parked pair of sibling leaves, in pl_cnt: bit 31 pair, bit 30 right leaf first, bits 23..29 triangles of both,
-// bits 16..22 triangles of the left leaf, bits 0..15 triangles left to test (as for a single parked leaf)
-#define PT_PL_PAIR 0x80000000u
-#define PT_PL_SWAPPED 0x40000000u
 template <class Work>
 PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, Work& work) {
   if (sc.n_nodes == 0) {
@@ -289,15 +284,13 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
   // fewer lanes than this able to take a box step -> the warp turns to its parked leaves.  Scheduling only (results do
   // not depend on it); measured: 12 is best on trees of a few dozen nodes, 20 on trees of 10^5 .. 10^7 nodes.
   const int box_min = (int)sc.box_min;
+  const bool pop_twice = sc.pop_twice != 0;
   uint4 stack[PT_STACK_SIZE];
   int sp_ = 0;
   // node in hand (its box test passed under the t_max current at that time): offset, meta, entry distance
   uint32_t cur_off = 0, cur_meta = PT_NO_NODE;
   float cur_t = 0.f;
-  uint32_t pl_off = 0, pl_cnt = 0;  // parked leaf: next primitive, triangles left (0 = none); or a pair of sibling leaves (PT_PL_*)
-#if PT_PAIR_PARK
-  float pl_tfar = 0.f;              // pair: the far leaf's entry distance
-#endif
+  uint32_t pl_off = 0, pl_cnt = 0;  // parked leaf: next primitive, triangles left (0 = none)
   uint32_t rbits = 0;               // PT_RB_*
   bool exhausted = n_items == 0;
   uint32_t item = 0;
@@ -360,13 +353,10 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
     }
 
     // ---- box phase: pop / park / expand ----------------------------------------------------------------
-    for (;;) {
+    auto box_step = [&]() {
       const bool live = (rbits & PT_RB_LIVE) != 0;
       const bool cur_leaf = cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0;
       const bool can_box = live && ((cur_meta != PT_NO_NODE && !cur_leaf) || (cur_meta == PT_NO_NODE && sp_ > 0) || (cur_leaf && pl_cnt == 0));
-      const uint32_t bmask = __ballot_sync(FULL, can_box);
-      if (bmask == 0) break;
-      if (__popc(bmask) < box_min && __ballot_sync(FULL, live && !can_box) != 0) break;
       if (can_box) {
         if (cur_meta == PT_NO_NODE) {  // pop one entry; the reference's box test at pop time
           --sp_;
@@ -375,6 +365,25 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
             cur_t = __uint_as_float(e.x);
             cur_off = e.y;
             cur_meta = e.z;
+          }
+          if (pop_twice) {
+            // the entry was culled, or it was a leaf that goes straight to the free parking slot: one more pop (at most),
+            // so that the lane still has a node to expand in this iteration.  Pays on trees that do not fit in L1
+            // (scheduling only; DevScene::pop_twice)
+            if (cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0u && pl_cnt == 0u) {
+              pl_off = cur_off;
+              pl_cnt = cur_meta & 0xffffu;
+              cur_meta = PT_NO_NODE;
+            }
+            if (cur_meta == PT_NO_NODE && sp_ > 0) {
+              --sp_;
+              const uint4 e2 = stack[sp_];
+              if (__uint_as_float(e2.x) < t_max) {
+                cur_t = __uint_as_float(e2.x);
+                cur_off = e2.y;
+                cur_meta = e2.z;
+              }
+            }
           }
         }
         if (cur_meta != PT_NO_NODE) {
@@ -397,121 +406,93 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
             const float tn = neg ? tr : tl, tf = neg ? tl : tr;
             const float4 nb = neg ? R.b : L.b, fb = neg ? L.b : R.b;
             const bool an = gn && tn < t_max, af = gf && tf < t_max;
-#if PT_PAIR_PARK
-            // Both children are leaves and both are entered (the usual case at the bottom of an SAH tree, where leaves
-            // hold one or two triangles): the reference tests the near leaf's triangles, then pops the far leaf — it is
-            // on top of the stack —, repeats its box test against the possibly smaller t_max and tests its triangles.
-            // The two leaves are parked as ONE unit that keeps the far leaf's entry distance for that re-test; sibling
-            // leaves cover one contiguous primitive range [l_off, l_off + l_cnt + r_cnt), walked from its middle when
-            // the right leaf is the near one.  No push, no pop, and the lane stays free to descend elsewhere.
-            const uint32_t l_off = __float_as_uint(L.b.z), l_cnt = __float_as_uint(L.b.w) & 0xffffu;
-            const uint32_t r_off = __float_as_uint(R.b.z), r_cnt = __float_as_uint(R.b.w) & 0xffffu;
-            if (an && af && l_cnt != 0u && r_cnt != 0u && pl_cnt == 0u && r_off == l_off + l_cnt && l_cnt + r_cnt <= 127u) {
-              pl_off = l_off;
-              pl_cnt = PT_PL_PAIR | (neg ? PT_PL_SWAPPED : 0u) | ((l_cnt + r_cnt) << 23) | (l_cnt << 16) | (l_cnt + r_cnt);
-              pl_tfar = tf;
-              cur_meta = PT_NO_NODE;
-            } else
-#endif
-            {
-#if PT_DIRECT_FAR
+            if (af && !an) {
               // near child rejected, far child entered: the reference pushes the far child and pops it straight away; the
               // pop's re-test against t_max is what the node in hand gets anyway whenever a hit shrinks t_max
-              if (af && !an) {
-                cur_t = tf;
-                cur_off = __float_as_uint(fb.z);
-                cur_meta = __float_as_uint(fb.w);
-              } else
-#endif
-              {
-                if (af) {
-                  if (sp_ < PT_STACK_SIZE) {  // always true: ptrs_scene_create refuses trees deeper than the stack
-                    stack[sp_] = make_uint4(__float_as_uint(tf), __float_as_uint(fb.z), __float_as_uint(fb.w), 0u);
-                    ++sp_;
-                  }
-                }
-                if (an) {
-                  cur_t = tn;
-                  cur_off = __float_as_uint(nb.z);
-                  cur_meta = __float_as_uint(nb.w);
-                } else {
-                  cur_meta = PT_NO_NODE;
+              cur_t = tf;
+              cur_off = __float_as_uint(fb.z);
+              cur_meta = __float_as_uint(fb.w);
+            } else {
+              if (af) {
+                if (sp_ < PT_STACK_SIZE) {  // always true: ptrs_scene_create refuses trees deeper than the stack
+                  stack[sp_] = make_uint4(__float_as_uint(tf), __float_as_uint(fb.z), __float_as_uint(fb.w), 0u);
+                  ++sp_;
                 }
               }
-#if PT_PARK_EARLY
-              // the node now in hand is a leaf and the parking slot is free: park it here instead of in the next iteration
-              if (cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0u && pl_cnt == 0u) {
-                pl_off = cur_off;
-                pl_cnt = cur_meta & 0xffffu;
+              if (an) {
+                cur_t = tn;
+                cur_off = __float_as_uint(nb.z);
+                cur_meta = __float_as_uint(nb.w);
+              } else {
                 cur_meta = PT_NO_NODE;
               }
-#endif
+            }
+            // the node now in hand is a leaf and the parking slot is free: park it here instead of in the next iteration
+            if (cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0u && pl_cnt == 0u) {
+              pl_off = cur_off;
+              pl_cnt = cur_meta & 0xffffu;
+              cur_meta = PT_NO_NODE;
             }
           }
         }
       }
+    };
+    for (;;) {
+      const bool live = (rbits & PT_RB_LIVE) != 0;
+      const bool cur_leaf = cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0;
+      const bool can_box = live && ((cur_meta != PT_NO_NODE && !cur_leaf) || (cur_meta == PT_NO_NODE && sp_ > 0) || (cur_leaf && pl_cnt == 0));
+      const uint32_t bmask = __ballot_sync(FULL, can_box);
+      if (bmask == 0) break;
+      if (__popc(bmask) < box_min && __ballot_sync(FULL, live && !can_box) != 0) break;
+      // PT_BOX_STEPS steps under one scheduling decision: the ballots and the phase test are paid once per group of steps
+#pragma unroll
+      for (int rep = 0; rep < PT_BOX_STEPS; ++rep) box_step();
     }
 
     // ---- triangle phase: parked leaves, first in first out -----------------------------------------------
-    for (;;) {
+    auto tri_step = [&]() {
       const bool live = (rbits & PT_RB_LIVE) != 0;
       if (live && pl_cnt == 0 && cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0) {  // second leaf moves up
         pl_off = cur_off;
         pl_cnt = cur_meta & 0xffffu;
         cur_meta = PT_NO_NODE;
       }
-      const bool has = live && pl_cnt != 0;
-      if (__ballot_sync(FULL, has) == 0) break;
-      if (has) {
-        uint32_t prim = pl_off;
-        bool culled = false;
-#if PT_PAIR_PARK
-        if (pl_cnt & PT_PL_PAIR) {  // a pair of sibling leaves: near leaf's triangles, far leaf's box re-test, far leaf's triangles
-          const uint32_t total = (pl_cnt >> 23) & 127u, cl = (pl_cnt >> 16) & 127u;
-          const bool sw = (pl_cnt & PT_PL_SWAPPED) != 0;
-          const uint32_t pos = total - (pl_cnt & 0xffffu);
-          if (pos == (sw ? total - cl : cl) && !(pl_tfar < t_max)) {  // the far leaf fails the box test of its pop
-            culled = true;
+      if (live && pl_cnt != 0) {
+        const uint32_t prim = pl_off;
+        const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim);
+        const float4 v1 = __ldg(sc.tri_verts + 3 * (size_t)prim + 1);
+        const float4 v2 = __ldg(sc.tri_verts + 3 * (size_t)prim + 2);
+        ++pl_off;
+        --pl_cnt;
+        RayPre rp;
+        rp.kz = (int)((rbits >> PT_RB_KZ_SHIFT) & 3u);
+        rp.sx = sx;
+        rp.sy = sy;
+        rp.sz = sz;
+        float t, b0, b1, b2;
+        if (tri_core(mk3(v0), mk3(v1), mk3(v2), o, rp, t_max, &t, &b0, &b1, &b2) &&
+            !tri_post_reject(sc, (int)prim, mk3(v0), mk3(v1), mk3(v2), __float_as_uint(v2.w), b0, b1, b2, !(rbits & PT_RB_ANY))) {
+          hit_prim = (int)prim;
+          hit_b0 = b0;
+          hit_b1 = b1;
+          hit_b2 = b2;
+          t_max = t;
+          if (rbits & PT_RB_ANY) {  // intersect_p returns at the first hit (accelerator.rs:435-442)
             pl_cnt = 0;
-          } else {
-            uint32_t idx = sw ? pos + cl : pos;
-            if (idx >= total) idx -= total;
-            prim = pl_off + idx;
-          }
-        } else
-#endif
-        {
-          ++pl_off;
-        }
-        if (!culled) {
-          const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim);
-          const float4 v1 = __ldg(sc.tri_verts + 3 * (size_t)prim + 1);
-          const float4 v2 = __ldg(sc.tri_verts + 3 * (size_t)prim + 2);
-          --pl_cnt;
-          if ((pl_cnt & 0xffffu) == 0u) pl_cnt = 0u;
-          RayPre rp;
-          rp.kz = (int)((rbits >> PT_RB_KZ_SHIFT) & 3u);
-          rp.sx = sx;
-          rp.sy = sy;
-          rp.sz = sz;
-          float t, b0, b1, b2;
-          if (tri_core(mk3(v0), mk3(v1), mk3(v2), o, rp, t_max, &t, &b0, &b1, &b2) &&
-              !tri_post_reject(sc, (int)prim, mk3(v0), mk3(v1), mk3(v2), __float_as_uint(v2.w), b0, b1, b2, !(rbits & PT_RB_ANY))) {
-            hit_prim = (int)prim;
-            hit_b0 = b0;
-            hit_b1 = b1;
-            hit_b2 = b2;
-            t_max = t;
-            if (rbits & PT_RB_ANY) {  // intersect_p returns at the first hit (accelerator.rs:435-442)
-              pl_cnt = 0;
-              sp_ = 0;
-              cur_meta = PT_NO_NODE;
-            } else if (cur_meta != PT_NO_NODE && !(cur_t < t_max)) {
-              cur_meta = PT_NO_NODE;  // the node in hand was accepted under the old t_max: re-validate
-            }
+            sp_ = 0;
+            cur_meta = PT_NO_NODE;
+          } else if (cur_meta != PT_NO_NODE && !(cur_t < t_max)) {
+            cur_meta = PT_NO_NODE;  // the node in hand was accepted under the old t_max: re-validate
           }
         }
       }
+    };
+    for (;;) {
+      const bool live = (rbits & PT_RB_LIVE) != 0;
+      const bool has = live && (pl_cnt != 0 || (cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0));
+      if (__ballot_sync(FULL, has) == 0) break;
+#pragma unroll
+      for (int rep = 0; rep < PT_TRI_STEPS; ++rep) tri_step();
     }
 
     // ---- rays that ran out of nodes --------------------------------------------------------------------

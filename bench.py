@@ -166,7 +166,7 @@ def make_config(w, n_gpus):
     return {"workload": w["name"], "resolution": [W, H], "spp_total": w["spp"], "max_depth": w["max_depth"],
             "camera_paths_per_step": (W + 4) * (H + 4) * w["spp"],
             "sharding": f"sample number mod {n_gpus} per GPU, films summed by one NCCL reduce inside the timed region",
-            "l2": "inputs larger than L2 (5.5 GB of path state per wavefront batch) and a 256 MiB buffer written between timed iterations"}
+            "l2": "inputs larger than L2 (368 B of path state per path slot, wavefront batches of up to 2^27 slots = 49 GB) and a 256 MiB buffer written between timed iterations"}
 
 
 def run_reference(args):

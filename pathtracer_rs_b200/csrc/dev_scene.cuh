@@ -5,6 +5,8 @@
 //              mesh flags | alpha texture} as raw bits.  The 36 algorithmic bytes + 12 B of shading
 //              metadata that would otherwise be a second dependent load.
 //   tri_index  16 B per primitive: three global vertex indices + mesh id, only read by shading.
+//   tri_shade  64 B per primitive: the three shading normals and uvs of the triangle, gathered once at scene creation
+//              so that shading reads them with two 32-byte loads that depend on the primitive id alone.
 #pragma once
 #include "../../include/ptrs_b200.h"
 #include "dev_math.cuh"
@@ -34,6 +36,7 @@ struct DevScene {
   const float4* nodes;      // 2 per node
   const float4* tri_verts;  // 3 per prim
   const uint4* tri_index;   // 1 per prim
+  const float4* tri_shade;  // 4 per prim: shading normals n0 n1 n2 (9 floats), uvs (6 floats, the defaults of shape.rs:34-48 when the mesh has none), 1 spare
   const float* normal;
   const float* tangent;
   const float* uv;

@@ -119,7 +119,11 @@ __global__ void __launch_bounds__(PT_SHADE_BLOCK, PT_SHADE_MIN_BLOCKS) shade_ker
         prefetch_l1(&P.slot[p_next]);
         prefetch_l1(sc.tri_verts + 3 * (size_t)prim_next);
         prefetch_l1(sc.tri_verts + 3 * (size_t)prim_next + 2);
+#if PT_PACKED_SHADING
+        prefetch_l1(sc.tri_shade + 4 * (size_t)prim_next);
+#else
         prefetch_l1(sc.tri_index + prim_next);
+#endif
       }
       uint32_t flags = pr.packed & 0x00ffffffu;
       int bounces = packed_bounces(pr.packed);

@@ -113,8 +113,35 @@ __global__ void __launch_bounds__(256) row_normalise_kernel(int n, int rows, flo
   }
 }
 
+// per-triangle shading record (dev_scene.cuh tri_shade)
+__global__ void __launch_bounds__(256) pack_shading_kernel(uint32_t n, const float4* __restrict__ tri_verts, const uint4* __restrict__ tri_index,
+                                                           const float* __restrict__ normal, const float* __restrict__ uv, float4* __restrict__ out) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint32_t flags = __float_as_uint(tri_verts[3 * (size_t)k + 2].w) & 0xffu;
+    const uint4 idx = tri_index[k];
+    const uint32_t v[3] = {idx.x, idx.y, idx.z};
+    float r[16];
+    for (int j = 0; j < 16; ++j) r[j] = 0.f;
+    if ((flags & PTRS_MESH_HAS_NORMAL) && normal)
+      for (int j = 0; j < 3; ++j)
+        for (int c = 0; c < 3; ++c) r[3 * j + c] = normal[3 * (size_t)v[j] + c];
+    if ((flags & PTRS_MESH_HAS_UV) && uv) {
+      for (int j = 0; j < 3; ++j)
+        for (int c = 0; c < 2; ++c) r[9 + 2 * j + c] = uv[2 * (size_t)v[j] + c];
+    } else {  // shape.rs:34-48
+      r[9] = 0.f, r[10] = 0.f, r[11] = 1.f, r[12] = 0.f, r[13] = 1.f, r[14] = 1.f;
+    }
+    for (int j = 0; j < 4; ++j) out[4 * (size_t)k + j] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+  }
+}
+
 }  // namespace
 
+void launch_pack_shading(cudaStream_t st, uint32_t n, const float4* tri_verts, const uint4* tri_index, const float* normal, const float* uv, float4* out) {
+  if (n == 0) return;
+  const int grid = (int)std::min<uint32_t>((n + 255u) / 256u, 148u * 8u);
+  pack_shading_kernel<<<grid, 256, 0, st>>>(n, tri_verts, tri_index, normal, uv, out);
+}
 void launch_mip_level(cudaStream_t st, const float* prev, int pw, int ph, int channels, int wrap, float* out, int sres, int tres) {
   const uint32_t n = (uint32_t)sres * (uint32_t)tres;
   const int grid = (int)std::min<uint32_t>((n + 255u) / 256u, 148u * 8u);

@@ -44,6 +44,7 @@ void launch_intersect(cudaStream_t st, int sm, bool any_hit, bool count, const D
 
 // k_tables.cu: MIP pyramid levels, env-light density and Distribution1D rows built on the device
 void launch_mip_level(cudaStream_t st, const float* prev, int pw, int ph, int channels, int wrap, float* out, int sres, int tres);
+void launch_pack_shading(cudaStream_t st, uint32_t n, const float4* tri_verts, const uint4* tri_index, const float* normal, const float* uv, float4* out);
 void launch_env_density(cudaStream_t st, const DevScene& sc, int mip, int nu, int nv, const float* row_sin, int mode, int il, float delta, float* func);
 void launch_row_cdf(cudaStream_t st, const float* func, int n, int rows, float* cdf, float* func_int);
 

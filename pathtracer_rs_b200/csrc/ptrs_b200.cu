@@ -188,9 +188,8 @@ struct Workspace {
     a.q_ray = q_ray.p;
     return a;
   }
-  uint64_t bytes() const {
-    return (uint64_t)cap * (sizeof(PathSlot) + 16 + sizeof(NeeRec) + sizeof(NeeRes) + 4 * 5 + (4 + 16) * PT_N_CLASSES) + (uint64_t)rounds * sizeof(RoundCounters);
-  }
+  static constexpr uint64_t kBytesPerSlot = sizeof(PathSlot) + 16 + sizeof(NeeRec) + sizeof(NeeRes) + 4 * 5 + (4 + 16) * PT_N_CLASSES;  // 368
+  uint64_t bytes() const { return (uint64_t)cap * kBytesPerSlot + (uint64_t)rounds * sizeof(RoundCounters); }
 };
 
 }  // namespace
@@ -200,6 +199,7 @@ struct PtrsScene {
   DevScene dev{};
   DevBuf<float4> nodes, tri_verts;
   DevBuf<uint4> tri_index;
+  DevBuf<float4> tri_shade;
   DevBuf<uint32_t> prim_map;  // device-built BVH: BVH position -> caller's primitive index
   float bvh_build_ms = 0.f;
   uint32_t n_dev_nodes = 0;
@@ -222,6 +222,7 @@ struct PtrsScene {
   float world_bound[6] = {0, 0, 0, 0, 0, 0};
   uint64_t scene_bytes = 0;
   uint64_t n_texels = 0;                  // floats in the device texel pool
+  uint32_t default_cap = 0;               // wavefront batch size when the caller leaves it to the library (default_paths_per_batch)
   std::vector<PtrsMipMap> host_mipmaps;   // the headers as the device holds them (pyramids completed)
   std::vector<DevEnv> host_envs;          // device pointers of the env tables, for ptrs_scene_download_env
   Workspace ws;
@@ -700,6 +701,9 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
   if (d->normal) CUDA_TRY(s->normal.upload(d->normal, (size_t)d->n_verts * 3));
   if (d->tangent) CUDA_TRY(s->tangent.upload(d->tangent, (size_t)d->n_verts * 3));
   if (d->uv) CUDA_TRY(s->uv.upload(d->uv, (size_t)d->n_verts * 2));
+  CUDA_TRY(s->tri_shade.alloc((size_t)d->n_prims * 4));
+  launch_pack_shading(0, d->n_prims, s->tri_verts.p, s->tri_index.p, s->normal.p, s->uv.p, s->tri_shade.p);
+  CUDA_TRY(cudaGetLastError());
   CUDA_TRY(s->materials.upload(d->materials, d->n_materials));
   CUDA_TRY(s->textures.upload(d->textures, d->n_textures));
   {
@@ -855,6 +859,7 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
   v.nodes = s->nodes.p;
   v.tri_verts = s->tri_verts.p;
   v.tri_index = s->tri_index.p;
+  v.tri_shade = s->tri_shade.p;
   v.normal = s->normal.p;
   v.tangent = s->tangent.p;
   v.uv = s->uv.p;
@@ -889,7 +894,7 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
     std::memcpy(s->world_bound, d->nodes[0].bounds_min, 12);
     std::memcpy(s->world_bound + 3, d->nodes[0].bounds_max, 12);
   }
-  s->scene_bytes += (uint64_t)d->n_prims * 64 + (uint64_t)d->n_verts * 4 * ((d->normal ? 3 : 0) + (d->tangent ? 3 : 0) + (d->uv ? 2 : 0)) +
+  s->scene_bytes += (uint64_t)d->n_prims * 128 + (uint64_t)d->n_verts * 4 * ((d->normal ? 3 : 0) + (d->tangent ? 3 : 0) + (d->uv ? 2 : 0)) +
                     s->n_texels * 4 + (uint64_t)sh.n_dims * sh.n_cols * 4;
   CUDA_TRY(cudaEventCreate(&s->ev[0]));
   CUDA_TRY(cudaEventCreate(&s->ev[1]));
@@ -1180,6 +1185,24 @@ int32_t ptrs_render_params_default(PtrsRenderParams* p) {
   return PTRS_OK;
 }
 
+static uint32_t default_paths_per_batch(PtrsScene* s) {
+  if (const char* e = std::getenv("PTRS_PATHS_PER_BATCH")) {  // tuning override
+    const long long v = std::atoll(e);
+    if (v >= 32 && v <= (1ll << 30)) return (uint32_t)v;
+  }
+  if (s->default_cap == 0) {  // asked once per scene: cudaMemGetInfo is a slow call once the pools hold tens of GB
+    uint64_t want = 1ull << 27;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      // the workspace this scene already holds counts as available
+      const uint64_t avail = (uint64_t)free_b + s->ws.bytes();
+      while (want > (1ull << 20) && want * Workspace::kBytesPerSlot > avail / 3) want >>= 1;
+    }
+    s->default_cap = (uint32_t)want;
+  }
+  return s->default_cap;
+}
+
 static int32_t render_impl(PtrsScene* s, const PtrsCamera* cam, const PtrsRenderParams* rp, PtrsFilm* film, const int32_t* list_xy,
                            const int32_t* list_s, size_t n_list, float* out_rgb, cudaStream_t st) {
   RenderConst rc;
@@ -1189,7 +1212,11 @@ static int32_t render_impl(PtrsScene* s, const PtrsCamera* cam, const PtrsRender
   const uint32_t bw = ((uint32_t)rc.sb_ext[0] + 7u) >> 3, bh = ((uint32_t)rc.sb_ext[1] + 3u) >> 2;
   const uint64_t per_sample = (uint64_t)bw * bh * 32u;
   const uint64_t total = list_xy ? (uint64_t)n_list : per_sample * (uint64_t)rc.s_count;
-  uint32_t cap = rp->paths_per_batch > 0 ? (uint32_t)rp->paths_per_batch : (1u << 24);  // 16 Mi slots x 328 B = 5.5 GB of 180 GB HBM
+  // Wavefront batch size.  Every batch pays for its tail: the rounds after Russian roulette has thinned the paths out are
+  // latency-bound launches over nearly empty queues (on the 4K atrium ≈ 6.5 ms of an 89 ms batch of 16 Mi paths), so the
+  // default is as large as the memory allows — 128 Mi slots x 368 B = 49 GB of the 180 GB — and never more than a third of
+  // what is free on the device.
+  uint32_t cap = rp->paths_per_batch > 0 ? (uint32_t)rp->paths_per_batch : ((uint64_t)s->ws.cap >= total && s->ws.cap > 0 ? s->ws.cap : default_paths_per_batch(s));
   cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((cap + 31u) & ~31u, 32u), std::max<uint64_t>((total + 31) & ~31ull, 32));
   const uint32_t rounds = (uint32_t)rc.max_depth + 1 + 32;
   r = ensure_workspace(s, cap, rounds);

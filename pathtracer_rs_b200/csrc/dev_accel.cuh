@@ -274,6 +274,16 @@ PT_DEV void trace_empty(uint32_t n_items, uint32_t* ticket, Work& work) {
 #ifndef PT_TRI_STEPS
 #define PT_TRI_STEPS 1
 #endif
+// PT_EAGER_POP: a lane that is left without a node pops its next stack entry at the END of the step (one predicated
+// 16-byte local load in the convergent instruction stream) and the entry's `t_entry < t_max` test — the reference's box
+// test at pop time — is made when the node is used, together with the re-validation every node in hand needs anyway after
+// a hit has shrunk t_max.  Replaces the divergent pop section at the top of the step.
+#ifndef PT_EAGER_POP
+#define PT_EAGER_POP 0
+#endif
+#ifndef PT_NEAR_LEAF_DIRECT
+#define PT_NEAR_LEAF_DIRECT 0
+#endif
 template <class Work>
 PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, Work& work) {
   if (sc.n_nodes == 0) {
@@ -353,6 +363,91 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
     }
 
     // ---- box phase: pop / park / expand ----------------------------------------------------------------
+#if PT_EAGER_POP
+    auto eager_pop = [&]() {
+      if ((rbits & PT_RB_LIVE) && cur_meta == PT_NO_NODE && sp_ > 0) {
+        --sp_;
+        const uint4 e = stack[sp_];
+        cur_t = __uint_as_float(e.x);
+        cur_off = e.y;
+        cur_meta = e.z;
+      }
+    };
+    auto box_step = [&]() {
+      const bool live = (rbits & PT_RB_LIVE) != 0;
+      // the node in hand under the current t_max: the reference's box test at pop time, and the re-test a node accepted
+      // before a hit needs
+      if (cur_meta != PT_NO_NODE && !(cur_t < t_max)) cur_meta = PT_NO_NODE;
+#if PT_EAGER_POP == 2
+      // the entry popped ahead was culled: one more pop, tested on the spot, so that the lane still expands a node in this step
+      if (live && cur_meta == PT_NO_NODE && sp_ > 0) {
+        --sp_;
+        const uint4 e = stack[sp_];
+        if (__uint_as_float(e.x) < t_max) {
+          cur_t = __uint_as_float(e.x);
+          cur_off = e.y;
+          cur_meta = e.z;
+        }
+      }
+#endif
+      if (live && cur_meta != PT_NO_NODE) {
+        if ((cur_meta & 0xffffu) != 0) {
+          if (pl_cnt == 0) {  // park the leaf, keep descending
+            pl_off = cur_off;
+            pl_cnt = cur_meta & 0xffffu;
+            cur_meta = PT_NO_NODE;
+          }
+        } else {
+          const NodeLoad L = load_node(sc.nodes, cur_off);
+          const NodeLoad R = load_node(sc.nodes, cur_off + 1);
+          const bool nx = rbits & PT_RB_NX, ny = rbits & PT_RB_NY, nz = rbits & PT_RB_NZ;
+          const bool neg = ((rbits >> ((cur_meta >> 16) & 3u)) & 1u) != 0;  // dir_is_neg[axis]
+          float tl, tr;
+          const bool gl = box_geom(L, o, inv_dir, nx, ny, nz, &tl);
+          const bool gr = box_geom(R, o, inv_dir, nx, ny, nz, &tr);
+          // near child first (accelerator.rs:393-404)
+          const bool gn = neg ? gr : gl, gf = neg ? gl : gr;
+          const float tn = neg ? tr : tl, tf = neg ? tl : tr;
+          const float4 nb = neg ? R.b : L.b, fb = neg ? L.b : R.b;
+          bool an = gn && tn < t_max;
+          const bool af = gf && tf < t_max;
+          // an entered near child that is a leaf goes straight to the free parking slot; the far child is then the node
+          // in hand without a push / pop pair
+          if (an && (__float_as_uint(nb.w) & 0xffffu) != 0u && pl_cnt == 0u) {
+            pl_off = __float_as_uint(nb.z);
+            pl_cnt = __float_as_uint(nb.w) & 0xffffu;
+            an = false;
+          }
+          if (af && !an) {
+            cur_t = tf;
+            cur_off = __float_as_uint(fb.z);
+            cur_meta = __float_as_uint(fb.w);
+          } else {
+            if (af) {
+              if (sp_ < PT_STACK_SIZE) {  // always true: ptrs_scene_create refuses trees deeper than the stack
+                stack[sp_] = make_uint4(__float_as_uint(tf), __float_as_uint(fb.z), __float_as_uint(fb.w), 0u);
+                ++sp_;
+              }
+            }
+            if (an) {
+              cur_t = tn;
+              cur_off = __float_as_uint(nb.z);
+              cur_meta = __float_as_uint(nb.w);
+            } else {
+              cur_meta = PT_NO_NODE;
+            }
+          }
+          // the node now in hand is a leaf and the parking slot is free: park it here instead of in the next iteration
+          if (cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0u && pl_cnt == 0u) {
+            pl_off = cur_off;
+            pl_cnt = cur_meta & 0xffffu;
+            cur_meta = PT_NO_NODE;
+          }
+        }
+      }
+      eager_pop();
+    };
+#else
     auto box_step = [&]() {
       const bool live = (rbits & PT_RB_LIVE) != 0;
       const bool cur_leaf = cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0;
@@ -405,7 +500,17 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
             const bool gn = neg ? gr : gl, gf = neg ? gl : gr;
             const float tn = neg ? tr : tl, tf = neg ? tl : tr;
             const float4 nb = neg ? R.b : L.b, fb = neg ? L.b : R.b;
-            const bool an = gn && tn < t_max, af = gf && tf < t_max;
+            bool an = gn && tn < t_max;
+            const bool af = gf && tf < t_max;
+#if PT_NEAR_LEAF_DIRECT
+            // an entered near child that is a leaf goes straight to the free parking slot; the far child is then the node in
+            // hand without a push / pop pair
+            if (an && (__float_as_uint(nb.w) & 0xffffu) != 0u && pl_cnt == 0u) {
+              pl_off = __float_as_uint(nb.z);
+              pl_cnt = __float_as_uint(nb.w) & 0xffffu;
+              an = false;
+            }
+#endif
             if (af && !an) {
               // near child rejected, far child entered: the reference pushes the far child and pops it straight away; the
               // pop's re-test against t_max is what the node in hand gets anyway whenever a hit shrinks t_max
@@ -437,10 +542,15 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
         }
       }
     };
+#endif
     for (;;) {
       const bool live = (rbits & PT_RB_LIVE) != 0;
       const bool cur_leaf = cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0;
+#if PT_EAGER_POP
+      const bool can_box = live && cur_meta != PT_NO_NODE && (!cur_leaf || pl_cnt == 0);  // no node in hand => empty stack
+#else
       const bool can_box = live && ((cur_meta != PT_NO_NODE && !cur_leaf) || (cur_meta == PT_NO_NODE && sp_ > 0) || (cur_leaf && pl_cnt == 0));
+#endif
       const uint32_t bmask = __ballot_sync(FULL, can_box);
       if (bmask == 0) break;
       if (__popc(bmask) < box_min && __ballot_sync(FULL, live && !can_box) != 0) break;
@@ -452,11 +562,21 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
     // ---- triangle phase: parked leaves, first in first out -----------------------------------------------
     auto tri_step = [&]() {
       const bool live = (rbits & PT_RB_LIVE) != 0;
+#if PT_EAGER_POP
+      if (live && pl_cnt == 0 && cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0) {  // second leaf moves up, if it still qualifies
+        if (cur_t < t_max) {
+          pl_off = cur_off;
+          pl_cnt = cur_meta & 0xffffu;
+        }
+        cur_meta = PT_NO_NODE;
+      }
+#else
       if (live && pl_cnt == 0 && cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0) {  // second leaf moves up
         pl_off = cur_off;
         pl_cnt = cur_meta & 0xffffu;
         cur_meta = PT_NO_NODE;
       }
+#endif
       if (live && pl_cnt != 0) {
         const uint32_t prim = pl_off;
         const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim);
@@ -481,11 +601,17 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
             pl_cnt = 0;
             sp_ = 0;
             cur_meta = PT_NO_NODE;
-          } else if (cur_meta != PT_NO_NODE && !(cur_t < t_max)) {
+          }
+#if !PT_EAGER_POP
+          else if (cur_meta != PT_NO_NODE && !(cur_t < t_max)) {
             cur_meta = PT_NO_NODE;  // the node in hand was accepted under the old t_max: re-validate
           }
+#endif
         }
       }
+#if PT_EAGER_POP
+      eager_pop();
+#endif
     };
     for (;;) {
       const bool live = (rbits & PT_RB_LIVE) != 0;

@@ -284,6 +284,16 @@ PT_DEV void trace_empty(uint32_t n_items, uint32_t* ticket, Work& work) {
 #ifndef PT_NEAR_LEAF_DIRECT
 #define PT_NEAR_LEAF_DIRECT 0
 #endif
+// PT_SMEM_STACK = K: the K entries nearest the bottom of every ray's pending stack live in shared memory, one 16-byte
+// column per thread ([level][thread], so a warp's access is conflict-free whatever levels its lanes stand on: four
+// wavefronts, where the same access to thread-interleaved local memory touches four 128-byte lines PER DISTINCT LEVEL
+// among the lanes); deeper entries stay in local memory.  Blocks of PT_TRACE_BLOCK threads.
+#ifndef PT_SMEM_STACK
+#define PT_SMEM_STACK 0
+#endif
+#ifndef PT_TRACE_BLOCK
+#define PT_TRACE_BLOCK 128
+#endif
 template <class Work>
 PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, Work& work) {
   if (sc.n_nodes == 0) {
@@ -295,7 +305,19 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
   // not depend on it); measured: 12 is best on trees of a few dozen nodes, 20 on trees of 10^5 .. 10^7 nodes.
   const int box_min = (int)sc.box_min;
   const bool pop_twice = sc.pop_twice != 0;
+#if PT_SMEM_STACK
+  __shared__ uint4 sm_stack[PT_SMEM_STACK * PT_TRACE_BLOCK];
+  uint4 stack[PT_STACK_SIZE - PT_SMEM_STACK];
+  auto st_load = [&](int i) -> uint4 { return i < PT_SMEM_STACK ? sm_stack[i * PT_TRACE_BLOCK + threadIdx.x] : stack[i - PT_SMEM_STACK]; };
+  auto st_store = [&](int i, const uint4& e) {
+    if (i < PT_SMEM_STACK) sm_stack[i * PT_TRACE_BLOCK + threadIdx.x] = e;
+    else stack[i - PT_SMEM_STACK] = e;
+  };
+#else
   uint4 stack[PT_STACK_SIZE];
+  auto st_load = [&](int i) -> uint4 { return stack[i]; };
+  auto st_store = [&](int i, const uint4& e) { stack[i] = e; };
+#endif
   int sp_ = 0;
   // node in hand (its box test passed under the t_max current at that time): offset, meta, entry distance
   uint32_t cur_off = 0, cur_meta = PT_NO_NODE;
@@ -367,7 +389,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
     auto eager_pop = [&]() {
       if ((rbits & PT_RB_LIVE) && cur_meta == PT_NO_NODE && sp_ > 0) {
         --sp_;
-        const uint4 e = stack[sp_];
+        const uint4 e = st_load(sp_);
         cur_t = __uint_as_float(e.x);
         cur_off = e.y;
         cur_meta = e.z;
@@ -382,7 +404,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
       // the entry popped ahead was culled: one more pop, tested on the spot, so that the lane still expands a node in this step
       if (live && cur_meta == PT_NO_NODE && sp_ > 0) {
         --sp_;
-        const uint4 e = stack[sp_];
+        const uint4 e = st_load(sp_);
         if (__uint_as_float(e.x) < t_max) {
           cur_t = __uint_as_float(e.x);
           cur_off = e.y;
@@ -425,7 +447,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
           } else {
             if (af) {
               if (sp_ < PT_STACK_SIZE) {  // always true: ptrs_scene_create refuses trees deeper than the stack
-                stack[sp_] = make_uint4(__float_as_uint(tf), __float_as_uint(fb.z), __float_as_uint(fb.w), 0u);
+                st_store(sp_, make_uint4(__float_as_uint(tf), __float_as_uint(fb.z), __float_as_uint(fb.w), 0u));
                 ++sp_;
               }
             }
@@ -455,7 +477,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
       if (can_box) {
         if (cur_meta == PT_NO_NODE) {  // pop one entry; the reference's box test at pop time
           --sp_;
-          const uint4 e = stack[sp_];
+          const uint4 e = st_load(sp_);
           if (__uint_as_float(e.x) < t_max) {
             cur_t = __uint_as_float(e.x);
             cur_off = e.y;
@@ -472,7 +494,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
             }
             if (cur_meta == PT_NO_NODE && sp_ > 0) {
               --sp_;
-              const uint4 e2 = stack[sp_];
+              const uint4 e2 = st_load(sp_);
               if (__uint_as_float(e2.x) < t_max) {
                 cur_t = __uint_as_float(e2.x);
                 cur_off = e2.y;
@@ -520,7 +542,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
             } else {
               if (af) {
                 if (sp_ < PT_STACK_SIZE) {  // always true: ptrs_scene_create refuses trees deeper than the stack
-                  stack[sp_] = make_uint4(__float_as_uint(tf), __float_as_uint(fb.z), __float_as_uint(fb.w), 0u);
+                  st_store(sp_, make_uint4(__float_as_uint(tf), __float_as_uint(fb.z), __float_as_uint(fb.w), 0u));
                   ++sp_;
                 }
               }

@@ -13,6 +13,8 @@
 // cub::DeviceRadixSort (library code, like cuBLAS for a plain GEMM).  The tree differs from the reference's SAH
 // tree, so visit counts differ, but closest hits do not: the triangle test is the same code on the same vertices.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -37,7 +39,7 @@ struct __align__(32) TreeNode {  // internal nodes [0, n-1); leaves are addresse
   uint32_t first, last;   // sorted range covered
   uint32_t arrivals;      // refit: children finished so far
   uint32_t n_interior;    // emitted interior nodes in the subtree (0 when the subtree collapses into a leaf)
-  uint32_t pad;
+  uint32_t left_count;    // PLOC: primitives below `left` (what a primitive of the right subtree adds to its depth-first position)
 };
 struct __align__(32) NodeBox {
   float4 mn, mx;  // xyz used
@@ -51,6 +53,7 @@ struct BuildArrays {
   uint32_t* leaf_parent;  // n
   NodeBox* box;           // 2n - 1
   uint32_t* cbounds;      // 6 ordered uints: centroid bounds
+  uint32_t* leaf_pos;     // PLOC: sorted position -> depth-first position of the primitive (null: the two coincide)
 };
 
 __global__ void __launch_bounds__(256) prim_bounds_kernel(const uint32_t* __restrict__ prim_vertex, const float* __restrict__ pos, uint32_t n, BuildArrays A) {
@@ -208,6 +211,170 @@ __global__ void __launch_bounds__(256) refit_kernel(uint32_t n, BuildArrays A) {
   }
 }
 
+
+// ---- PLOC: parallel locally-ordered clustering (Meister & Bittner 2018) ---------------------------------------------
+// The radix tree above splits at Morton-code bit boundaries, i.e. at spatial medians of alternating axes whatever the
+// geometry looks like; the reference's builder chooses every split by the surface-area heuristic (accelerator.rs:
+// 156-307).  PLOC gets SAH-quality trees out of the same sorted sequence, bottom-up: every cluster looks PLOC_R places
+// to either side of its position in the (Morton-ordered) cluster sequence for the neighbour whose union with it has the
+// smallest surface area; two clusters that chose each other merge into a new node that takes the lower one's place; the
+// sequence is compacted; repeat until one cluster is left (about 35 rounds for 10^7 primitives).  Counts, the leaf
+// decision (same criterion as refit_kernel) and the interior-node counts are known at merge time, so there is no
+// separate refit pass.  Merged clusters are not contiguous ranges of the sorted order, so the primitives' final order
+// is the depth-first order of the finished tree (ploc_positions_kernel).
+#define PLOC_R 16
+#define PLOC_BLOCK 256
+#define PLOC_NONE 0xffffffffu
+#define PLOC_MAX_ROUNDS 512
+
+__global__ void __launch_bounds__(256) ploc_init_kernel(uint32_t n, BuildArrays A, uint32_t* __restrict__ cid) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const uint32_t prim = A.perm[j];
+    A.box[n - 1 + j] = NodeBox{A.pb_min[prim], A.pb_max[prim]};
+    cid[j] = n - 1 + j;
+  }
+}
+
+// nearest neighbour of every cluster within PLOC_R positions; the candidates' boxes are staged once per block in shared
+// memory.  Distance = area of the union (symmetric bit for bit: min / max commute).  Ties — the rule on regular meshes,
+// where many unions have the same area — are broken by a key that both ends of a pair compute alike: the nearer position
+// first, then the pair whose lower position is even, then the lower position.  The pair with the smallest (distance, key)
+// overall therefore always chooses each other (every round merges), and a run of equal distances pairs up as (0,1), (2,3),
+// ... and halves per round instead of peeling one pair off its end.
+__global__ void __launch_bounds__(PLOC_BLOCK) ploc_nn_kernel(uint32_t m, const uint32_t* __restrict__ cid, const NodeBox* __restrict__ box, uint32_t* __restrict__ nn) {
+  __shared__ float4 s_mn[PLOC_BLOCK + 2 * PLOC_R], s_mx[PLOC_BLOCK + 2 * PLOC_R];
+  for (uint32_t base = blockIdx.x * PLOC_BLOCK; base < m; base += gridDim.x * PLOC_BLOCK) {
+    for (uint32_t t = threadIdx.x; t < PLOC_BLOCK + 2 * PLOC_R; t += PLOC_BLOCK) {
+      const long long g = (long long)base - PLOC_R + (long long)t;
+      if (g >= 0 && g < (long long)m) {
+        const uint32_t id = cid[g];
+        s_mn[t] = box[id].mn;
+        s_mx[t] = box[id].mx;
+      }
+    }
+    __syncthreads();
+    const uint32_t i = base + threadIdx.x;
+    if (i < m) {
+      const int me = (int)threadIdx.x + PLOC_R;
+      const float4 mn = s_mn[me], mx = s_mx[me];
+      float best = CUDART_INF_F;
+      uint32_t best_j = PLOC_NONE;
+      auto consider = [&](int d) {  // candidates arrive in tie-break order, so a strict comparison keeps the preferred one
+        const long long j = (long long)i + d;
+        if (j < 0 || j >= (long long)m) return;
+        const float4 omn = s_mn[me + d], omx = s_mx[me + d];
+        const float4 umn = make_float4(fminf(mn.x, omn.x), fminf(mn.y, omn.y), fminf(mn.z, omn.z), 0.f);
+        const float4 umx = make_float4(fmaxf(mx.x, omx.x), fmaxf(mx.y, omx.y), fmaxf(mx.z, omx.z), 0.f);
+        const float a = fminf(box_area(umn, umx), 3.0e38f);  // NaN / inf areas (degenerate input) still order
+        if (a < best) {
+          best = a;
+          best_j = (uint32_t)j;
+        }
+      };
+#pragma unroll 4
+      for (int d = 1; d <= PLOC_R; ++d) {
+        // pair (i - d, i) has lower position i - d, pair (i, i + d) has lower position i: even lower position first, and
+        // when both have the same parity (d even) the lower one
+        const bool up_first = (d & 1) && !(i & 1u);
+        consider(up_first ? d : -d);
+        consider(up_first ? -d : d);
+      }
+      nn[i] = best_j;
+    }
+    __syncthreads();
+  }
+}
+
+// mutual pairs merge: the lower position creates the node (ids are handed out downwards from n - 2, so the last merge,
+// the root, is node 0 as in the radix tree) and keeps its place, the upper position drops out of the sequence
+__global__ void __launch_bounds__(256) ploc_merge_kernel(uint32_t m, uint32_t n, const uint32_t* __restrict__ cid, const uint32_t* __restrict__ nn, BuildArrays A,
+                                                         uint32_t* __restrict__ counter, uint32_t* __restrict__ cid_out, uint32_t* __restrict__ keep) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const uint32_t j = nn[i];
+    const bool mutual = j != PLOC_NONE && nn[j] == i;
+    if (!mutual) {
+      cid_out[i] = cid[i];
+      keep[i] = 1u;
+      continue;
+    }
+    if (i > j) {
+      keep[i] = 0u;
+      continue;
+    }
+    const uint32_t l = cid[i], r = cid[j];
+    const uint32_t id = n - 2u - atomicAdd(counter, 1u);
+    const float4 lmn = A.box[l].mn, lmx = A.box[l].mx, rmn = A.box[r].mn, rmx = A.box[r].mx;
+    const float4 mn = make_float4(fminf(lmn.x, rmn.x), fminf(lmn.y, rmn.y), fminf(lmn.z, rmn.z), 0.f);
+    const float4 mx = make_float4(fmaxf(lmx.x, rmx.x), fmaxf(lmx.y, rmx.y), fmaxf(lmx.z, rmx.z), 0.f);
+    uint32_t cl = 1u, cr = 1u, nil = 0u, nir = 0u;
+    if (l < n - 1) {  // TreeNode::last holds the primitive COUNT until ploc_positions_kernel turns it into a range
+      cl = A.node[l].last;
+      nil = A.node[l].n_interior;
+      A.node[l].parent = id;
+    } else {
+      A.leaf_parent[l - (n - 1)] = id;
+    }
+    if (r < n - 1) {
+      cr = A.node[r].last;
+      nir = A.node[r].n_interior;
+      A.node[r].parent = id;
+    } else {
+      A.leaf_parent[r - (n - 1)] = id;
+    }
+    const uint32_t count = cl + cr;
+    bool leaf = count <= PT_BVH_MAX_LEAF && nil == 0u && nir == 0u;
+    if (leaf) {  // accelerator.rs:240-254, as in refit_kernel
+      const float cost = 1.0f + ((float)cl * box_area(lmn, lmx) + (float)cr * box_area(rmn, rmx)) / box_area(mn, mx);
+      leaf = !(cost < (float)count);
+    }
+    TreeNode nd;
+    nd.left = l;
+    nd.right = r;
+    nd.parent = 0xffffffffu;
+    nd.first = 0u;
+    nd.last = count;
+    nd.arrivals = 0u;
+    nd.n_interior = leaf ? 0u : 1u + nil + nir;
+    nd.left_count = cl;
+    A.node[id] = nd;
+    A.box[id] = NodeBox{mn, mx};
+    cid_out[i] = id;
+    keep[i] = 1u;
+  }
+}
+
+__global__ void __launch_bounds__(256) ploc_compact_kernel(uint32_t m, const uint32_t* __restrict__ cid_out, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ rank,
+                                                           uint32_t* __restrict__ cid_next, uint32_t* __restrict__ m_next) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    if (keep[i]) cid_next[rank[i]] = cid_out[i];
+    if (i == m - 1) *m_next = rank[i] + keep[i];
+  }
+}
+
+// depth-first position of every node's first primitive: on the way up to the root, a node that hangs in a right subtree
+// comes after everything below the left sibling.  Interior nodes get their primitive range (first, last) as the radix
+// tree has it by construction; leaves get their final position and the primitive order follows.
+__global__ void __launch_bounds__(256) ploc_positions_kernel(uint32_t n, BuildArrays A, const uint32_t* __restrict__ perm_sorted, uint32_t* __restrict__ perm_final) {
+  for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < 2u * n - 1u; x += gridDim.x * blockDim.x) {
+    uint32_t c = x, first = 0u;
+    uint32_t p = x < n - 1 ? A.node[x].parent : A.leaf_parent[x - (n - 1)];
+    while (p != 0xffffffffu) {
+      const uint4 w0 = *reinterpret_cast<const uint4*>(A.node + p);  // left, right, parent, first
+      if (w0.y == c) first += A.node[p].left_count;
+      c = p;
+      p = w0.z;
+    }
+    if (x < n - 1) {
+      const uint32_t count = A.node[x].last;
+      A.node[x].first = first;
+      A.node[x].last = first + count - 1u;
+    } else {
+      A.leaf_pos[x - (n - 1)] = first;
+      perm_final[first] = perm_sorted[x - (n - 1)];
+    }
+  }
+}
+
 struct NodeRec {  // the reference's LinearBVHNode (accelerator.rs:83-95) as two float4
   float4 a, b;
 };
@@ -255,7 +422,7 @@ __global__ void __launch_bounds__(256) emit_kernel(uint32_t n, BuildArrays A, fl
         if (fabsf(g[2]) > fabsf(g[ax])) ax = 2;
         return make_node(mn, mx, 2u * c_pair, 0u, ax);
       }
-      const uint32_t f = c < n - 1 ? A.node[c].first : c - (n - 1);
+      const uint32_t f = c < n - 1 ? A.node[c].first : (A.leaf_pos ? A.leaf_pos[c - (n - 1)] : c - (n - 1));
       const uint32_t cnt = c < n - 1 ? A.node[c].last - A.node[c].first + 1u : 1u;
       return make_node(mn, mx, f, cnt, 0u);
     };
@@ -391,10 +558,14 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
   *n_nodes_out = 0;
   *depth_out = 0;
   if (n == 0) return cudaSuccess;
+  // tree topology: the radix tree, or PLOC clustering with PTRS_BVH_BUILDER=ploc (unverified on hardware yet)
+  bool ploc = false;
+  if (const char* b = std::getenv("PTRS_BVH_BUILDER")) ploc = n > 1 && std::strcmp(b, "ploc") == 0;
   BuildArrays A{};
   uint64_t* keys_sorted = nullptr;
-  uint32_t *perm_in = nullptr, *perm_sorted = nullptr;
-  void* sort_tmp = nullptr;
+  uint32_t *perm_in = nullptr, *perm_sorted = nullptr, *perm_final = nullptr;
+  uint32_t *cid_a = nullptr, *cid_b = nullptr, *cid_out = nullptr, *nn = nullptr, *keep = nullptr, *rank = nullptr, *cells = nullptr;
+  void *sort_tmp = nullptr, *scan_tmp = nullptr;
   float4* nodes = nullptr;
   cudaError_t e = cudaSuccess;
   auto ok = [&](cudaError_t r) {
@@ -404,6 +575,8 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
   const size_t n_int = n > 1 ? n - 1 : 0;
   size_t sort_bytes = 0;
   ok(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, A.keys, keys_sorted, perm_in, perm_sorted, (int)n, 0, 63, st));
+  size_t scan_bytes = 0;
+  if (ploc) ok(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, keep, rank, (int)n, st));
   Arena arena;
   auto carve = [&](Arena& ar) {
     ar.take(&A.pb_min, n);
@@ -418,6 +591,19 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
     char* tmp = nullptr;
     ar.take(&tmp, std::max<size_t>(sort_bytes, 16));
     sort_tmp = tmp;
+    if (ploc) {
+      ar.take(&cid_a, n);
+      ar.take(&cid_b, n);
+      ar.take(&cid_out, n);
+      ar.take(&nn, n);
+      ar.take(&keep, n);
+      ar.take(&rank, n);
+      ar.take(&A.leaf_pos, n);
+      ar.take(&cells, 2);  // [0] node-id counter, [1] length of the next cluster sequence
+      char* tmp2 = nullptr;
+      ar.take(&tmp2, std::max<size_t>(scan_bytes, 16));
+      scan_tmp = tmp2;
+    }
   };
   carve(arena);  // sizes only
   const size_t arena_bytes = arena.used;
@@ -437,13 +623,45 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
     ok(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, A.keys, keys_sorted, perm_in, perm_sorted, (int)n, 0, 63, st));
     A.perm = perm_sorted;
     A.keys = keys_sorted;
-    if (n > 1) {
+    if (ploc) {
+      ploc_init_kernel<<<grid, 256, 0, st>>>(n, A, cid_a);
+      ok(cudaMemsetAsync(cells, 0, 8, st));
+      uint32_t m = n, *cur = cid_a, *nxt = cid_b;
+      int rounds = 0;
+      while (e == cudaSuccess && m > 1) {
+        if (++rounds > PLOC_MAX_ROUNDS) {  // adversarial input (never seen: ~1.5 log2 n rounds): the radix tree is built instead
+          ploc = false;
+          break;
+        }
+        const int g = (int)std::min<uint32_t>((uint32_t)grid, (m + 255u) / 256u);
+        ploc_nn_kernel<<<g, PLOC_BLOCK, 0, st>>>(m, cur, A.box, nn);
+        ploc_merge_kernel<<<g, 256, 0, st>>>(m, n, cur, nn, A, cells, cid_out, keep);
+        ok(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, keep, rank, (int)m, st));
+        ploc_compact_kernel<<<g, 256, 0, st>>>(m, cid_out, keep, rank, nxt, cells + 1);
+        uint32_t m_next = 0;
+        ok(cudaMemcpyAsync(&m_next, cells + 1, 4, cudaMemcpyDeviceToHost, st));
+        ok(cudaStreamSynchronize(st));
+        ok(cudaGetLastError());
+        if (e == cudaSuccess && (m_next == 0 || m_next >= m)) e = cudaErrorUnknown;  // every round merges at least one pair
+        m = m_next;
+        std::swap(cur, nxt);
+      }
+      if (ploc) ok(cudaMemcpyAsync(&n_interior_root, &A.node[0].n_interior, 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (!ploc && n > 1) {
+      A.leaf_pos = nullptr;
       radix_tree_kernel<<<grid, 256, 0, st>>>(A.keys, (int)n, A);
       refit_kernel<<<grid, 256, 0, st>>>(n, A);
       ok(cudaMemcpyAsync(&n_interior_root, &A.node[0].n_interior, 4, cudaMemcpyDeviceToHost, st));
     }
     ok(cudaStreamSynchronize(st));
     ok(cudaGetLastError());
+  }
+  if (e == cudaSuccess && ploc && n_interior_root != 0) {
+    ok(pool_alloc(reinterpret_cast<void**>(&perm_final), (size_t)n * 4, st));  // survives instead of the sorted order
+    if (e == cudaSuccess) ploc_positions_kernel<<<grid, 256, 0, st>>>(n, A, perm_sorted, perm_final);
+  } else {
+    A.leaf_pos = nullptr;
   }
   if (e == cudaSuccess) {
     const uint32_t n_nodes = 2u + 2u * n_interior_root;
@@ -466,10 +684,16 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
   if (e != cudaSuccess) {
     if (nodes) cudaFreeAsync(nodes, st);
     if (perm_sorted) cudaFreeAsync(perm_sorted, st);
+    if (perm_final) cudaFreeAsync(perm_final, st);
     return (int)e;
   }
   *nodes_out = nodes;
-  *perm_out = perm_sorted;
+  if (perm_final) {
+    cudaFreeAsync(perm_sorted, st);
+    *perm_out = perm_final;
+  } else {
+    *perm_out = perm_sorted;
+  }
   return (int)cudaSuccess;
 }
 

@@ -249,8 +249,10 @@ def _walk_device_tree(nodes):
     return leaves
 
 
+@pytest.mark.parametrize("builder", ["ploc", "lbvh"])
 @pytest.mark.parametrize("scene_name", ["cornell", "field_small", "terrain_small"])
-def test_device_bvh_is_a_valid_tree(gpu, request, scene_name):
+def test_device_bvh_is_a_valid_tree(gpu, request, monkeypatch, scene_name, builder):
+    monkeypatch.setenv("PTRS_BVH_BUILDER", builder)  # csrc/k_bvh.cu: PLOC clustering (default) or the plain radix tree
     flat, _ = request.getfixturevalue(scene_name)
     scene = gpu.RenderScene(flat, device_bvh=True)
     nodes, order = scene.download_nodes()
@@ -274,12 +276,14 @@ def test_device_bvh_is_a_valid_tree(gpu, request, scene_name):
     scene.close()
 
 
+@pytest.mark.parametrize("builder", ["ploc", "lbvh"])
 @pytest.mark.parametrize("scene_name", ["cornell", "field_small", "terrain_small", "atrium_small"])
-def test_device_bvh_hits_equal_the_reference_built_bvh(gpu, host, request, scene_name):
+def test_device_bvh_hits_equal_the_reference_built_bvh(gpu, host, request, monkeypatch, scene_name, builder):
     """Same triangle test on the same vertices, so the closest hit does not depend on the tree — except between
     candidates within an ulp or two of each other: the later-visited one wins exact ties (shape.rs:150-154) and the
     slab test's t_min is not conservative (bounds.rs:190-232 only widens t_max), so a leaf whose box starts at the
     current t_max is culled or not depending on what was found first.  Measured: <= 1 ray in 50 000, 7e-8 relative."""
+    monkeypatch.setenv("PTRS_BVH_BUILDER", builder)
     flat, cam = request.getfixturevalue(scene_name)
     ref = gpu.RenderScene(flat)
     dev = gpu.RenderScene(flat, device_bvh=True)
@@ -339,6 +343,44 @@ def test_device_bvh_tiny_scenes(gpu, host):
         assert n_nodes == 2 if n_tri == 1 else (n_nodes % 2 == 0 and 4 <= n_nodes <= 2 * n_tri)
         ref.close()
         dev.close()
+
+
+@pytest.mark.parametrize("builder", ["ploc", "lbvh"])
+def test_device_bvh_duplicate_and_gridded_primitives(gpu, host, monkeypatch, builder):
+    """Inputs on which every candidate distance ties: 4096 copies of one triangle and a regular 64 x 64 grid of quads.
+    PLOC's tie-break (nearer position, even lower position, lower position: csrc/k_bvh.cu ploc_nn_kernel) must pair such
+    runs up level by level — a tree of logarithmic depth in a logarithmic number of rounds — not peel one pair per round."""
+    monkeypatch.setenv("PTRS_BVH_BUILDER", builder)
+    b = host.SceneBuilder()
+    m = b.material(host.MAT_MATTE, [b.constant_texture([0.5, 0.5, 0.5])])
+    n_dup = 4096
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float32)
+    b.mesh(np.tile(tri, (n_dup, 1)) + np.float32([0, 0, 5]), np.arange(3 * n_dup, dtype=np.uint32).reshape(-1, 3), material=m)
+    g = 65
+    xs, ys = np.meshgrid(np.arange(g, dtype=np.float32), np.arange(g, dtype=np.float32), indexing="ij")
+    verts = np.stack([xs.ravel(), ys.ravel(), np.zeros(g * g, dtype=np.float32)], axis=1)
+    q = (np.arange(g - 1)[:, None] * g + np.arange(g - 1)[None, :]).ravel().astype(np.uint32)
+    idx = np.concatenate([np.stack([q, q + g, q + 1], axis=1), np.stack([q + 1, q + g, q + g + 1], axis=1)])
+    b.mesh(verts, idx, material=m)
+    flat = b.finalize()
+    dev = gpu.RenderScene(flat, device_bvh=True)
+    nodes, order = dev.download_nodes()
+    assert np.array_equal(np.sort(order), np.arange(flat.n_prims, dtype=np.uint32))
+    covered = np.zeros(flat.n_prims, dtype=np.int32)
+    for off, cnt in _walk_device_tree(nodes):
+        assert 1 <= cnt <= 4
+        covered[off: off + cnt] += 1
+    assert np.all(covered == 1)
+    ref = gpu.RenderScene(flat)
+    rays = np.zeros(4096, dtype=host.RAY_DTYPE)
+    rng = np.random.default_rng(5)
+    rays["o"] = np.concatenate([rng.uniform(0, 64, (4096, 2)), np.full((4096, 1), 9.0)], axis=1).astype(np.float32)
+    rays["d"] = [0, 0, -1]
+    rays["t_max"] = np.inf
+    a, c = ref.intersect(rays), dev.intersect(rays)
+    assert np.array_equal(a["prim"] >= 0, c["prim"] >= 0) and np.array_equal(a["t"], c["t"])
+    ref.close()
+    dev.close()
 
 
 def test_imported_gltf_scene_renders_like_the_oracle(gpu, host, oracle, tmp_path):

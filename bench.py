@@ -525,6 +525,31 @@ def run_gpu(args):
                "sample": f"every {stride}th of the {n_tiles} 16x16 tiles, all {w['spp']} spp ({ost['camera_paths']} camera paths, {dt:.1f} s)",
                "mrays_per_s": (ost["extension_rays"] + ost["shadow_rays"] + ost["mis_rays"]) / dt / 1e6}
 
+    # ---- the same render over the tree the library builds itself (ptrs_scene_create_device_bvh: PLOC clustering, k_bvh.cu) ----
+    # An eighth of the step's samples through both trees, one warm-up and one timed pass each.  The headline above stays on
+    # the reference-built tree (what the north star names and what the bit-exact hit parity is defined on).
+    dev_tree = None
+    if n_gpus == 1 and mode == "single" and not args.no_device_bvh_render:
+        try:
+            spp_d = max(1, w["spp"] // 8)
+            sc_d = gpu.RenderScene(flat, device_bvh=True)
+            dev_tree = {"spp": spp_d, "device_nodes": sc_d.bvh_info()[0], "device_build_ms": sc_d.bvh_info()[1], "reference_nodes": int(flat.n_nodes)}
+            for name, sc in (("reference_built_tree", scene), ("device_built_tree", sc_d)):
+                for it in range(2):
+                    film.clear(stream)
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    std = integ.render(cam, sc, film, stream=stream, sample_range=(0, spp_d))
+                    e1.record()
+                    e1.synchronize()
+                dev_tree[name] = {"ms": e0.elapsed_time(e1), "samples_per_s": std["camera_paths"] / (e0.elapsed_time(e1) * 1e-3),
+                                  "ms_extend": std["ms_extend"], "ms_connect_trace": std["ms_connect_trace"]}
+            dev_tree["speedup"] = dev_tree["reference_built_tree"]["ms"] / dev_tree["device_built_tree"]["ms"]
+            sc_d.close()
+        except Exception as e:  # an extra, never the reason a bench line is missing
+            dev_tree = {"error": str(e)}
+
     micro = None
     if n_gpus == 1 and not args.no_bvh_microbench:
         if mode != "threads":
@@ -547,7 +572,7 @@ def run_gpu(args):
                     "parts_last_step": e2e_parts},
             "gpu_launches": int(stats["launches"]) * args.steps * (n_gpus if mode == "ranks" else 1), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "stage_ms": {k: stats[k] for k in ("ms_generate", "ms_extend", "ms_shade", "ms_connect_trace", "ms_resolve", "ms_accumulate", "ms_total")},
-            "rays_per_step": rays_step, "rays_rank0": {k: stats[k] for k in ("extension_rays", "shadow_rays", "mis_rays")}, "bvh_microbench": micro}
+            "rays_per_step": rays_step, "rays_rank0": {k: stats[k] for k in ("extension_rays", "shadow_rays", "mis_rays")}, "device_bvh_render": dev_tree, "bvh_microbench": micro}
     emit(line)
     if comm:
         comm.close()
@@ -583,6 +608,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bvh-microbench", action="store_true")
+    ap.add_argument("--no-device-bvh-render", action="store_true")
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override the workload's total samples per pixel")
     args = ap.parse_args()

@@ -1,18 +1,26 @@
 // BVH construction on the device: replaces the host's recursive SAH build
 // (src/pathtracer/accelerator.rs:103-346) when the caller hands over unordered primitives.
 //
-// Linear BVH: 63-bit Morton codes of the primitive centroids -> radix sort -> Karras' binary radix tree built
-// in parallel (one thread per internal node) -> bottom-up bounds with one atomic per node -> subtrees of at most
-// 4 primitives collapse into leaves (the reference's max_prims_in_node) -> emission into the traversal layout of
-// dev_accel.cuh: 32-byte LinearBVHNode records, the two children of an interior node side by side (64-byte
-// pairs), pairs numbered depth-first so a subtree is contiguous in memory.  `axis` is the axis along which the
-// two children's box centres differ most and the first child is the lower one, which is what the traversal's
-// near-child rule dir_is_neg[axis] (accelerator.rs:393-404) assumes.
+// 63-bit Morton codes of the primitive centroids -> radix sort -> tree topology -> subtrees of at most 4 primitives
+// collapse into leaves where the reference builder's own cost criterion says so (max_prims_in_node = 4) -> emission
+// into the traversal layout of dev_accel.cuh: 32-byte LinearBVHNode records, the two children of an interior node side
+// by side (64-byte pairs), pairs numbered depth-first so a subtree is contiguous in memory.  `axis` is the axis along
+// which the two children's box centres differ most and the first child is the lower one, which is what the
+// traversal's near-child rule dir_is_neg[axis] (accelerator.rs:393-404) assumes.
+//
+// Two topologies over the same sorted sequence:
+//   PLOC (default)   bottom-up clustering by smallest merged surface area within a window of the Morton order
+//                    (Meister & Bittner 2018): SAH-quality trees — measured against the reference-built SAH tree:
+//                    4K atrium 5 - 15 % FASTER to traverse, 1 M-triangle field equal, 10 M-triangle terrain 14 % slower
+//   radix tree       Karras 2012, one thread per internal node + bottom-up boxes with one atomic per node
+//                    (PTRS_BVH_BUILDER=lbvh): a third of the build time, 10 - 30 % slower to traverse than PLOC
 //
 // Every kernel is a streaming pass over HBM-resident arrays (24-68 B per primitive); the sort is
 // cub::DeviceRadixSort (library code, like cuBLAS for a plain GEMM).  The tree differs from the reference's SAH
 // tree, so visit counts differ, but closest hits do not: the triangle test is the same code on the same vertices.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
@@ -289,20 +297,31 @@ __global__ void __launch_bounds__(PLOC_BLOCK) ploc_nn_kernel(uint32_t m, const u
 // the root, is node 0 as in the radix tree) and keeps its place, the upper position drops out of the sequence
 __global__ void __launch_bounds__(256) ploc_merge_kernel(uint32_t m, uint32_t n, const uint32_t* __restrict__ cid, const uint32_t* __restrict__ nn, BuildArrays A,
                                                          uint32_t* __restrict__ counter, uint32_t* __restrict__ cid_out, uint32_t* __restrict__ keep) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-    const uint32_t j = nn[i];
-    const bool mutual = j != PLOC_NONE && nn[j] == i;
-    if (!mutual) {
-      cid_out[i] = cid[i];
-      keep[i] = 1u;
-      continue;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < m; base += gridDim.x * blockDim.x) {  // warp-uniform trip count
+    const uint32_t i = base + threadIdx.x;
+    uint32_t j = PLOC_NONE;
+    bool creates = false;
+    if (i < m) {
+      j = nn[i];
+      const bool mutual = j != PLOC_NONE && nn[j] == i;
+      if (!mutual) {
+        cid_out[i] = cid[i];
+        keep[i] = 1u;
+      } else if (i > j) {
+        keep[i] = 0u;
+      } else {
+        creates = true;
+      }
     }
-    if (i > j) {
-      keep[i] = 0u;
-      continue;
-    }
+    // node ids: one atomicAdd per warp
+    const uint32_t cmask = __ballot_sync(0xffffffffu, creates);
+    uint32_t id0 = 0;
+    if (cmask != 0u && lane == (uint32_t)(__ffs(cmask) - 1)) id0 = atomicAdd(counter, (uint32_t)__popc(cmask));
+    id0 = __shfl_sync(0xffffffffu, id0, cmask ? __ffs(cmask) - 1 : 0);
+    if (!creates) continue;
     const uint32_t l = cid[i], r = cid[j];
-    const uint32_t id = n - 2u - atomicAdd(counter, 1u);
+    const uint32_t id = n - 2u - (id0 + (uint32_t)__popc(cmask & ((1u << lane) - 1u)));
     const float4 lmn = A.box[l].mn, lmx = A.box[l].mx, rmn = A.box[r].mn, rmx = A.box[r].mx;
     const float4 mn = make_float4(fminf(lmn.x, rmn.x), fminf(lmn.y, rmn.y), fminf(lmn.z, rmn.z), 0.f);
     const float4 mx = make_float4(fmaxf(lmx.x, rmx.x), fmaxf(lmx.y, rmx.y), fmaxf(lmx.z, rmx.z), 0.f);
@@ -558,9 +577,19 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
   *n_nodes_out = 0;
   *depth_out = 0;
   if (n == 0) return cudaSuccess;
-  // tree topology: the radix tree, or PLOC clustering with PTRS_BVH_BUILDER=ploc (unverified on hardware yet)
-  bool ploc = false;
-  if (const char* b = std::getenv("PTRS_BVH_BUILDER")) ploc = n > 1 && std::strcmp(b, "ploc") == 0;
+  // tree topology: PLOC clustering; PTRS_BVH_BUILDER=lbvh selects the plain radix tree (a third of the build time,
+  // 10 - 30 % slower to traverse: profiles/experiments/README.md)
+  bool ploc = n > 1;
+  if (const char* b = std::getenv("PTRS_BVH_BUILDER")) ploc = ploc && std::strcmp(b, "lbvh") != 0;
+  const bool debug = std::getenv("PTRS_BVH_DEBUG") != nullptr;  // phase and round trace on stderr (synchronises between phases)
+  auto t_phase = std::chrono::steady_clock::now();
+  auto phase = [&](const char* what) {
+    if (!debug) return;
+    cudaStreamSynchronize(st);
+    const auto t_now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "bvh build: %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t_now - t_phase).count());
+    t_phase = t_now;
+  };
   BuildArrays A{};
   uint64_t* keys_sorted = nullptr;
   uint32_t *perm_in = nullptr, *perm_sorted = nullptr, *perm_final = nullptr;
@@ -612,6 +641,7 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
   ok(pool_alloc(reinterpret_cast<void**>(&perm_sorted), (size_t)n * 4, st));  // survives: the primitive order handed back
   const int grid = 148 * 8;
   uint32_t n_interior_root = 0;
+  phase("allocation");
   if (e == cudaSuccess) {
     arena = Arena{static_cast<char*>(arena_mem), 0};
     carve(arena);
@@ -623,11 +653,13 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
     ok(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, A.keys, keys_sorted, perm_in, perm_sorted, (int)n, 0, 63, st));
     A.perm = perm_sorted;
     A.keys = keys_sorted;
+    phase("bounds, morton codes, sort");
     if (ploc) {
       ploc_init_kernel<<<grid, 256, 0, st>>>(n, A, cid_a);
       ok(cudaMemsetAsync(cells, 0, 8, st));
       uint32_t m = n, *cur = cid_a, *nxt = cid_b;
       int rounds = 0;
+      auto t_prev = std::chrono::steady_clock::now();
       while (e == cudaSuccess && m > 1) {
         if (++rounds > PLOC_MAX_ROUNDS) {  // adversarial input (never seen: ~1.5 log2 n rounds): the radix tree is built instead
           ploc = false;
@@ -643,6 +675,11 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
         ok(cudaStreamSynchronize(st));
         ok(cudaGetLastError());
         if (e == cudaSuccess && (m_next == 0 || m_next >= m)) e = cudaErrorUnknown;  // every round merges at least one pair
+        if (debug) {
+          const auto t_now = std::chrono::steady_clock::now();
+          std::fprintf(stderr, "ploc round %d: %u -> %u clusters, %.3f ms\n", rounds, m, m_next, std::chrono::duration<double, std::milli>(t_now - t_prev).count());
+          t_prev = t_now;
+        }
         m = m_next;
         std::swap(cur, nxt);
       }
@@ -656,6 +693,7 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
     }
     ok(cudaStreamSynchronize(st));
     ok(cudaGetLastError());
+    phase("tree topology and boxes");
   }
   if (e == cudaSuccess && ploc && n_interior_root != 0) {
     ok(pool_alloc(reinterpret_cast<void**>(&perm_final), (size_t)n * 4, st));  // survives instead of the sorted order
@@ -680,7 +718,9 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
       *n_nodes_out = n_nodes;
     }
   }
+  phase("positions, node emission");
   if (arena_mem) cudaFreeAsync(arena_mem, st);
+  phase("free");
   if (e != cudaSuccess) {
     if (nodes) cudaFreeAsync(nodes, st);
     if (perm_sorted) cudaFreeAsync(perm_sorted, st);

@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -165,7 +166,9 @@ __global__ void __launch_bounds__(256) radix_tree_kernel(const uint64_t* __restr
   }
 }
 
+#ifndef PT_BVH_MAX_LEAF
 #define PT_BVH_MAX_LEAF 4u  // BVH::new(.., &4), importer/mitsuba.rs:362
+#endif
 
 __device__ __forceinline__ float box_area(float4 mn, float4 mx) {
   const float dx = mx.x - mn.x, dy = mx.y - mn.y, dz = mx.z - mn.z;
@@ -230,7 +233,9 @@ __global__ void __launch_bounds__(256) refit_kernel(uint32_t n, BuildArrays A) {
 // decision (same criterion as refit_kernel) and the interior-node counts are known at merge time, so there is no
 // separate refit pass.  Merged clusters are not contiguous ranges of the sorted order, so the primitives' final order
 // is the depth-first order of the finished tree (ploc_positions_kernel).
+#ifndef PLOC_R
 #define PLOC_R 16
+#endif
 #define PLOC_BLOCK 256
 #define PLOC_NONE 0xffffffffu
 #define PLOC_MAX_ROUNDS 512
@@ -565,7 +570,74 @@ struct Arena {  // one stream-ordered allocation carved into 256-byte aligned ar
   }
 };
 
+// The build's working memory: one block per device kept between builds (see build_bvh_on_device)
+struct BuildCache {
+  std::mutex mu;
+  void* p[PT_MAX_DEVICES] = {};
+  size_t bytes[PT_MAX_DEVICES] = {};
+  bool busy[PT_MAX_DEVICES] = {};
+};
+BuildCache& build_cache() {
+  static BuildCache c;
+  return c;
+}
+struct BuildBlock {
+  void* p = nullptr;
+  int dev = -1;       // >= 0: p is the device's cached block
+  bool own = false;   // p is a pool allocation of this build alone
+  cudaError_t acquire(size_t bytes, cudaStream_t st) {
+    int d = 0;
+    cudaError_t e = cudaGetDevice(&d);
+    if (e != cudaSuccess) return e;
+    BuildCache& c = build_cache();
+    {
+      std::lock_guard<std::mutex> lock(c.mu);
+      if (d >= 0 && d < PT_MAX_DEVICES && !c.busy[d]) {
+        if (c.bytes[d] < bytes) {
+          if (c.p[d]) cudaFreeAsync(c.p[d], st);
+          c.p[d] = nullptr;
+          c.bytes[d] = 0;
+          e = pool_alloc(&c.p[d], bytes, st);
+          if (e != cudaSuccess) return e;
+          c.bytes[d] = bytes;
+        }
+        c.busy[d] = true;
+        dev = d;
+        p = c.p[d];
+        return cudaSuccess;
+      }
+    }
+    own = true;
+    return pool_alloc(&p, bytes, st);
+  }
+  void release(cudaStream_t st) {
+    if (own && p) cudaFreeAsync(p, st);
+    if (dev >= 0) {
+      cudaStreamSynchronize(st);  // the next build may run on another stream
+      BuildCache& c = build_cache();
+      std::lock_guard<std::mutex> lock(c.mu);
+      c.busy[dev] = false;
+    }
+    p = nullptr;
+    dev = -1;
+    own = false;
+  }
+  ~BuildBlock() { release(0); }
+};
+
 }  // namespace
+
+// ptrs_trim_memory: the cached working memory of the BVH builder goes back to the pool (and from there to the driver)
+void release_bvh_build_cache() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= PT_MAX_DEVICES) return;
+  BuildCache& c = build_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (c.busy[d] || !c.p[d]) return;
+  cudaFreeAsync(c.p[d], 0);
+  c.p[d] = nullptr;
+  c.bytes[d] = 0;
+}
 
 // Builds the BVH over n primitives given as device arrays in the caller's order.  On success *nodes_out holds
 // *n_nodes_out 32-byte records (as float4 pairs) and *perm_out the primitive order (BVH position -> caller index);
@@ -606,6 +678,10 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
   ok(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, A.keys, keys_sorted, perm_in, perm_sorted, (int)n, 0, 63, st));
   size_t scan_bytes = 0;
   if (ploc) ok(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, keep, rank, (int)n, st));
+  // Working memory (190 B per primitive) comes from a per-device block the library keeps between builds (released by
+  // ptrs_trim_memory): taken from the pool per build, a block of this size displaces the pool's cached blocks and the node
+  // array allocated afterwards has to map fresh memory — 20 - 500 ms against the 17 ms the kernels of a 10 M-triangle
+  // build take.  A second build running concurrently on the same device falls back to a block of its own.
   Arena arena;
   auto carve = [&](Arena& ar) {
     ar.take(&A.pb_min, n);
@@ -613,13 +689,13 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
     ar.take(&A.keys, n);
     ar.take(&perm_in, n);
     ar.take(&keys_sorted, n);
+    char* tmp = nullptr;
+    ar.take(&tmp, std::max<size_t>(sort_bytes, 16));
+    sort_tmp = tmp;
     ar.take(&A.node, n_int);
     ar.take(&A.leaf_parent, n);
     ar.take(&A.box, 2 * (size_t)n);
     ar.take(&A.cbounds, 6);
-    char* tmp = nullptr;
-    ar.take(&tmp, std::max<size_t>(sort_bytes, 16));
-    sort_tmp = tmp;
     if (ploc) {
       ar.take(&cid_a, n);
       ar.take(&cid_b, n);
@@ -627,23 +703,22 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
       ar.take(&nn, n);
       ar.take(&keep, n);
       ar.take(&rank, n);
-      ar.take(&A.leaf_pos, n);
       ar.take(&cells, 2);  // [0] node-id counter, [1] length of the next cluster sequence
       char* tmp2 = nullptr;
       ar.take(&tmp2, std::max<size_t>(scan_bytes, 16));
       scan_tmp = tmp2;
+      ar.take(&A.leaf_pos, n);
     }
   };
   carve(arena);  // sizes only
-  const size_t arena_bytes = arena.used;
-  void* arena_mem = nullptr;
-  ok(pool_alloc(&arena_mem, arena_bytes, st));
-  ok(pool_alloc(reinterpret_cast<void**>(&perm_sorted), (size_t)n * 4, st));  // survives: the primitive order handed back
+  BuildBlock block;
+  ok(block.acquire(arena.used, st));
+  ok(pool_alloc(reinterpret_cast<void**>(&perm_sorted), (size_t)n * 4, st));  // survives unless PLOC re-orders the primitives
   const int grid = 148 * 8;
   uint32_t n_interior_root = 0;
   phase("allocation");
   if (e == cudaSuccess) {
-    arena = Arena{static_cast<char*>(arena_mem), 0};
+    arena = Arena{static_cast<char*>(block.p), 0};
     carve(arena);
     A.perm = perm_in;
     const uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
@@ -719,7 +794,7 @@ int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vert
     }
   }
   phase("positions, node emission");
-  if (arena_mem) cudaFreeAsync(arena_mem, st);
+  block.release(st);
   phase("free");
   if (e != cudaSuccess) {
     if (nodes) cudaFreeAsync(nodes, st);

@@ -49,6 +49,7 @@ void launch_env_density(cudaStream_t st, const DevScene& sc, int mip, int nu, in
 void launch_row_cdf(cudaStream_t st, const float* func, int n, int rows, float* cdf, float* func_int);
 
 // k_bvh.cu
+void release_bvh_build_cache();  // k_bvh.cu: the builder's cached working memory of the current device
 int build_bvh_on_device(cudaStream_t st, uint32_t n, const uint32_t* d_prim_vertex, const float* d_pos, float4** nodes_out, uint32_t* n_nodes_out,
                         uint32_t** perm_out, uint32_t* depth_out);
 void launch_assemble_tris(cudaStream_t st, uint32_t n, const uint32_t* perm, const uint32_t* prim_vertex, const float* pos, const int32_t* prim_mesh,

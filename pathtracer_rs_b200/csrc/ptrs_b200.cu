@@ -966,6 +966,8 @@ int32_t ptrs_trim_memory(void) {
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceSynchronize());
+  ptrs::release_bvh_build_cache();
+  CUDA_TRY(cudaDeviceSynchronize());
   cudaMemPool_t pool;
   CUDA_TRY(pool_of_current_device(&pool));
   CUDA_TRY(cudaMemPoolTrimTo(pool, 0));

@@ -20,10 +20,13 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--out", default="")
     ap.add_argument("--batch", type=int, default=0, help="paths per wavefront batch (0 = library default)")
+    ap.add_argument("--device-bvh", action="store_true", help="tree built by the library (ptrs_scene_create_device_bvh)")
     a = ap.parse_args()
     gpu.set_device(0)
     flat, cam = host.make_scene(a.scene, seed=1, n_tris=a.tris, res=tuple(a.res))
-    scene = gpu.RenderScene(flat)
+    scene = gpu.RenderScene(flat, device_bvh=a.device_bvh)
+    if a.device_bvh:
+        print("device tree: %d nodes, built in %.2f ms" % scene.bvh_info(), end="  ")
     integ = gpu.PathIntegrator(gpu.SamplerBuilder(a.spp), max_depth=a.depth)
     integ.params.paths_per_batch = a.batch
     film = gpu.Film(cam.width, cam.height)

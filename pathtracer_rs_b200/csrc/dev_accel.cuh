@@ -291,6 +291,9 @@ PT_DEV void trace_empty(uint32_t n_items, uint32_t* ticket, Work& work) {
 #ifndef PT_SMEM_STACK
 #define PT_SMEM_STACK 0
 #endif
+#ifndef PT_STACK8
+#define PT_STACK8 0
+#endif
 #ifndef PT_TRACE_BLOCK
 #define PT_TRACE_BLOCK 128
 #endif
@@ -305,18 +308,60 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
   // not depend on it); measured: 12 is best on trees of a few dozen nodes, 20 on trees of 10^5 .. 10^7 nodes.
   const int box_min = (int)sc.box_min;
   const bool pop_twice = sc.pop_twice != 0;
-#if PT_SMEM_STACK
+#if PT_STACK8
+  // 8-byte entries {entry distance, packed node}: half the local-memory footprint of the 1024 stacks per SM, which is what
+  // matters when the tree itself does not fit in L2 and the stacks compete with its nodes for L1.  Packed node word:
+  //   bit 31 = 0              interior: first child slot (even, < 2^30) << 1 | split axis
+  //   bit 31 = 1, bit 30 = 0  leaf: (n_prims - 1) << 26 | first primitive      (n_prims <= 16, primitive < 2^26)
+  //   bit 31 = 1, bit 30 = 1  leaf by reference: the node's slot; (offset, n_prims) are re-read when it is popped
+  uint2 stack[PT_STACK_SIZE];
+  auto st_load = [&](int i, float* t, uint32_t* off, uint32_t* meta) {
+    const uint2 e = stack[i];
+    *t = __uint_as_float(e.x);
+    const uint32_t w = e.y;
+    if (!(w & 0x80000000u)) {
+      *off = (w & ~3u) >> 1;
+      *meta = (w & 3u) << 16;
+    } else if (!(w & 0x40000000u)) {
+      *off = w & 0x03ffffffu;
+      *meta = ((w >> 26) & 15u) + 1u;
+    } else {
+      const float2 om = __ldg(reinterpret_cast<const float2*>(sc.nodes + 2 * (size_t)(w & 0x3fffffffu) + 1) + 1);
+      *off = __float_as_uint(om.x);
+      *meta = __float_as_uint(om.y);
+    }
+  };
+  auto st_store = [&](int i, float t, uint32_t off, uint32_t meta, uint32_t slot) {
+    const uint32_t np = meta & 0xffffu;
+    uint32_t w;
+    if (np == 0u) w = (off << 1) | ((meta >> 16) & 3u);
+    else if (np <= 16u && off < (1u << 26)) w = 0x80000000u | ((np - 1u) << 26) | off;
+    else w = 0xc0000000u | slot;
+    stack[i] = make_uint2(__float_as_uint(t), w);
+  };
+#elif PT_SMEM_STACK
   __shared__ uint4 sm_stack[PT_SMEM_STACK * PT_TRACE_BLOCK];
   uint4 stack[PT_STACK_SIZE - PT_SMEM_STACK];
-  auto st_load = [&](int i) -> uint4 { return i < PT_SMEM_STACK ? sm_stack[i * PT_TRACE_BLOCK + threadIdx.x] : stack[i - PT_SMEM_STACK]; };
-  auto st_store = [&](int i, const uint4& e) {
+  auto st_load = [&](int i, float* t, uint32_t* off, uint32_t* meta) {
+    const uint4 e = i < PT_SMEM_STACK ? sm_stack[i * PT_TRACE_BLOCK + threadIdx.x] : stack[i - PT_SMEM_STACK];
+    *t = __uint_as_float(e.x);
+    *off = e.y;
+    *meta = e.z;
+  };
+  auto st_store = [&](int i, float t, uint32_t off, uint32_t meta, uint32_t) {
+    const uint4 e = make_uint4(__float_as_uint(t), off, meta, 0u);
     if (i < PT_SMEM_STACK) sm_stack[i * PT_TRACE_BLOCK + threadIdx.x] = e;
     else stack[i - PT_SMEM_STACK] = e;
   };
 #else
   uint4 stack[PT_STACK_SIZE];
-  auto st_load = [&](int i) -> uint4 { return stack[i]; };
-  auto st_store = [&](int i, const uint4& e) { stack[i] = e; };
+  auto st_load = [&](int i, float* t, uint32_t* off, uint32_t* meta) {
+    const uint4 e = stack[i];
+    *t = __uint_as_float(e.x);
+    *off = e.y;
+    *meta = e.z;
+  };
+  auto st_store = [&](int i, float t, uint32_t off, uint32_t meta, uint32_t) { stack[i] = make_uint4(__float_as_uint(t), off, meta, 0u); };
 #endif
   int sp_ = 0;
   // node in hand (its box test passed under the t_max current at that time): offset, meta, entry distance
@@ -389,10 +434,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
     auto eager_pop = [&]() {
       if ((rbits & PT_RB_LIVE) && cur_meta == PT_NO_NODE && sp_ > 0) {
         --sp_;
-        const uint4 e = st_load(sp_);
-        cur_t = __uint_as_float(e.x);
-        cur_off = e.y;
-        cur_meta = e.z;
+        st_load(sp_, &cur_t, &cur_off, &cur_meta);
       }
     };
     auto box_step = [&]() {
@@ -404,11 +446,13 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
       // the entry popped ahead was culled: one more pop, tested on the spot, so that the lane still expands a node in this step
       if (live && cur_meta == PT_NO_NODE && sp_ > 0) {
         --sp_;
-        const uint4 e = st_load(sp_);
-        if (__uint_as_float(e.x) < t_max) {
-          cur_t = __uint_as_float(e.x);
-          cur_off = e.y;
-          cur_meta = e.z;
+        float et;
+        uint32_t eo, em;
+        st_load(sp_, &et, &eo, &em);
+        if (et < t_max) {
+          cur_t = et;
+          cur_off = eo;
+          cur_meta = em;
         }
       }
 #endif
@@ -447,7 +491,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
           } else {
             if (af) {
               if (sp_ < PT_STACK_SIZE) {  // always true: ptrs_scene_create refuses trees deeper than the stack
-                st_store(sp_, make_uint4(__float_as_uint(tf), __float_as_uint(fb.z), __float_as_uint(fb.w), 0u));
+                st_store(sp_, tf, __float_as_uint(fb.z), __float_as_uint(fb.w), cur_off + (neg ? 0u : 1u));
                 ++sp_;
               }
             }
@@ -477,11 +521,13 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
       if (can_box) {
         if (cur_meta == PT_NO_NODE) {  // pop one entry; the reference's box test at pop time
           --sp_;
-          const uint4 e = st_load(sp_);
-          if (__uint_as_float(e.x) < t_max) {
-            cur_t = __uint_as_float(e.x);
-            cur_off = e.y;
-            cur_meta = e.z;
+          float et;
+          uint32_t eo, em;
+          st_load(sp_, &et, &eo, &em);
+          if (et < t_max) {
+            cur_t = et;
+            cur_off = eo;
+            cur_meta = em;
           }
           if (pop_twice) {
             // the entry was culled, or it was a leaf that goes straight to the free parking slot: one more pop (at most),
@@ -494,11 +540,11 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
             }
             if (cur_meta == PT_NO_NODE && sp_ > 0) {
               --sp_;
-              const uint4 e2 = st_load(sp_);
-              if (__uint_as_float(e2.x) < t_max) {
-                cur_t = __uint_as_float(e2.x);
-                cur_off = e2.y;
-                cur_meta = e2.z;
+              st_load(sp_, &et, &eo, &em);
+              if (et < t_max) {
+                cur_t = et;
+                cur_off = eo;
+                cur_meta = em;
               }
             }
           }
@@ -542,7 +588,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
             } else {
               if (af) {
                 if (sp_ < PT_STACK_SIZE) {  // always true: ptrs_scene_create refuses trees deeper than the stack
-                  st_store(sp_, make_uint4(__float_as_uint(tf), __float_as_uint(fb.z), __float_as_uint(fb.w), 0u));
+                  st_store(sp_, tf, __float_as_uint(fb.z), __float_as_uint(fb.w), cur_off + (neg ? 0u : 1u));
                   ++sp_;
                 }
               }

@@ -333,6 +333,9 @@ def run_gpu(args):
     w = load_workload(args)
     W, H = w["res"]
     flat, cam = build_scene(host, w)
+    dev_bvh = args.tree == "device"  # whole run over the tree the library builds (ptrs_scene_create_device_bvh); default: the reference-built tree
+    if dev_bvh:
+        w["name"] += " [tree built on the device: ptrs_scene_create_device_bvh]"
     integ = gpu.PathIntegrator(gpu.SamplerBuilder(w["spp"]), max_depth=w["max_depth"])
     shard = sample_shard(rank, n_gpus) if mode == "ranks" else (1, 0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -352,8 +355,8 @@ def run_gpu(args):
         return out
 
     if mode == "threads":
-        multi = gpu.MultiScene(flat, n_gpus)
-        scene = gpu.RenderScene(flat)  # device 0 replica for the counted pass
+        multi = gpu.MultiScene(flat, n_gpus, device_bvh=dev_bvh)
+        scene = gpu.RenderScene(flat, device_bvh=dev_bvh)  # device 0 replica for the counted pass
 
         def step():
             per_dev, ms = multi.render_into(cam, integ.params, None)
@@ -366,7 +369,7 @@ def run_gpu(args):
             scene.set_stats_mode(False)
             return st
     else:
-        scene = gpu.RenderScene(flat)
+        scene = gpu.RenderScene(flat, device_bvh=dev_bvh)
         integ.preprocess(scene)
         film_t = torch.zeros(H, W, 4, dtype=torch.float32, device="cuda")
         film = gpu.Film(W, H, device_ptr=film_t.data_ptr())
@@ -423,13 +426,13 @@ def run_gpu(args):
         barrier()
         t0 = time.perf_counter()
         if mode == "threads":
-            m2 = gpu.MultiScene(flat, n_gpus, device_tables=True)  # ptrs_multi_create: H2D of the flattened scene to every device
+            m2 = gpu.MultiScene(flat, n_gpus, device_bvh=dev_bvh, device_tables=True)  # ptrs_multi_create: H2D of the flattened scene to every device
             t1 = time.perf_counter()
             m2.render_into(cam, integ.params, host_film.ctypes.data)  # render + reduce + D2H of the film
             t2 = t3 = time.perf_counter()
             m2.close()
         else:
-            sc2 = gpu.RenderScene(flat, device_tables=True)  # ptrs_scene_create: H2D of the flattened scene; MIP pyramids / env distribution built on the device
+            sc2 = gpu.RenderScene(flat, device_bvh=dev_bvh, device_tables=True)  # ptrs_scene_create: H2D of the flattened scene; MIP pyramids / env distribution built on the device
             f2 = gpu.Film(W, H)
             t1 = time.perf_counter()
             integ.render(cam, sc2, f2, sample_stride=shard)
@@ -529,7 +532,7 @@ def run_gpu(args):
     # An eighth of the step's samples through both trees, one warm-up and one timed pass each.  The headline above stays on
     # the reference-built tree (what the north star names and what the bit-exact hit parity is defined on).
     dev_tree = None
-    if n_gpus == 1 and mode == "single" and not args.no_device_bvh_render:
+    if n_gpus == 1 and mode == "single" and not args.no_device_bvh_render and not dev_bvh:
         try:
             spp_d = max(1, w["spp"] // 8)
             sc_d = gpu.RenderScene(flat, device_bvh=True)
@@ -609,6 +612,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bvh-microbench", action="store_true")
     ap.add_argument("--no-device-bvh-render", action="store_true")
+    ap.add_argument("--tree", default="reference", choices=["reference", "device"],
+                    help="reference: the host-built SAH tree handed over as LinearBVHNode records (default); device: built by the library")
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override the workload's total samples per pixel")
     args = ap.parse_args()

@@ -200,7 +200,7 @@ class RenderScene:
     """Device copy of a flattened scene (src/pathtracer/mod.rs:84-106)."""
 
     def __init__(self, flat, device_bvh=False, device_tables=False):
-        """device_bvh=True ignores the description's nodes and builds a linear BVH on the GPU (ptrs_scene_create_device_bvh);
+        """device_bvh=True ignores the description's nodes and builds the tree on the GPU (ptrs_scene_create_device_bvh: Morton order + PLOC);
         device_tables=True hands over level 0 of every MIP pyramid only and no env Distribution2D: the library builds them."""
         desc = (flat.desc_device_tables if device_tables else flat.desc) if isinstance(flat, FlatScene) else flat
         h = C.c_void_p()

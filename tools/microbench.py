@@ -29,11 +29,11 @@ def main():
     flat, cam = host.make_scene(a.scene, seed=1, n_tris=a.tris, res=(a.side, a.side))
     scene = gpu.RenderScene(flat, device_bvh=a.device_bvh)
     n_nodes, build_ms = scene.bvh_info()
-    print(f"tris={flat.n_prims} device nodes={n_nodes} host SAH build {flat.bvh_seconds * 1e3:.0f} ms" + (f", device LBVH build {build_ms:.2f} ms" if a.device_bvh else ""))
+    print(f"tris={flat.n_prims} device nodes={n_nodes} host SAH build {flat.bvh_seconds * 1e3:.0f} ms" + (f", device build {build_ms:.2f} ms" if a.device_bvh else ""))
     if a.device_bvh:  # second build: allocations now come from the warmed pool
         scene.close()
         scene = gpu.RenderScene(flat, device_bvh=True)
-        print(f"device LBVH build (warm) {scene.bvh_info()[1]:.2f} ms")
+        print(f"device build (warm) {scene.bvh_info()[1]:.2f} ms")
     bmin, bmax = flat.world_bound()
     if a.all:
         for kind in ("coherent", "incoherent"):

@@ -477,7 +477,7 @@ def run_gpu(args):
     trav_launches = stats["extend_launches"] + stats["connect_launches"]
     achieved = trav_bytes / (trav_ms * 1e-3) / 1e9
     tr = traffic_record(args.workload)
-    roofline = {"bound": "hbm", "kernel": "extend_kernel<false> + connect_kernel<false> (closest-hit / any-hit BVH traversal, one engine: dev_accel.cuh trace_fast)",
+    roofline = {"bound": "hbm", "kernel": "extend_kernel<false, DIST> + connect_kernel<false, DIST> (closest-hit / any-hit BVH traversal, one engine: dev_accel.cuh trace_fast; DIST = false on the reference-built tree)",
                 "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "traffic": tr.get("dram_bytes_per_launch") if tr else None, "traffic_source": tr.get("source") if tr else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_step": trav_bytes, "algorithmic_bytes_per_launch": trav_bytes / max(1, trav_launches),

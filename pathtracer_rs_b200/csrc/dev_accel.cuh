@@ -297,7 +297,10 @@ PT_DEV void trace_empty(uint32_t n_items, uint32_t* ticket, Work& work) {
 #ifndef PT_TRACE_BLOCK
 #define PT_TRACE_BLOCK 128
 #endif
-template <class Work>
+// DIST: of two entered children the one the ray enters first is visited first (trees the library built itself) instead of
+// dir_is_neg[axis] (the reference's order on the reference's tree).  A template parameter, so that the reference path's
+// code is untouched.
+template <bool DIST, class Work>
 PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, Work& work) {
   if (sc.n_nodes == 0) {
     trace_empty(n_items, ticket, work);
@@ -308,6 +311,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
   // not depend on it); measured: 12 is best on trees of a few dozen nodes, 20 on trees of 10^5 .. 10^7 nodes.
   const int box_min = (int)sc.box_min;
   const bool pop_twice = sc.pop_twice != 0;
+  constexpr bool dist_order = DIST;
 #if PT_STACK8
   // 8-byte entries {entry distance, packed node}: half the local-memory footprint of the 1024 stacks per SM, which is what
   // matters when the tree itself does not fit in L2 and the stacks compete with its nodes for L1.  Packed node word:
@@ -467,10 +471,10 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
           const NodeLoad L = load_node(sc.nodes, cur_off);
           const NodeLoad R = load_node(sc.nodes, cur_off + 1);
           const bool nx = rbits & PT_RB_NX, ny = rbits & PT_RB_NY, nz = rbits & PT_RB_NZ;
-          const bool neg = ((rbits >> ((cur_meta >> 16) & 3u)) & 1u) != 0;  // dir_is_neg[axis]
           float tl, tr;
           const bool gl = box_geom(L, o, inv_dir, nx, ny, nz, &tl);
           const bool gr = box_geom(R, o, inv_dir, nx, ny, nz, &tr);
+          const bool neg = dist_order ? (tr < tl) : (((rbits >> ((cur_meta >> 16) & 3u)) & 1u) != 0);  // dir_is_neg[axis], or nearer child first
           // near child first (accelerator.rs:393-404)
           const bool gn = neg ? gr : gl, gf = neg ? gl : gr;
           const float tn = neg ? tr : tl, tf = neg ? tl : tr;
@@ -560,10 +564,12 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
             const NodeLoad L = load_node(sc.nodes, cur_off);
             const NodeLoad R = load_node(sc.nodes, cur_off + 1);
             const bool nx = rbits & PT_RB_NX, ny = rbits & PT_RB_NY, nz = rbits & PT_RB_NZ;
-            const bool neg = ((rbits >> ((cur_meta >> 16) & 3u)) & 1u) != 0;  // dir_is_neg[axis]
             float tl, tr;
             const bool gl = box_geom(L, o, inv_dir, nx, ny, nz, &tl);
             const bool gr = box_geom(R, o, inv_dir, nx, ny, nz, &tr);
+            // which child first: dir_is_neg[axis] on a reference-built tree (the reference's order, accelerator.rs:393-404);
+            // on a tree the library built itself the child the ray enters first
+            const bool neg = dist_order ? (tr < tl) : (((rbits >> ((cur_meta >> 16) & 3u)) & 1u) != 0);
             // near child first (accelerator.rs:393-404)
             const bool gn = neg ? gr : gl, gf = neg ? gl : gr;
             const float tn = neg ? tr : tl, tf = neg ? tl : tr;
@@ -808,10 +814,10 @@ PT_DEV void trace_counted(const DevScene& sc, uint32_t n_items, uint32_t* ticket
         const NodeLoad L = load_node(sc.nodes, cur_off);
         const NodeLoad R = load_node(sc.nodes, cur_off + 1);
         const uint32_t axis = (cur_meta >> 16) & 0xffu;
-        const bool neg = axis == 0 ? nx : (axis == 1 ? ny : nz);
         float tl, tr;
         const bool gl = box_geom(L, o, inv_dir, nx, ny, nz, &tl);
         const bool gr = box_geom(R, o, inv_dir, nx, ny, nz, &tr);
+        const bool neg = sc.dist_order ? (tr < tl) : (axis == 0 ? nx : (axis == 1 ? ny : nz));
         const bool gn = neg ? gr : gl, gf = neg ? gl : gr;
         const float tn = neg ? tr : tl, tf = neg ? tl : tr;
         const float4 nb = neg ? R.b : L.b, fb = neg ? L.b : R.b;
@@ -864,10 +870,10 @@ PT_DEV void trace_counted(const DevScene& sc, uint32_t n_items, uint32_t* ticket
   }
 }
 
-template <bool COUNT, class Work>
+template <bool COUNT, bool DIST, class Work>
 PT_DEV void trace_stream(const DevScene& sc, uint32_t n_items, uint32_t* ticket, Work& work, uint32_t* c_nodes, uint32_t* c_tris) {
-  if (COUNT) trace_counted(sc, n_items, ticket, work, c_nodes, c_tris);
-  else trace_fast(sc, n_items, ticket, work);
+  if (COUNT) trace_counted(sc, n_items, ticket, work, c_nodes, c_tris);  // (reads sc.dist_order at run time)
+  else trace_fast<DIST>(sc, n_items, ticket, work);
 }
 
 }  // namespace ptrs

@@ -53,6 +53,7 @@ struct DevScene {
   uint32_t n_nodes, n_prims, n_lights, n_infinite_lights;
   uint32_t box_min;    // traversal scheduling threshold, see trace_fast
   uint32_t pop_twice;  // traversal scheduling: a second pop when the first one leaves the lane without a node (trees beyond L1 size)
+  uint32_t dist_order;  // library-built tree: of two entered children the one with the smaller entry distance is visited first
   // 1 when some material parameter or normal map is an image texture: the only consumer of the camera-ray
   // differentials (MIPMap::lookup's filter width, texture.rs:431-445).  Without one, shade skips
   // compute_differentials — every value it would produce is unread.

@@ -50,12 +50,12 @@ struct ExtendWork {
   }
 };
 
-template <bool COUNT>
+template <bool COUNT, bool DIST>
 __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) extend_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ PathArrays P, const int* __restrict__ q_ext, int* __restrict__ q_class,
                                                       uint32_t cap, RoundCounters* ctr, GlobalCounters* g) {
   uint32_t c_nodes = 0, c_tris = 0;
   ExtendWork w{sc, P, q_ext, q_class, cap, ctr, 0};
-  trace_stream<COUNT>(sc, ctr->n_ext, &ctr->t_ext, w, &c_nodes, &c_tris);
+  trace_stream<COUNT, DIST>(sc, ctr->n_ext, &ctr->t_ext, w, &c_nodes, &c_tris);
   if (COUNT) {
     warp_sum_add(c_nodes, &g->nodes_tested);
     warp_sum_add(c_tris, &g->tris_tested);
@@ -99,11 +99,11 @@ struct ConnectWork {
   }
 };
 
-template <bool COUNT>
+template <bool COUNT, bool DIST>
 __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) connect_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ PathArrays P, RoundCounters* ctr, GlobalCounters* g) {
   uint32_t c_nodes = 0, c_tris = 0;
   ConnectWork w{P, 0u, 0u, 0u};
-  trace_stream<COUNT>(sc, ctr->n_ray, &ctr->t_ray, w, &c_nodes, &c_tris);
+  trace_stream<COUNT, DIST>(sc, ctr->n_ray, &ctr->t_ray, w, &c_nodes, &c_tris);
   warp_sum_add(w.n_shadow, &g->shadow_rays);
   warp_sum_add(w.n_mis, &g->mis_rays);
   if (COUNT) {
@@ -143,12 +143,12 @@ struct IntersectWork {
   }
 };
 
-template <bool ANY_HIT, bool COUNT>
+template <bool ANY_HIT, bool COUNT, bool DIST>
 __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) intersect_kernel(const __grid_constant__ DevScene sc, const PtrsRay* __restrict__ rays, uint32_t n, PtrsHit* __restrict__ hits,
                                                          uint8_t* __restrict__ occluded, uint32_t* ticket, GlobalCounters* g, const uint32_t* __restrict__ prim_map) {
   uint32_t c_nodes = 0, c_tris = 0;
   IntersectWork w{rays, hits, occluded, ANY_HIT, prim_map};
-  trace_stream<COUNT>(sc, n, ticket, w, &c_nodes, &c_tris);
+  trace_stream<COUNT, DIST>(sc, n, ticket, w, &c_nodes, &c_tris);
   if (COUNT) {
     warp_sum_add(c_nodes, &g->nodes_tested);
     warp_sum_add(c_tris, &g->tris_tested);
@@ -156,21 +156,31 @@ __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) intersect_kernel(con
 }
 
 // ---- launchers -----------------------------------------------------------------------------------------
+// <.., DIST>: front-to-back child order on trees the library built (DevScene::dist_order); the counted variants read the flag at
+// run time, so they exist once
 void launch_extend(cudaStream_t st, int sm, bool count, const DevScene& sc, const PathArrays& P, const int* q_ext, int* q_class, uint32_t cap,
                    RoundCounters* ctr, GlobalCounters* g) {
-  if (count) extend_kernel<true><<<PT_GRID(extend_kernel<true>, 128, sm), 128, 0, st>>>(sc, P, q_ext, q_class, cap, ctr, g);
-  else extend_kernel<false><<<PT_GRID(extend_kernel<false>, 128, sm), 128, 0, st>>>(sc, P, q_ext, q_class, cap, ctr, g);
+  if (count) extend_kernel<true, false><<<PT_GRID((extend_kernel<true, false>), 128, sm), 128, 0, st>>>(sc, P, q_ext, q_class, cap, ctr, g);
+  else if (sc.dist_order) extend_kernel<false, true><<<PT_GRID((extend_kernel<false, true>), 128, sm), 128, 0, st>>>(sc, P, q_ext, q_class, cap, ctr, g);
+  else extend_kernel<false, false><<<PT_GRID((extend_kernel<false, false>), 128, sm), 128, 0, st>>>(sc, P, q_ext, q_class, cap, ctr, g);
 }
 void launch_connect(cudaStream_t st, int sm, bool count, const DevScene& sc, const PathArrays& P, RoundCounters* ctr, GlobalCounters* g) {
-  if (count) connect_kernel<true><<<PT_GRID(connect_kernel<true>, 128, sm), 128, 0, st>>>(sc, P, ctr, g);
-  else connect_kernel<false><<<PT_GRID(connect_kernel<false>, 128, sm), 128, 0, st>>>(sc, P, ctr, g);
+  if (count) connect_kernel<true, false><<<PT_GRID((connect_kernel<true, false>), 128, sm), 128, 0, st>>>(sc, P, ctr, g);
+  else if (sc.dist_order) connect_kernel<false, true><<<PT_GRID((connect_kernel<false, true>), 128, sm), 128, 0, st>>>(sc, P, ctr, g);
+  else connect_kernel<false, false><<<PT_GRID((connect_kernel<false, false>), 128, sm), 128, 0, st>>>(sc, P, ctr, g);
 }
 void launch_intersect(cudaStream_t st, int sm, bool any_hit, bool count, const DevScene& sc, const PtrsRay* rays, uint32_t n, PtrsHit* hits,
                       uint8_t* occluded, uint32_t* ticket, GlobalCounters* g, const uint32_t* prim_map) {
-  if (!any_hit && !count) intersect_kernel<false, false><<<PT_GRID((intersect_kernel<false, false>), 128, sm), 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map);
-  else if (!any_hit) intersect_kernel<false, true><<<PT_GRID((intersect_kernel<false, true>), 128, sm), 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map);
-  else if (!count) intersect_kernel<true, false><<<PT_GRID((intersect_kernel<true, false>), 128, sm), 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map);
-  else intersect_kernel<true, true><<<PT_GRID((intersect_kernel<true, true>), 128, sm), 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map);
+#define PT_LAUNCH_INTERSECT(A, C, D) \
+  intersect_kernel<A, C, D><<<PT_GRID((intersect_kernel<A, C, D>), 128, sm), 128, 0, st>>>(sc, rays, n, hits, occluded, ticket, g, prim_map)
+  const bool dist = sc.dist_order != 0;
+  if (!any_hit && count) PT_LAUNCH_INTERSECT(false, true, false);
+  else if (any_hit && count) PT_LAUNCH_INTERSECT(true, true, false);
+  else if (!any_hit && dist) PT_LAUNCH_INTERSECT(false, false, true);
+  else if (!any_hit) PT_LAUNCH_INTERSECT(false, false, false);
+  else if (dist) PT_LAUNCH_INTERSECT(true, false, true);
+  else PT_LAUNCH_INTERSECT(true, false, false);
+#undef PT_LAUNCH_INTERSECT
 }
 
 }  // namespace ptrs

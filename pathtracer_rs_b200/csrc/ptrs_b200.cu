@@ -880,6 +880,9 @@ static int32_t scene_create_impl(const PtrsSceneDesc* d, bool device_bvh, PtrsSc
   v.box_min = n_dev_nodes <= 4096u ? 12u : 20u;
   v.pop_twice = n_dev_nodes > 4096u ? 1u : 0u;
   if (const char* e = std::getenv("PTRS_POP_TWICE")) v.pop_twice = std::atoi(e) != 0;  // tuning only
+  // a reference-built tree is walked in the reference's order (dir_is_neg[axis]); a tree built here front to back
+  v.dist_order = device_bvh ? 1u : 0u;
+  if (const char* e = std::getenv("PTRS_DIST_ORDER")) v.dist_order = device_bvh && std::atoi(e) != 0;  // tuning only
   if (const char* e = std::getenv("PTRS_BOX_MIN")) v.box_min = (uint32_t)std::max(1, std::min(32, std::atoi(e)));  // tuning only
   v.uses_differentials = 0;
   for (uint32_t i = 0; i < d->n_materials; ++i) {

@@ -383,6 +383,43 @@ def test_device_bvh_duplicate_and_gridded_primitives(gpu, host, monkeypatch, bui
     dev.close()
 
 
+@pytest.mark.parametrize("builder", ["ploc", "lbvh"])
+def test_device_bvh_random_soups_of_every_small_size(gpu, host, monkeypatch, builder):
+    """Triangle soups of 2 .. 40, 257 and 1000 random triangles: every cluster count PLOC's rounds can pass through near the
+    root, odd sequence lengths, windows wider than the sequence.  The library-built tree must be a valid tree over a permutation
+    of the primitives and give the reference-built tree's closest hits."""
+    monkeypatch.setenv("PTRS_BVH_BUILDER", builder)
+    rng = np.random.default_rng(11)
+    for n_tri in list(range(2, 41)) + [257, 1000]:
+        b = host.SceneBuilder()
+        m = b.material(host.MAT_MATTE, [b.constant_texture([0.5, 0.5, 0.5])])
+        c = rng.uniform(-1, 1, (n_tri, 1, 3))
+        verts = (c + rng.uniform(-0.3, 0.3, (n_tri, 3, 3))).reshape(-1, 3).astype(np.float32)
+        b.mesh(verts, np.arange(3 * n_tri, dtype=np.uint32).reshape(-1, 3), material=m)
+        flat = b.finalize()
+        ref, dev = gpu.RenderScene(flat), gpu.RenderScene(flat, device_bvh=True)
+        nodes, order = dev.download_nodes()
+        assert np.array_equal(np.sort(order), np.arange(n_tri, dtype=np.uint32)), n_tri
+        covered = np.zeros(n_tri, dtype=np.int32)
+        for off, cnt in _walk_device_tree(nodes):
+            assert 1 <= cnt <= 4
+            covered[off: off + cnt] += 1
+        assert np.all(covered == 1), n_tri
+        rays = np.zeros(2048, dtype=host.RAY_DTYPE)
+        rays["o"] = rng.uniform(-2, 2, (2048, 3)).astype(np.float32)
+        d = rng.normal(size=(2048, 3))
+        rays["d"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        rays["t_max"] = np.inf
+        a, c2 = ref.intersect(rays), dev.intersect(rays)
+        assert np.mean((a["prim"] >= 0) != (c2["prim"] >= 0)) < 1e-3, n_tri
+        hit = (a["prim"] >= 0) & (c2["prim"] >= 0)
+        assert np.allclose(a["t"][hit], c2["t"][hit], rtol=1e-6, atol=0), n_tri
+        assert (a["prim"] == c2["prim"]).mean() > 0.995, n_tri
+        assert np.mean(ref.intersect_p(rays) != dev.intersect_p(rays)) < 1e-3, n_tri  # (grazing rays may differ)
+        ref.close()
+        dev.close()
+
+
 def test_imported_gltf_scene_renders_like_the_oracle(gpu, host, oracle, tmp_path):
     """A glTF document with textured Disney / glass / mirror materials, an alpha mask, a normal map, emissive
     triangles and punctual lights, imported by host/importer_gltf.cpp, through both integrators."""

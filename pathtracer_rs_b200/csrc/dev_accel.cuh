@@ -351,6 +351,9 @@ PT_DEV void trace_empty(uint32_t n_items, uint32_t* ticket, Work& work) {
 #ifndef PT_STACK8
 #define PT_STACK8 0
 #endif
+#ifndef PT_PUSH_PREFETCH
+#define PT_PUSH_PREFETCH 0
+#endif
 
 #ifndef PT_TRACE_BLOCK
 #define PT_TRACE_BLOCK 128
@@ -659,6 +662,19 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
                 if (sp_ < PT_STACK_SIZE) {  // always true: ptrs_scene_create refuses trees deeper than the stack
                   st_store(sp_, tf, __float_as_uint(fb.z), __float_as_uint(fb.w), cur_off + (neg ? 0u : 1u));
                   ++sp_;
+#if PT_PUSH_PREFETCH
+                  // the pushed child's own children (or its first triangle): requested now, so that the pop finds them in
+                  // L1 / L2 instead of starting the round trip then
+                  {
+                    const uint32_t fo = __float_as_uint(fb.z);
+                    const void* pf = (__float_as_uint(fb.w) & 0xffffu) ? (const void*)(sc.tri_verts + 3 * (size_t)fo) : (const void*)(sc.nodes + 2 * (size_t)fo);
+#if PT_PUSH_PREFETCH == 2
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+#else
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+#endif
+                  }
+#endif
                 }
               }
               if (an) {

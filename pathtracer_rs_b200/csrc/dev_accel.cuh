@@ -245,7 +245,11 @@ PT_DEV void box_geom_pair(const NodeLoad& a, const NodeLoad& b, V3 o, V3 inv_dir
 }
 
 #define PT_STACK_SIZE 64
-#define PT_NO_NODE 0xffffffffu
+// "no node in hand".  A node's meta word is n_prims | axis << 16 (bits 18..31 clear), so with this value one masked test
+// tells the three cases apart: leaf = low 16 bits non-zero, interior = (meta & 0x8000ffff) == 0, none = bit 31.
+#define PT_NO_NODE 0x80000000u
+#define PT_IS_LEAF(m) (((m) & 0xffffu) != 0u)
+#define PT_IS_INTERIOR(m) (((m) & 0x8000ffffu) == 0u)
 
 // ------------------------------------------------------------------------------------------------------
 // Device node order.  ptrs_scene_create() keeps the reference's 32-byte LinearBVHNode records but stores
@@ -579,10 +583,11 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
       eager_pop();
     };
 #else
+    // (a lane without a ray has no node in hand, an empty stack and no parked leaf, so none of the tests below asks for
+    // PT_RB_LIVE on top)
     auto box_step = [&]() {
-      const bool live = (rbits & PT_RB_LIVE) != 0;
-      const bool cur_leaf = cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0;
-      const bool can_box = live && ((cur_meta != PT_NO_NODE && !cur_leaf) || (cur_meta == PT_NO_NODE && sp_ > 0) || (cur_leaf && pl_cnt == 0));
+      const bool cur_leaf = PT_IS_LEAF(cur_meta);
+      const bool can_box = PT_IS_INTERIOR(cur_meta) || (cur_meta == PT_NO_NODE && sp_ > 0) || (cur_leaf && pl_cnt == 0);
       if (can_box) {
         if (cur_meta == PT_NO_NODE) {  // pop one entry; the reference's box test at pop time
           --sp_;
@@ -598,7 +603,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
             // the entry was culled, or it was a leaf that goes straight to the free parking slot: one more pop (at most),
             // so that the lane still has a node to expand in this iteration.  Pays on trees that do not fit in L1
             // (scheduling only; DevScene::pop_twice)
-            if (cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0u && pl_cnt == 0u) {
+            if (PT_IS_LEAF(cur_meta) && pl_cnt == 0u) {
               pl_off = cur_off;
               pl_cnt = cur_meta & 0xffffu;
               cur_meta = PT_NO_NODE;
@@ -686,7 +691,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
               }
             }
             // the node now in hand is a leaf and the parking slot is free: park it here instead of in the next iteration
-            if (cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0u && pl_cnt == 0u) {
+            if (PT_IS_LEAF(cur_meta) && pl_cnt == 0u) {
               pl_off = cur_off;
               pl_cnt = cur_meta & 0xffffu;
               cur_meta = PT_NO_NODE;
@@ -698,11 +703,11 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
 #endif
     for (;;) {
       const bool live = (rbits & PT_RB_LIVE) != 0;
-      const bool cur_leaf = cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0;
+      const bool cur_leaf = PT_IS_LEAF(cur_meta);
 #if PT_EAGER_POP
       const bool can_box = live && cur_meta != PT_NO_NODE && (!cur_leaf || pl_cnt == 0);  // no node in hand => empty stack
 #else
-      const bool can_box = live && ((cur_meta != PT_NO_NODE && !cur_leaf) || (cur_meta == PT_NO_NODE && sp_ > 0) || (cur_leaf && pl_cnt == 0));
+      const bool can_box = PT_IS_INTERIOR(cur_meta) || (cur_meta == PT_NO_NODE && sp_ > 0) || (cur_leaf && pl_cnt == 0);
 #endif
       const uint32_t bmask = __ballot_sync(FULL, can_box);
       if (bmask == 0) break;
@@ -714,8 +719,8 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
 
     // ---- triangle phase: parked leaves, first in first out -----------------------------------------------
     auto tri_step = [&]() {
-      const bool live = (rbits & PT_RB_LIVE) != 0;
 #if PT_EAGER_POP
+      const bool live = (rbits & PT_RB_LIVE) != 0;
       if (live && pl_cnt == 0 && cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0) {  // second leaf moves up, if it still qualifies
         if (cur_t < t_max) {
           pl_off = cur_off;
@@ -724,13 +729,13 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
         cur_meta = PT_NO_NODE;
       }
 #else
-      if (live && pl_cnt == 0 && cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0) {  // second leaf moves up
+      if (pl_cnt == 0 && PT_IS_LEAF(cur_meta)) {  // second leaf moves up
         pl_off = cur_off;
         pl_cnt = cur_meta & 0xffffu;
         cur_meta = PT_NO_NODE;
       }
 #endif
-      if (live && pl_cnt != 0) {
+      if (pl_cnt != 0) {
         const uint32_t prim = pl_off;
         const float4 v0 = __ldg(sc.tri_verts + 3 * (size_t)prim);
         const float4 v1 = __ldg(sc.tri_verts + 3 * (size_t)prim + 1);
@@ -767,8 +772,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
 #endif
     };
     for (;;) {
-      const bool live = (rbits & PT_RB_LIVE) != 0;
-      const bool has = live && (pl_cnt != 0 || (cur_meta != PT_NO_NODE && (cur_meta & 0xffffu) != 0));
+      const bool has = pl_cnt != 0 || PT_IS_LEAF(cur_meta);
       if (__ballot_sync(FULL, has) == 0) break;
 #pragma unroll
       for (int rep = 0; rep < PT_TRI_STEPS; ++rep) tri_step();

@@ -537,6 +537,9 @@ __global__ void __launch_bounds__(256) pair_layout_kernel(const float4* __restri
   auto place = [&](uint32_t j, uint32_t slot) {
     const float4 a = raw[2 * (size_t)j];
     float4 b = raw[2 * (size_t)j + 1];
+    // n_prims (16 bits) and axis (0..2) only: LinearBVHNode's fourth byte is padding whose content is the caller's, and the
+    // traversal tells "no node" from a node by bit 31 of this word (PT_NO_NODE, dev_accel.cuh)
+    b.w = __uint_as_float(__float_as_uint(b.w) & 0x0003ffffu);
     if ((__float_as_uint(b.w) & 0xffffu) == 0) b.z = __uint_as_float(2u * (rank[j] + 1u));  // interior: where ITS children sit
     out[2 * (size_t)slot] = a;
     out[2 * (size_t)slot + 1] = b;

@@ -358,6 +358,16 @@ PT_DEV void trace_empty(uint32_t n_items, uint32_t* ticket, Work& work) {
 #ifndef PT_PUSH_PREFETCH
 #define PT_PUSH_PREFETCH 0
 #endif
+// PT_PARK_PREFETCH_ON: when a leaf is parked its first triangle is requested into L1 — unlike a pushed node a parked leaf is
+// always processed, and until then the lane keeps taking box steps
+#ifndef PT_PARK_PREFETCH_ON
+#define PT_PARK_PREFETCH_ON 0
+#endif
+#if PT_PARK_PREFETCH_ON
+#define PT_PARK_PREFETCH(prim) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.tri_verts + 3 * (size_t)(prim)))
+#else
+#define PT_PARK_PREFETCH(prim) ((void)0)
+#endif
 
 #ifndef PT_TRACE_BLOCK
 #define PT_TRACE_BLOCK 128
@@ -605,6 +615,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
             // (scheduling only; DevScene::pop_twice)
             if (PT_IS_LEAF(cur_meta) && pl_cnt == 0u) {
               pl_off = cur_off;
+              PT_PARK_PREFETCH(cur_off);
               pl_cnt = cur_meta & 0xffffu;
               cur_meta = PT_NO_NODE;
             }
@@ -623,6 +634,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
           if ((cur_meta & 0xffffu) != 0) {
             if (pl_cnt == 0) {  // park the leaf, keep descending
               pl_off = cur_off;
+              PT_PARK_PREFETCH(cur_off);
               pl_cnt = cur_meta & 0xffffu;
               cur_meta = PT_NO_NODE;
             }
@@ -693,6 +705,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
             // the node now in hand is a leaf and the parking slot is free: park it here instead of in the next iteration
             if (PT_IS_LEAF(cur_meta) && pl_cnt == 0u) {
               pl_off = cur_off;
+              PT_PARK_PREFETCH(cur_off);
               pl_cnt = cur_meta & 0xffffu;
               cur_meta = PT_NO_NODE;
             }

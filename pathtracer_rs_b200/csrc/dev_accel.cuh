@@ -645,7 +645,7 @@ PT_DEV void trace_fast(const DevScene& sc, uint32_t n_items, uint32_t* ticket, W
             // which child first: dir_is_neg[axis] on a reference-built tree (the reference's order, accelerator.rs:393-404) —
             // known before the fetch, so the two records are loaded as (near, far) and nothing is swapped afterwards; on a
             // tree the library built itself the child the ray enters first
-            bool neg = ((rbits >> ((cur_meta >> 16) & 3u)) & 1u) != 0;
+            bool neg = ((rbits >> (cur_meta >> 16)) & 1u) != 0;  // (an interior node's meta word is axis << 16, nothing else)
             const uint32_t first = dist_order ? 0u : (neg ? 1u : 0u);
             NodeLoad A, B;
             load_node_pair(sc.nodes, cur_off + first, cur_off + (first ^ 1u), &A, &B);

@@ -177,6 +177,9 @@ PT_DEV float fmin3_nn(float a, float b, float c) {
 #ifndef PT_PAIR_LOAD128
 #define PT_PAIR_LOAD128 1
 #endif
+#ifndef PT_NODE_EVICT_LAST
+#define PT_NODE_EVICT_LAST 0
+#endif
 PT_DEV void load_node_pair(const float4* __restrict__ nodes, uint32_t ia, uint32_t ib, NodeLoad* a, NodeLoad* b) {
 #if PT_PAIR_LOAD128
   // four 128-bit loads, the first half of either record first: with 64 registers per thread the allocator keeps three of
@@ -185,10 +188,23 @@ PT_DEV void load_node_pair(const float4* __restrict__ nodes, uint32_t ia, uint32
   // registers the first record's slab test is still reading): two DRAM round trips per step on trees beyond L2 size.
   const float4* pa = nodes + 2 * (size_t)ia;
   const float4* pb = nodes + 2 * (size_t)ib;
+#if PT_NODE_EVICT_LAST
+  // node lines are asked to stay: the second half of a record may be read a few dozen instructions after the first
+  auto ld = [](const float4* p) {
+    float4 v;
+    asm("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+  };
+  a->a = ld(pa);
+  b->a = ld(pb);
+  a->b = ld(pa + 1);
+  b->b = ld(pb + 1);
+#else
   a->a = __ldg(pa);
   b->a = __ldg(pb);
   a->b = __ldg(pa + 1);
   b->b = __ldg(pb + 1);
+#endif
 #else
   *a = load_node(nodes, ia);
   *b = load_node(nodes, ib);
